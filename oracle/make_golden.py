@@ -1,0 +1,191 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference here (build container).
+
+TEST INFRASTRUCTURE ONLY.  Run:  python oracle/make_golden.py
+It imports /root/reference/Uformer_ProbSparse/My_model_1.py through oracle/ref_shim.py,
+runs LeWinTransformerBlock / Uformer forward (+ backward) on CPU in fp32 with fixed seeds,
+records the exact ``index_sample`` draws (attn.py:91), the selected ``M_top`` (attn.py:122)
+and DropPath masks, cross-checks the numpy oracle against the reference, and writes small
+fixtures.  The GPU box has no reference tree; it only reads the committed fixtures.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import lewin_oracle as O          # noqa: E402
+from oracle import param_fill, ref_shim       # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class Recorder:
+    """Records torch.randint draws, ProbAttention top-u indices and DropPath masks."""
+
+    def __init__(self, ref_mod):
+        import ProbSparse.attn as attn_mod
+        self.attn_mod = attn_mod
+        self.idx, self.top, self.drop = [], [], []
+        self._randint = torch.randint
+        self._prob_qk = attn_mod.ProbAttention._prob_QK
+
+    def __enter__(self):
+        rec = self
+
+        def randint(*a, **k):
+            t = rec._randint(*a, **k)
+            rec.idx.append(t.clone())
+            return t
+
+        def prob_qk(self_, Q, K, sample_k, n_top):
+            qk, top = rec._prob_qk(self_, Q, K, sample_k, n_top)
+            rec.top.append(top.clone())
+            return qk, top
+
+        torch.randint = randint
+        self.attn_mod.ProbAttention._prob_QK = prob_qk
+        return self
+
+    def __exit__(self, *exc):
+        torch.randint = self._randint
+        self.attn_mod.ProbAttention._prob_QK = self._prob_qk
+
+
+def _hook_droppath(block, store):
+    from timm.models.layers import DropPath
+    if not isinstance(block.drop_path, DropPath):
+        return
+    orig = block.drop_path.forward
+
+    def fwd(x):
+        if block.drop_path.drop_prob == 0.0 or not block.drop_path.training:
+            return x
+        keep = 1.0 - block.drop_path.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep).div_(keep)
+        store.append(mask.reshape(-1).clone())
+        return x * mask
+
+    block.drop_path.forward = fwd
+    return orig
+
+
+BLOCK_CASES = [
+    # name, C, nH, map, B, shift, input_mask, drop_path, train
+    ("block_c32_h1_s0", 32, 1, 16, 2, 0, False, 0.0, False),
+    ("block_c32_h1_s4", 32, 1, 16, 2, 4, False, 0.0, False),
+    ("block_c64_h2_s4", 64, 2, 16, 2, 4, False, 0.0, False),
+    ("block_c64_h2_s4_inmask", 64, 2, 24, 1, 4, True, 0.0, False),
+    ("block_c64_h2_s4_droppath", 64, 2, 16, 4, 4, False, 0.4, True),
+    ("block_c128_h4_s0", 128, 4, 8, 3, 0, False, 0.0, False),
+]
+
+
+def make_block_case(ref, name, C, nH, hw, B, shift, use_inmask, drop_path, train, seed):
+    torch.manual_seed(seed)
+    blk = ref.LeWinTransformerBlock(dim=C, input_resolution=(128, 128), num_heads=nH, win_size=8,
+                                    shift_size=shift, token_mlp="leff", drop_path=drop_path)
+    param_fill.fill_module(blk, seed)
+    blk.train(train)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, hw * hw, C, generator=g, requires_grad=True)
+    dout = torch.randn(B, hw * hw, C, generator=g)
+    inmask = None
+    if use_inmask:
+        inmask = torch.zeros(1, 1, hw * 2, hw * 2)
+        inmask[:, :, -10:, :] = 1.0
+        inmask[:, :, :, -6:] = 1.0
+    drops = []
+    _hook_droppath(blk, drops)
+    torch.manual_seed(seed + 2)
+    with Recorder(ref) as rec:
+        out = blk(x, inmask)
+    out.backward(dout)
+    assert len(rec.idx) == 1 and len(rec.top) == 1
+    idx = rec.idx[0].numpy()
+    top = np.sort(rec.top[0].numpy(), -1)
+    drop_scale = np.stack([d.numpy() for d in drops]) if drops else None
+
+    p = {k: v.detach().numpy() for k, v in blk.state_dict().items()}
+    grads = {k: v.grad.detach().numpy() for k, v in blk.named_parameters() if v.grad is not None}
+    dead = sorted(k for k, v in blk.named_parameters() if v.grad is None)
+    assert sorted(grads) == sorted(O.GRAD_KEYS), (sorted(grads), dead)
+
+    # ---- cross-check the numpy oracle against the reference (fp32 and fp64)
+    xn, don = x.detach().numpy(), dout.numpy()
+    inm = None if inmask is None else inmask.numpy()
+    report = {}
+    for dt, tol in ((np.float32, 2e-4), (np.float64, 2e-4)):
+        pp = O.as_dtype(p, dt)
+        o, aux = O.lewin_block(xn.astype(dt), pp, shift, idx, inm, True, drop_scale, return_aux=True)
+        same_top = np.array_equal(aux["top"], top)
+        if not same_top:   # near-tie rows: evaluate the oracle with the reference's selection
+            nbad = int((aux["top"] != top).any(-1).sum())
+            print(f"  [{name}/{dt.__name__}] {nbad} (window,head) rows differ in top-u (near ties); forcing reference selection")
+            o = O.lewin_block(xn.astype(dt), pp, shift, idx, inm, True, drop_scale, top=top)
+        err = np.abs(o - out.detach().numpy()).max()
+        dx, go = O.lewin_block_bwd(don.astype(dt), xn.astype(dt), pp, shift, idx, inm, True, drop_scale, top=top)
+        # key_projection.bias has a mathematically zero gradient (softmax shift invariance): floor the scale
+        gscale = max(np.abs(grads[k]).max() for k in O.GRAD_KEYS)
+        gerr = max(np.abs(go[k] - grads[k]).max() / max(np.abs(grads[k]).max(), 1e-4 * gscale) for k in O.GRAD_KEYS)
+        dxerr = np.abs(dx - x.grad.numpy()).max() / np.abs(x.grad.numpy()).max()
+        report[dt.__name__] = (err, dxerr, gerr, same_top)
+        assert err < tol * max(1.0, np.abs(out.detach().numpy()).max()), (name, dt, err)
+        assert dxerr < 1e-3 and gerr < 1e-3, (name, dt, dxerr, gerr)
+    print(f"{name}: " + "  ".join(f"{k}: out {v[0]:.2e} dx {v[1]:.2e} dparam {v[2]:.2e} top_equal={v[3]}" for k, v in report.items()))
+
+    save = dict(x=xn, dout=don, out=out.detach().numpy(), dx=x.grad.numpy(), idx=idx.astype(np.int64),
+                top=top.astype(np.int64), shift=np.int64(shift), nH=np.int64(nH), hw=np.int64(hw),
+                seed=np.int64(seed))
+    if inm is not None:
+        save["input_mask"] = inm
+    if drop_scale is not None:
+        save["drop_scale"] = drop_scale
+    for k, v in p.items():
+        save["p:" + k] = v
+    for k, v in grads.items():
+        save["g:" + k] = v
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **save)
+
+
+def make_model_case(ref, name, B, seed, mask=False):
+    """Uformer(img_size=128, embed_dim=32) forward, config 1 of BASELINE.json (B tiles)."""
+    torch.manual_seed(seed)
+    model = ref.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff")
+    param_fill.fill_module(model, seed)
+    model.eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(B, 3, 128, 128, generator=g)
+    torch.manual_seed(seed + 2)
+    with Recorder(ref) as rec, torch.no_grad():
+        y = model(x)
+    assert len(rec.idx) == 18
+    keys = sorted(model.state_dict().keys())
+    np.savez_compressed(
+        os.path.join(GOLD, name + ".npz"),
+        x=x.numpy(), y=y.numpy(), idx=np.stack([i.numpy() for i in rec.idx]).astype(np.int8),
+        seed=np.int64(seed), n_keys=np.int64(len(keys)),
+        key_crc=np.int64(__import__("zlib").crc32("\n".join(
+            f"{k}:{tuple(model.state_dict()[k].shape)}" for k in keys).encode())))
+    with open(os.path.join(GOLD, "uformer32_state_dict_keys.txt"), "w") as f:
+        for k in keys:
+            f.write(f"{k} {tuple(model.state_dict()[k].shape)} {str(model.state_dict()[k].dtype).replace('torch.', '')}\n")
+    print(f"{name}: out range [{y.min():.3f}, {y.max():.3f}], |y-x| max {np.abs((y - x).numpy()).max():.3f}")
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref = ref_shim.import_reference()
+    torch.set_num_threads(os.cpu_count() or 1)
+    for i, case in enumerate(BLOCK_CASES):
+        make_block_case(ref, *case, seed=100 + 10 * i)
+    make_model_case(ref, "uformer32_b2", B=2, seed=1234)
+
+
+if __name__ == "__main__":
+    main()

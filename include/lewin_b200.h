@@ -1,0 +1,201 @@
+/*
+ * lewin_b200.h — C ABI of the B200 (sm_100a) LeWin hot path.
+ *
+ * The reference (xin-fight/...Vision-Transformer, Uformer_ProbSparse/) is pure PyTorch; the
+ * "FFI" a maintainer binds is ctypes from Python.  Every entry point
+ * replaces a reference nn.Module forward (or its autograd backward), cited per function
+ * as file:line relative to /root/reference/Uformer_ProbSparse/.
+ *
+ * Contract (all functions):
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (inputs, outputs, saved tensors and the workspace) — the library never allocates,
+ *     frees or retains pointers;
+ *   - work is enqueued on `stream` of the caller's current device and never synchronises;
+ *   - re-entrant, no global mutable state (safe under nn.DataParallel threads and under
+ *     one-process-per-GPU torch.distributed);
+ *   - return 0 on success; negative = argument/shape/alignment violation detected before
+ *     any launch (LEWIN_E_*); positive = cudaError_t of a failed launch.  No C++ exception
+ *     crosses the boundary;
+ *   - there is no CPU fallback and no other architecture: the library contains sm_100a
+ *     code only.
+ *
+ * dtype: `_f32` entry points take fp32 activations (the reference's inference precision,
+ * test_long_GPU.py:91) and compute every contraction with error-compensated 3xTF32 tensor
+ * core MMAs (fp32-grade accuracy, needed for exact top-u parity).  `_bf16` entry points
+ * take bf16 activations (the reference under torch.autocast(bfloat16); My_train.py:224 uses
+ * fp16 autocast) with fp32 accumulation and the reference's rounding points
+ * (SURVEY.md A.4).  Parameters are always fp32 (the state_dict dtype).
+ */
+#ifndef LEWIN_B200_H
+#define LEWIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* lewin_stream_t; /* == cudaStream_t */
+
+#define LEWIN_ABI_VERSION 1
+
+/* error codes (negative) */
+#define LEWIN_E_NULL      (-1)  /* a required pointer is NULL */
+#define LEWIN_E_SHAPE     (-2)  /* unsupported dims (C % 32, head_dim != 32, H/W % 8, ...) */
+#define LEWIN_E_ALIGN     (-3)  /* a pointer is not 16-byte aligned */
+#define LEWIN_E_WORKSPACE (-4)  /* workspace too small */
+#define LEWIN_E_DTYPE     (-5)  /* unknown dtype tag */
+#define LEWIN_E_ARCH      (-6)  /* current device is not compute capability 10.x */
+
+#define LEWIN_DTYPE_F32  0
+#define LEWIN_DTYPE_BF16 1
+
+#define LEWIN_WIN      8     /* window side, My_model_1.py:752 */
+#define LEWIN_NTOK     64    /* tokens per window */
+#define LEWIN_TOPU     25    /* u = U_part = 5*ceil(ln 64), ProbSparse/attn.py:310-315 */
+#define LEWIN_RPB_ROWS 225   /* (2*8-1)^2, My_model_1.py:362 */
+
+/* ------------------------------------------------------------------------------------------
+ * Attention half of LeWinTransformerBlock.forward (My_model_1.py:803-872):
+ *   y = x + drop_scale[b] * unroll(unwindow( WindowAttention( window(roll( LN1(x) )) ) ))
+ * with WindowAttention.forward (My_model_1.py:400-415) -> AttentionLayer.forward
+ * (ProbSparse/attn.py:385-461) -> ProbAttention.forward (attn.py:287-342).
+ *
+ * Two addressing modes:
+ *   windowed == 0 (fused block half): x, y are [B, H, W, C] token-major; LN1, the cyclic shift,
+ *       window_partition / window_reverse (My_model_1.py:550-601) and the residual add are folded
+ *       into the load / store addressing.
+ *   windowed == 1 (strict drop-in at WindowAttention.forward): x, y are [B_, 64, C] windows
+ *       (B_ = B * (H/8) * (W/8), batch-major); no LN, no roll, no residual.
+ * Mask: `mask` (nullable) is a dense fp32 [nW_mask, 64, 64] added to the post-softmax
+ * probabilities of window (w mod nW_mask) exactly as attn.py:236-261; if `analytic_shift_mask`
+ * != 0 and shift > 0 the shift mask of My_model_1.py:803-836 is evaluated in registers instead
+ * of being materialised (the two may be combined).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t B, H, W, C, nH;        /* head_dim = C / nH must be 32 */
+    int32_t shift;                 /* 0 or 4 (My_model_1.py:927) */
+    int32_t windowed;              /* addressing mode, see above */
+    int32_t use_rpb;               /* options.is_relative_position_bias (options.py:5, attn.py:227) */
+    int32_t analytic_shift_mask;   /* evaluate the shift mask from coordinates */
+    int32_t nW_mask;               /* windows in `mask` (0 if mask == NULL) */
+    int32_t save_for_backward;     /* 1: qkv / ctx / top are kept valid for lewin_attn_bwd_* */
+    int32_t reserved;
+
+    const void*  x;                /* activations, dtype per entry point */
+    void*        y;
+    const float* ln_w;             /* norm1.weight [C]   (ignored when windowed) */
+    const float* ln_b;             /* norm1.bias   [C] */
+    const float* w_qkv;            /* [3C, C]: rows = query|key|value_projection.weight (attn.py:377-379) */
+    const float* b_qkv;            /* [3C] */
+    const float* w_out;            /* out_projection.weight [C, C] (attn.py:381) */
+    const float* b_out;            /* [C] */
+    const float* rpb_table;        /* relative_position_bias_table [225, nH] (My_model_1.py:362), or NULL if rpb_dense */
+    const float* rpb_dense;        /* gathered bias [nH, 64, 64] as AttentionLayer.forward receives it (attn.py:385), or NULL */
+    const int32_t* index_sample;   /* [64, 25] key-sample indices drawn by the caller exactly as attn.py:91 */
+    const float* mask;             /* dense [nW_mask, 64, 64] or NULL */
+    const float* drop_scale;       /* [B] per-sample DropPath factor (0 or 1/keep) or NULL (My_model_1.py:872) */
+
+    /* caller-owned intermediates (also the saved tensors for backward) */
+    void*    qkv;                  /* [B_*64, 3C] activations dtype */
+    void*    ctx;                  /* [B_*64, C]  activations dtype */
+    uint8_t* top;                  /* [B_, nH, 25] selected query indices (M_top, attn.py:122), by descending M */
+} LewinAttnFwdArgs;
+
+int lewin_attn_fwd_f32 (const LewinAttnFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+int lewin_attn_fwd_bf16(const LewinAttnFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+
+/* Backward of the attention half (autograd of the same reference lines; gradient paths in
+ * SURVEY.md section 3.4).  Gradients of parameters are ACCUMULATED (+=) into fp32 buffers the
+ * caller zero-initialises, dx is written. */
+typedef struct {
+    LewinAttnFwdArgs fwd;          /* same tensors as the forward call (x, params, qkv, ctx, top, ...) */
+    const void* dy;                /* same shape/dtype as y */
+    void*       dx;                /* same shape/dtype as x */
+    float* d_ln_w;  float* d_ln_b; /* [C]  (ignored when windowed) */
+    float* d_w_qkv; float* d_b_qkv;/* [3C, C], [3C] */
+    float* d_w_out; float* d_b_out;/* [C, C], [C] */
+    float* d_rpb_table;            /* [225, nH] */
+} LewinAttnBwdArgs;
+
+int lewin_attn_bwd_f32 (const LewinAttnBwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+int lewin_attn_bwd_bf16(const LewinAttnBwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ProbAttention.forward alone (ProbSparse/attn.py:287-342) on already-projected q | k | v:
+ * qkv is [B_*64, 3C] (columns q | k | v, head h at [h*32, h*32+32) of each third), ctx is
+ * [B_*64, C] == the reference's returned context [B_, 64, nH, 32].  Forward only.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t B_, nH, use_rpb, nW_mask;
+    const void*  qkv;
+    void*        ctx;
+    const float* rpb_table;        /* [225, nH] or NULL */
+    const float* rpb_dense;        /* [nH, 64, 64] or NULL */
+    const int32_t* index_sample;   /* [64, 25] */
+    const float* mask;             /* [nW_mask, 64, 64] or NULL */
+    uint8_t*     top;              /* [B_, nH, 25] or NULL */
+} LewinCoreFwdArgs;
+
+int lewin_probsparse_core_fwd_f32 (const LewinCoreFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+int lewin_probsparse_core_fwd_bf16(const LewinCoreFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs* a, int dtype);
+
+/* ------------------------------------------------------------------------------------------
+ * LeFF half of the block (My_model_1.py:873 with LeFF.forward :496-534):
+ *   out = y + drop_scale[b] * Linear2( GELU( dwconv3x3( GELU( Linear1( LN2(y) ) ) ) ) )
+ * fused == 1: y, out are [B, H, W, C] and LN2 + residual are applied (block half);
+ * fused == 0: strict drop-in at LeFF.forward: out = LeFF(y), no LN, no residual.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t B, H, W, C, hidden;    /* hidden = 4C (mlp_ratio 4, My_model_1.py:777) */
+    int32_t fused;
+    int32_t save_for_backward;     /* 1: pre-activations a1, a2 are written as well */
+    int32_t reserved;
+
+    const void*  y;
+    void*        out;
+    const float* ln_w;  const float* ln_b;   /* norm2 [C] (ignored when !fused) */
+    const float* w1;    const float* b1;     /* mlp.linear1.0 [hidden, C], [hidden] */
+    const float* w_dw;  const float* b_dw;   /* mlp.dwconv.0 [hidden, 1, 3, 3], [hidden] */
+    const float* w2;    const float* b2;     /* mlp.linear2.0 [C, hidden], [C] */
+    const float* drop_scale;                 /* [B] or NULL */
+
+    void* h1;                      /* [B*H*W, hidden] GELU(linear1), activations dtype */
+    void* h2;                      /* [B*H*W, hidden] GELU(dwconv) */
+    void* a1;                      /* pre-GELU linear1 output (only if save_for_backward) */
+    void* a2;                      /* pre-GELU dwconv output  (only if save_for_backward) */
+} LewinLeffFwdArgs;
+
+int lewin_leff_fwd_f32 (const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+int lewin_leff_fwd_bf16(const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+
+typedef struct {
+    LewinLeffFwdArgs fwd;
+    const void* dout;              /* gradient of `out` */
+    void*       dy;                /* gradient of `y` */
+    float* d_ln_w; float* d_ln_b;
+    float* d_w1;   float* d_b1;
+    float* d_w_dw; float* d_b_dw;
+    float* d_w2;   float* d_b2;
+} LewinLeffBwdArgs;
+
+int lewin_leff_bwd_f32 (const LewinLeffBwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+int lewin_leff_bwd_bf16(const LewinLeffBwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+
+/* Workspace sizes (bytes) for the calls above; dtype = LEWIN_DTYPE_*.  0 is a valid answer. */
+size_t lewin_attn_fwd_workspace_bytes(const LewinAttnFwdArgs* a, int dtype);
+size_t lewin_attn_bwd_workspace_bytes(const LewinAttnBwdArgs* a, int dtype);
+size_t lewin_leff_fwd_workspace_bytes(const LewinLeffFwdArgs* a, int dtype);
+size_t lewin_leff_bwd_workspace_bytes(const LewinLeffBwdArgs* a, int dtype);
+
+/* Library / build identification. */
+int         lewin_abi_version(void);     /* == LEWIN_ABI_VERSION */
+const char* lewin_build_info(void);      /* "sm_100a nvcc <ver> ..." */
+const char* lewin_error_string(int code);/* text for a negative LEWIN_E_* code */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEWIN_B200_H */

@@ -1,0 +1,153 @@
+// Shared device helpers for the sm_100a LeWin kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace lewin {
+
+constexpr int kWin = 8;
+constexpr int kTok = 64;
+constexpr int kTopU = 25;
+constexpr int kSampleK = 25;
+constexpr int kHeadDim = 32;
+
+// ---------------------------------------------------------------- activation dtype traits
+template <typename T> struct Act;
+template <> struct Act<float> {
+    static constexpr int kPasses = 3;           // 3xTF32 error-compensated MMA
+    static constexpr bool kIsBf16 = false;
+    __device__ static __forceinline__ float ld(const float* p) { return *p; }
+    __device__ static __forceinline__ void st(float* p, float v) { *p = v; }
+    __device__ static __forceinline__ float round(float v) { return v; }
+};
+template <> struct Act<__nv_bfloat16> {
+    static constexpr int kPasses = 1;           // bf16 values are exact in TF32
+    static constexpr bool kIsBf16 = true;
+    __device__ static __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    __device__ static __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+    __device__ static __forceinline__ float round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+};
+
+// 4 consecutive activations <-> float4 (16-byte load for fp32, 8-byte for bf16)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+
+// ---------------------------------------------------------------- TF32 tensor-core MMA
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// D(16x8) += A(16x8, row) * B(8x8, col), tf32 inputs, fp32 accumulate.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Split an fp32 value into tf32 hi + tf32 lo (x ~= hi + lo to ~2^-22 relative).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = f2tf32(x);
+    lo = f2tf32(x - __uint_as_float(hi));
+}
+
+// Error-compensated product: PASSES == 3 -> a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (small terms first);
+// PASSES == 1 -> a_hi*b_hi only (exact when the operands are bf16-valued).
+template <int PASSES>
+__device__ __forceinline__ void mma_x(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+    uint32_t ah[4], bh[2];
+    if (PASSES == 3) {
+        uint32_t al[4], bl[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) split_tf32(b[i], bh[i], bl[i]);
+        mma_tf32(d, al, bh);
+        mma_tf32(d, ah, bl);
+        mma_tf32(d, ah, bh);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ah[i] = f2tf32(a[i]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) bh[i] = f2tf32(b[i]);
+        mma_tf32(d, ah, bh);
+    }
+}
+
+// ---------------------------------------------------------------- cp.async
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// ---------------------------------------------------------------- math
+__device__ __forceinline__ float gelu_erf(float x) {      // nn.GELU() exact form (My_model_1.py:487-491)
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {     // reduce over aligned groups of G lanes
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- window addressing
+// Row m of the window-ordered token matrix -> token offset in the [B, H, W] map, with the cyclic
+// shift of My_model_1.py:846 and window_partition of :550-574 folded in:
+//   window (b, wy, wx), token (ty, tx)  ->  pixel ((8*wy + ty + s) mod H, (8*wx + tx + s) mod W)
+struct WinMap {
+    int H, W, nWw, nWin, shift;   // nWin = windows per image
+    __device__ __forceinline__ long long token(long long m) const {
+        int n = static_cast<int>(m & 63);
+        long long wg = m >> 6;
+        int b = static_cast<int>(wg / nWin);
+        int w = static_cast<int>(wg - static_cast<long long>(b) * nWin);
+        int wy = w / nWw, wx = w - wy * nWw;
+        int y = wy * 8 + (n >> 3) + shift;
+        int x = wx * 8 + (n & 7) + shift;
+        if (y >= H) y -= H;
+        if (x >= W) x -= W;
+        return (static_cast<long long>(b) * H + y) * W + x;
+    }
+};
+
+}  // namespace lewin

@@ -1,0 +1,287 @@
+// C-ABI of the sm_100a LeWin hot path (see include/lewin_b200.h for the contract).
+#include "../../include/lewin_b200.h"
+
+#include "common.cuh"
+#include "dwconv.cuh"
+#include "gemm_fused.cuh"
+#include "probsparse_core.cuh"
+#include "backward.cuh"
+
+using namespace lewin;
+
+namespace {
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DeviceInfo { int sms; int cc_major; };
+
+inline int device_info(DeviceInfo* d) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaDeviceGetAttribute(&d->cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    return d->cc_major == 10 ? 0 : LEWIN_E_ARCH;
+}
+
+#define CK(expr)                                         \
+    do {                                                 \
+        cudaError_t _e = (expr);                         \
+        if (_e != cudaSuccess) return static_cast<int>(_e); \
+    } while (0)
+
+// ------------------------------------------------------------------ attention forward
+int check_attn(const LewinAttnFwdArgs* a) {
+    if (!a) return LEWIN_E_NULL;
+    if (!a->x || !a->y || !a->w_qkv || !a->b_qkv || !a->w_out || !a->b_out || !a->index_sample || !a->qkv || !a->ctx)
+        return LEWIN_E_NULL;
+    if (!a->windowed && (!a->ln_w || !a->ln_b)) return LEWIN_E_NULL;
+    if (a->use_rpb && !a->rpb_table && !a->rpb_dense) return LEWIN_E_NULL;
+    if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->nH <= 0) return LEWIN_E_SHAPE;
+    if (a->H % 8 || a->W % 8 || a->C % 32 || a->C != a->nH * kHeadDim) return LEWIN_E_SHAPE;
+    if (a->shift < 0 || a->shift >= 8) return LEWIN_E_SHAPE;
+    if (a->shift > 0 && (a->H <= 8 || a->W <= 8)) return LEWIN_E_SHAPE;   // My_model_1.py:764-766 forces shift 0
+    if (a->windowed && (a->shift != 0 || a->analytic_shift_mask)) return LEWIN_E_SHAPE;
+    if (a->mask && a->nW_mask <= 0) return LEWIN_E_SHAPE;
+    if (a->mask && ((a->B * (a->H / 8) * (a->W / 8)) % a->nW_mask)) return LEWIN_E_SHAPE;
+    const void* ps[] = {a->x, a->y, a->ln_w, a->ln_b, a->w_qkv, a->b_qkv, a->w_out, a->b_out, a->qkv, a->ctx, a->mask};
+    for (const void* p : ps)
+        if (p && !aligned16(p)) return LEWIN_E_ALIGN;
+    return 0;
+}
+
+size_t attn_fwd_ws(const LewinAttnFwdArgs* a) {
+    const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
+    return 2 * align_up(tokens * sizeof(float), 256) + align_up(kTok * kTok, 256);
+}
+
+template <typename T>
+int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (int rc = check_attn(a)) return rc;
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    if (!ws || ws_bytes < attn_fwd_ws(a)) return LEWIN_E_WORKSPACE;
+    if (!aligned16(ws)) return LEWIN_E_ALIGN;
+
+    const long long tokens = static_cast<long long>(a->B) * a->H * a->W;
+    const int nWin = (a->H / 8) * (a->W / 8);
+    const int B_ = a->B * nWin;
+    const int C = a->C;
+    unsigned char* wsp = static_cast<unsigned char*>(ws);
+    float* mean = reinterpret_cast<float*>(wsp);
+    float* rstd = reinterpret_cast<float*>(wsp + align_up(tokens * sizeof(float), 256));
+    uint8_t* cnt = wsp + 2 * align_up(tokens * sizeof(float), 256);
+
+    WinMap map{a->H, a->W, a->W / 8, nWin, a->shift};
+    const T* x = static_cast<const T*>(a->x);
+
+    if (!a->windowed) CK(launch_ln_stats<T>(x, tokens, C, mean, rstd, stream));
+    build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
+    CK(cudaGetLastError());
+
+    {   // q | k | v projections (attn.py:420-422) with LN1 + roll + window_partition as the A prologue
+        GemmArgs<T> g{};
+        g.A = x; g.lda = C;
+        g.Wt = a->w_qkv; g.bias = a->b_qkv;
+        g.Y = static_cast<T*>(a->qkv); g.Y2 = nullptr; g.ldy = 3 * C;
+        g.M = tokens; g.N = 3 * C; g.K = C;
+        if (!a->windowed) { g.mean = mean; g.rstd = rstd; g.ln_w = a->ln_w; g.ln_b = a->ln_b; }
+        g.mapA = a->windowed ? 0 : 1; g.mapY = 0; g.map = map;
+        g.tokens_per_image = a->H * a->W;
+        CK((launch_gemm<T, EPI_BIAS>(g, stream)));
+    }
+    {   // ProbSparse core (attn.py:287-342)
+        CoreFwdArgs<T> c{};
+        c.qkv = static_cast<const T*>(a->qkv);
+        c.ctx = static_cast<T*>(a->ctx);
+        c.top = a->top;
+        c.rpb_table = a->rpb_table;
+        c.rpb_dense = a->rpb_table ? nullptr : a->rpb_dense;
+        c.cnt = cnt;
+        c.mask = a->mask; c.nW_mask = a->mask ? a->nW_mask : 1;
+        c.B_ = B_; c.nH = a->nH; c.C = C;
+        c.use_rpb = a->use_rpb;
+        c.shift = (a->analytic_shift_mask && !a->windowed) ? a->shift : 0;
+        c.H = a->H; c.W = a->W; c.nWw = a->W / 8; c.nWin = nWin;
+        CK(launch_core_fwd<T>(c, di.sms, stream));
+    }
+    {   // out projection (attn.py:456) + window_reverse + un-roll + DropPath scale + residual
+        GemmArgs<T> g{};
+        g.A = static_cast<const T*>(a->ctx); g.lda = C;
+        g.Wt = a->w_out; g.bias = a->b_out;
+        g.Y = static_cast<T*>(a->y); g.ldy = C;
+        g.M = tokens; g.N = C; g.K = C;
+        g.mapA = 0; g.mapY = a->windowed ? 0 : 1; g.map = map;
+        g.tokens_per_image = a->H * a->W;
+        if (a->windowed) {
+            CK((launch_gemm<T, EPI_BIAS>(g, stream)));
+        } else {
+            g.R = x; g.drop_scale = a->drop_scale;
+            CK((launch_gemm<T, EPI_BIAS_RESID>(g, stream)));
+        }
+    }
+    return 0;
+}
+
+template <typename T>
+int core_only_fwd(const LewinCoreFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!a || !a->qkv || !a->ctx || !a->index_sample) return LEWIN_E_NULL;
+    if (a->use_rpb && !a->rpb_table && !a->rpb_dense) return LEWIN_E_NULL;
+    if (a->B_ <= 0 || a->nH <= 0) return LEWIN_E_SHAPE;
+    if (a->mask && (a->nW_mask <= 0 || a->B_ % a->nW_mask)) return LEWIN_E_SHAPE;
+    if (!aligned16(a->qkv) || !aligned16(a->ctx) || (a->mask && !aligned16(a->mask))) return LEWIN_E_ALIGN;
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    if (!ws || ws_bytes < static_cast<size_t>(kTok * kTok)) return LEWIN_E_WORKSPACE;
+    if (!aligned16(ws)) return LEWIN_E_ALIGN;
+    uint8_t* cnt = static_cast<uint8_t*>(ws);
+    build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
+    CK(cudaGetLastError());
+    CoreFwdArgs<T> c{};
+    c.qkv = static_cast<const T*>(a->qkv);
+    c.ctx = static_cast<T*>(a->ctx);
+    c.top = a->top;
+    c.rpb_table = a->rpb_table;
+    c.rpb_dense = a->rpb_table ? nullptr : a->rpb_dense;
+    c.cnt = cnt;
+    c.mask = a->mask; c.nW_mask = a->mask ? a->nW_mask : 1;
+    c.B_ = a->B_; c.nH = a->nH; c.C = a->nH * kHeadDim;
+    c.use_rpb = a->use_rpb;
+    c.shift = 0; c.H = 8; c.W = 8; c.nWw = 1; c.nWin = 1;
+    CK(launch_core_fwd<T>(c, di.sms, stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ LeFF forward
+int check_leff(const LewinLeffFwdArgs* a) {
+    if (!a) return LEWIN_E_NULL;
+    if (!a->y || !a->out || !a->w1 || !a->b1 || !a->w_dw || !a->b_dw || !a->w2 || !a->b2 || !a->h1 || !a->h2)
+        return LEWIN_E_NULL;
+    if (a->fused && (!a->ln_w || !a->ln_b)) return LEWIN_E_NULL;
+    if (a->save_for_backward && (!a->a1 || !a->a2)) return LEWIN_E_NULL;
+    if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->hidden <= 0) return LEWIN_E_SHAPE;
+    if (a->C % 32 || a->hidden % 32) return LEWIN_E_SHAPE;
+    const void* ps[] = {a->y, a->out, a->ln_w, a->ln_b, a->w1, a->b1, a->w_dw, a->b_dw, a->w2, a->b2, a->h1, a->h2, a->a1, a->a2};
+    for (const void* p : ps)
+        if (p && !aligned16(p)) return LEWIN_E_ALIGN;
+    return 0;
+}
+
+size_t leff_fwd_ws(const LewinLeffFwdArgs* a) {
+    const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
+    return 2 * align_up(tokens * sizeof(float), 256);
+}
+
+template <typename T>
+int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (int rc = check_leff(a)) return rc;
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    if (!ws || ws_bytes < leff_fwd_ws(a)) return LEWIN_E_WORKSPACE;
+    if (!aligned16(ws)) return LEWIN_E_ALIGN;
+    const long long tokens = static_cast<long long>(a->B) * a->H * a->W;
+    const int C = a->C, Ch = a->hidden;
+    unsigned char* wsp = static_cast<unsigned char*>(ws);
+    float* mean = reinterpret_cast<float*>(wsp);
+    float* rstd = reinterpret_cast<float*>(wsp + align_up(tokens * sizeof(float), 256));
+    const T* y = static_cast<const T*>(a->y);
+    const bool save = a->save_for_backward != 0;
+
+    if (a->fused) CK(launch_ln_stats<T>(y, tokens, C, mean, rstd, stream));
+    {   // linear1 + GELU (My_model_1.py:508) with LN2 as the A prologue
+        GemmArgs<T> g{};
+        g.A = y; g.lda = C;
+        g.Wt = a->w1; g.bias = a->b1;
+        g.Y = static_cast<T*>(a->h1); g.Y2 = save ? static_cast<T*>(a->a1) : nullptr; g.ldy = Ch;
+        g.M = tokens; g.N = Ch; g.K = C;
+        if (a->fused) { g.mean = mean; g.rstd = rstd; g.ln_w = a->ln_w; g.ln_b = a->ln_b; }
+        g.tokens_per_image = a->H * a->W;
+        CK((launch_gemm<T, EPI_BIAS_GELU>(g, stream)));
+    }
+    CK(launch_dwconv_gelu<T>(static_cast<const T*>(a->h1), static_cast<T*>(a->h2), save ? static_cast<T*>(a->a2) : nullptr,
+                             a->w_dw, a->b_dw, a->B, a->H, a->W, Ch, stream));
+    {   // linear2 (My_model_1.py:529) + DropPath scale + residual (My_model_1.py:873)
+        GemmArgs<T> g{};
+        g.A = static_cast<const T*>(a->h2); g.lda = Ch;
+        g.Wt = a->w2; g.bias = a->b2;
+        g.Y = static_cast<T*>(a->out); g.ldy = C;
+        g.M = tokens; g.N = C; g.K = Ch;
+        g.tokens_per_image = a->H * a->W;
+        if (a->fused) {
+            g.R = y; g.drop_scale = a->drop_scale;
+            CK((launch_gemm<T, EPI_BIAS_RESID>(g, stream)));
+        } else {
+            CK((launch_gemm<T, EPI_BIAS>(g, stream)));
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lewin_attn_fwd_f32(const LewinAttnFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return attn_fwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+int lewin_attn_fwd_bf16(const LewinAttnFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return attn_fwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+int lewin_probsparse_core_fwd_f32(const LewinCoreFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return core_only_fwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+int lewin_probsparse_core_fwd_bf16(const LewinCoreFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return core_only_fwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs*, int) { return kTok * kTok; }
+int lewin_leff_fwd_f32(const LewinLeffFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return leff_fwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+int lewin_leff_fwd_bf16(const LewinLeffFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return leff_fwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+
+int lewin_attn_bwd_f32(const LewinAttnBwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return lewin::attn_bwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+int lewin_attn_bwd_bf16(const LewinAttnBwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return lewin::attn_bwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+int lewin_leff_bwd_f32(const LewinLeffBwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return lewin::leff_bwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+int lewin_leff_bwd_bf16(const LewinLeffBwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return lewin::leff_bwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+
+size_t lewin_attn_fwd_workspace_bytes(const LewinAttnFwdArgs* a, int) { return a ? attn_fwd_ws(a) : 0; }
+size_t lewin_leff_fwd_workspace_bytes(const LewinLeffFwdArgs* a, int) { return a ? leff_fwd_ws(a) : 0; }
+size_t lewin_attn_bwd_workspace_bytes(const LewinAttnBwdArgs* a, int dtype) { return a ? lewin::attn_bwd_ws(a, dtype) : 0; }
+size_t lewin_leff_bwd_workspace_bytes(const LewinLeffBwdArgs* a, int dtype) { return a ? lewin::leff_bwd_ws(a, dtype) : 0; }
+
+int lewin_abi_version(void) { return LEWIN_ABI_VERSION; }
+
+const char* lewin_build_info(void) {
+#define LEWIN_STR2(x) #x
+#define LEWIN_STR(x) LEWIN_STR2(x)
+    return "lewin_b200 sm_100a; nvcc " LEWIN_STR(__CUDACC_VER_MAJOR__) "." LEWIN_STR(__CUDACC_VER_MINOR__)
+           "; mma.sync tf32 (3xTF32 for f32)";
+}
+
+const char* lewin_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case LEWIN_E_NULL: return "required pointer is NULL";
+        case LEWIN_E_SHAPE: return "unsupported shape (need H,W % 8 == 0, C % 32 == 0, head_dim == 32, shift in {0..7})";
+        case LEWIN_E_ALIGN: return "pointer not 16-byte aligned";
+        case LEWIN_E_WORKSPACE: return "workspace missing or too small";
+        case LEWIN_E_DTYPE: return "unknown dtype";
+        case LEWIN_E_ARCH: return "device is not compute capability 10.x (sm_100a only, no fallback)";
+        default: return code > 0 ? "CUDA runtime error (cudaError_t)" : "unknown error";
+    }
+}
+
+}  // extern "C"

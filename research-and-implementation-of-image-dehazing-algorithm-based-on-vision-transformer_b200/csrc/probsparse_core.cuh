@@ -1,0 +1,299 @@
+// ProbSparse window-attention core, forward: one CTA (4 warps) per (window, head).
+//
+// Reference: ProbAttention.forward, ProbSparse/attn.py:287-342
+//   _prob_QK           attn.py:71-152   sampled scores, sparsity measure M, top-u, Q^K^T
+//   _get_initial_context attn.py:154-176 mean(V) fill
+//   _update_context    attn.py:178-281  softmax -> +rpb -> +mask -> softmax (double softmax!) -> P.V scatter
+//
+// B200 restatement: the full 64x64 score tile S = Q.K^T is produced on tensor cores (cheaper than
+// gathering 25 keys per query, and the top-u rows of S are re-used); the reference's materialised
+// K_sample[B_,nH,64,25,D] gather (attn.py:104) becomes a multiplicity matrix cnt[n][m] = #{t :
+// idx[n,t] == m}, so  M_n = max_{cnt>0} S[n,m] - (sum_m cnt[n,m] S[n,m]) / 64  (attn.py:117) is a
+// quad-shuffle reduction over the MMA accumulators.  Top-u is rank-by-counting (ties -> lower
+// index).  Only the 25 selected rows go through the two softmaxes and P.V.
+#pragma once
+#include "common.cuh"
+
+namespace lewin {
+
+template <typename T>
+struct CoreFwdArgs {
+    const T* qkv;            // [B_*64, 3C]  q | k | v
+    T* ctx;                  // [B_*64, C]
+    uint8_t* top;            // [B_, nH, 25] or null
+    const float* rpb_table;  // [225, nH] (or null)
+    const float* rpb_dense;  // [nH, 64, 64] (or null)
+    const uint8_t* cnt;      // [64, 64] sample multiplicities (built from index_sample)
+    const float* mask;       // dense [nW_mask, 64, 64] or null
+    int nW_mask;
+    int B_, nH, C;
+    int use_rpb;
+    // analytic shift mask (My_model_1.py:803-836)
+    int shift, H, W, nWw, nWin;
+};
+
+constexpr int CORE_THREADS = 128;
+constexpr int QK_LD = 36;   // q/k smem row stride (floats)
+constexpr int V_LD = 40;    // v smem row stride: conflict-free B-fragment loads for P.V
+constexpr int P_LD = 68;    // selected-row score / probability stride
+
+struct CoreSmem {
+    float q[kTok * QK_LD];
+    float k[kTok * QK_LD];
+    float v[kTok * V_LD];
+    float p[32 * P_LD];           // rows = selection slots (25 used, 7 zero)
+    float M[kTok];
+    float vmean[kHeadDim];
+    float vpart[4 * kHeadDim];
+    float tbl[232];
+    uint8_t cnt[kTok * kTok];
+    int slot_of[kTok];            // token -> slot (or -1)
+    int tok_of[32];               // slot -> token
+    int region[kTok];
+};
+
+// build cnt[64][64] from index_sample[64][25] (attn.py:91); one block of 64 threads
+__global__ void build_cnt_kernel(const int32_t* __restrict__ idx, uint8_t* __restrict__ cnt) {
+    const int n = threadIdx.x;
+    if (n >= kTok) return;
+    uint8_t row[kTok];
+#pragma unroll
+    for (int m = 0; m < kTok; ++m) row[m] = 0;
+    for (int t = 0; t < kSampleK; ++t) {
+        int m = idx[n * kSampleK + t] & 63;
+        row[m]++;
+    }
+    for (int m = 0; m < kTok; ++m) cnt[n * kTok + m] = row[m];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const CoreFwdArgs<T> a) {
+    constexpr int PASSES = Act<T>::kPasses;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CoreSmem& s = *reinterpret_cast<CoreSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int C3 = 3 * a.C;
+    const float scale = rsqrtf(static_cast<float>(kHeadDim));   // attn.py:327
+
+    // launch-invariant: sample multiplicities
+    for (int i = tid; i < kTok * kTok / 16; i += CORE_THREADS)
+        reinterpret_cast<uint4*>(s.cnt)[i] = reinterpret_cast<const uint4*>(a.cnt)[i];
+
+    const int items = a.B_ * a.nH;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int wg = item / a.nH;          // global window index (batch-major)
+        const int h = item - wg * a.nH;
+        __syncthreads();                     // previous item fully consumed
+
+        // ---- stage q, k, v (64 x 32 each) as fp32
+        {
+            const T* base = a.qkv + static_cast<long long>(wg) * kTok * C3 + h * kHeadDim;
+            for (int c = tid; c < 3 * kTok * 8; c += CORE_THREADS) {
+                int which = c / (kTok * 8);
+                int rem = c - which * kTok * 8;
+                int r = rem >> 3, d4 = (rem & 7) * 4;
+                float4 v = ld4(base + static_cast<long long>(r) * C3 + which * a.C + d4);
+                float* dst = which == 0 ? s.q + r * QK_LD + d4 : which == 1 ? s.k + r * QK_LD + d4 : s.v + r * V_LD + d4;
+                *reinterpret_cast<float4*>(dst) = v;
+            }
+            if (a.use_rpb && a.rpb_table)
+                for (int i = tid; i < 225; i += CORE_THREADS) s.tbl[i] = a.rpb_table[i * a.nH + h];
+            if (a.shift > 0 && tid < kTok) {
+                // region id of each token in the shifted frame (My_model_1.py:809-820)
+                int w = wg % a.nWin;
+                int wy = w / a.nWw, wx = w - wy * a.nWw;
+                int y = wy * 8 + (tid >> 3), x = wx * 8 + (tid & 7);
+                int rb = y < a.H - 8 ? 0 : (y < a.H - a.shift ? 1 : 2);
+                int cb = x < a.W - 8 ? 0 : (x < a.W - a.shift ? 1 : 2);
+                s.region[tid] = rb * 3 + cb;
+            }
+        }
+        __syncthreads();
+
+        // ---- S = Q K^T : warp owns query rows [16*warp, 16*warp+16), all 64 keys
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < kHeadDim / 8; ++ks) {
+            float af[4];
+            const float* pa = s.q + (warp * 16 + gq) * QK_LD + ks * 8 + tq;
+            af[0] = pa[0]; af[1] = pa[8 * QK_LD]; af[2] = pa[4]; af[3] = pa[8 * QK_LD + 4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float bf[2];
+                const float* pb = s.k + (j * 8 + gq) * QK_LD + ks * 8 + tq;
+                bf[0] = pb[0]; bf[1] = pb[4];
+                mma_x<PASSES>(acc[j], af, bf);
+            }
+        }
+
+        // ---- sparsity measure (attn.py:117) on unscaled scores; bf16 mode rounds S~ first (A.4)
+        {
+            float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int r = warp * 16 + gq + half * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = j * 8 + 2 * tq;
+                    const uint16_t c2 = *reinterpret_cast<const uint16_t*>(s.cnt + r * kTok + col);
+                    const int c0 = c2 & 0xff, c1 = c2 >> 8;
+                    const float s0 = Act<T>::round(acc[j][half * 2 + 0]);
+                    const float s1 = Act<T>::round(acc[j][half * 2 + 1]);
+                    if (c0) { mx[half] = fmaxf(mx[half], s0); sm[half] += c0 * s0; }
+                    if (c1) { mx[half] = fmaxf(mx[half], s1); sm[half] += c1 * s1; }
+                }
+                mx[half] = group_max<4>(mx[half]);
+                sm[half] = group_sum<4>(sm[half]);
+                if (tq == 0) s.M[r] = mx[half] - sm[half] * (1.0f / kTok);
+            }
+        }
+        __syncthreads();
+
+        // ---- top-u by rank counting (attn.py:122); ties -> lower index first
+        if (tid < kTok) {
+            const float mine = s.M[tid];
+            int rank = 0;
+#pragma unroll 8
+            for (int m = 0; m < kTok; ++m) {
+                const float o = s.M[m];
+                rank += (o > mine) || (o == mine && m < tid);
+            }
+            const int slot = rank < kTopU ? rank : -1;
+            s.slot_of[tid] = slot;
+            if (slot >= 0) {
+                s.tok_of[slot] = tid;
+                if (a.top) a.top[static_cast<long long>(item) * kTopU + slot] = static_cast<uint8_t>(tid);
+            }
+        } else if (tid < kTok + 7) {
+            s.tok_of[kTopU + tid - kTok] = -1;
+        }
+        __syncthreads();
+
+        // ---- selected rows: scaled scores -> smem (attn.py:150, 327-329)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = warp * 16 + gq + half * 8;
+            const int slot = s.slot_of[r];
+            if (slot >= 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float2 v;
+                    v.x = Act<T>::round(Act<T>::round(acc[j][half * 2 + 0]) * scale);
+                    v.y = Act<T>::round(Act<T>::round(acc[j][half * 2 + 1]) * scale);
+                    *reinterpret_cast<float2*>(s.p + slot * P_LD + j * 8 + 2 * tq) = v;
+                }
+            }
+        }
+        // column means of V (attn.py:168)
+        {
+            const int d = tid & 31, part = tid >> 5;
+            float sum = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) sum += s.v[(part * 16 + r) * V_LD + d];
+            s.vpart[part * kHeadDim + d] = sum;
+        }
+        __syncthreads();
+        if (tid < kHeadDim)
+            s.vmean[tid] = Act<T>::round((s.vpart[tid] + s.vpart[32 + tid] + s.vpart[64 + tid] + s.vpart[96 + tid]) * (1.0f / kTok));
+
+        // ---- softmax -> +rpb -> +mask -> softmax on the selected rows (attn.py:195-264)
+        for (int slot = warp; slot < 32; slot += 4) {
+            float* prow = s.p + slot * P_LD;
+            if (slot >= kTopU) { prow[lane] = 0.f; prow[lane + 32] = 0.f; continue; }
+            const int r = s.tok_of[slot];
+            float x0 = prow[lane], x1 = prow[lane + 32];
+            float mx = group_max<32>(fmaxf(x0, x1));
+            float e0 = expf(x0 - mx), e1 = expf(x1 - mx);
+            float inv = 1.0f / group_sum<32>(e0 + e1);
+            float p0 = e0 * inv, p1 = e1 * inv;                  // P1 (first softmax)
+            if (a.use_rpb) {                                     // My_model_1.py:366-381 index, attn.py:229
+                if (a.rpb_table) {
+                    const int ry = r >> 3, rx = r & 7;
+                    const int c0 = lane, c1 = lane + 32;
+                    p0 += s.tbl[(ry - (c0 >> 3) + 7) * 15 + (rx - (c0 & 7) + 7)];
+                    p1 += s.tbl[(ry - (c1 >> 3) + 7) * 15 + (rx - (c1 & 7) + 7)];
+                } else {
+                    const float* brow = a.rpb_dense + (static_cast<long long>(h) * kTok + r) * kTok;
+                    p0 += brow[lane];
+                    p1 += brow[lane + 32];
+                }
+            }
+            if (a.mask) {                                        // attn.py:250: window index within the image
+                const float* mrow = a.mask + (static_cast<long long>(wg % a.nW_mask) * kTok + r) * kTok;
+                p0 += mrow[lane];
+                p1 += mrow[lane + 32];
+            }
+            if (a.shift > 0) {
+                const int rr = s.region[r];
+                p0 += (s.region[lane] != rr) ? -100.0f : 0.f;
+                p1 += (s.region[lane + 32] != rr) ? -100.0f : 0.f;
+            }
+            mx = group_max<32>(fmaxf(p0, p1));
+            e0 = expf(p0 - mx); e1 = expf(p1 - mx);
+            inv = 1.0f / group_sum<32>(e0 + e1);
+            prow[lane] = Act<T>::round(e0 * inv);                // P2 (second softmax)
+            prow[lane + 32] = Act<T>::round(e1 * inv);
+        }
+        __syncthreads();
+
+        // ---- ctx_sel[32 x 32] = P2[32 x 64] . V[64 x 32]  (attn.py:272): warp -> (m-tile, 2 n-tiles)
+        {
+            const int mt = warp & 1, nb = (warp >> 1) * 2;
+            float o[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[j][c] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < kTok / 8; ++ks) {
+                float af[4];
+                const float* pa = s.p + (mt * 16 + gq) * P_LD + ks * 8 + tq;
+                af[0] = pa[0]; af[1] = pa[8 * P_LD]; af[2] = pa[4]; af[3] = pa[8 * P_LD + 4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float bf[2];
+                    const float* pb = s.v + (ks * 8 + tq) * V_LD + (nb + j) * 8 + gq;
+                    bf[0] = pb[0]; bf[1] = pb[4 * V_LD];
+                    mma_x<PASSES>(o[j], af, bf);
+                }
+            }
+            T* cbase = a.ctx + static_cast<long long>(wg) * kTok * a.C + h * kHeadDim;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int slot = mt * 16 + gq + half * 8;
+                const int r = s.tok_of[slot];
+                if (r >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        st2(cbase + static_cast<long long>(r) * a.C + (nb + j) * 8 + 2 * tq, o[j][half * 2], o[j][half * 2 + 1]);
+                }
+            }
+            // lazy queries: mean(V) (attn.py:172)
+            for (int c = tid; c < kTok * 8; c += CORE_THREADS) {
+                const int r = c >> 3, d4 = (c & 7) * 4;
+                if (s.slot_of[r] < 0)
+                    st4(cbase + static_cast<long long>(r) * a.C + d4, *reinterpret_cast<const float4*>(s.vmean + d4));
+            }
+        }
+    }
+}
+
+template <typename T>
+cudaError_t launch_core_fwd(const CoreFwdArgs<T>& a, int num_sms, cudaStream_t stream) {
+    auto k = probsparse_core_fwd_kernel<T>;
+    const size_t smem = sizeof(CoreSmem);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    long long items = static_cast<long long>(a.B_) * a.nH;
+    long long cap = static_cast<long long>(num_sms) * 4 * 4;      // 4 resident CTAs/SM, ~4 waves before looping
+    unsigned grid = static_cast<unsigned>(items < cap ? items : cap);
+    k<<<grid, CORE_THREADS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace lewin

@@ -1,0 +1,113 @@
+"""Full-resolution dehazing: the caller of the hot path for BASELINE config 3.
+
+Reference: test_long_GPU.py:74-93 wrap-pads a 1200x1600 image to a 1664x1664 canvas and runs the model
+ONCE on the canvas ("canvas mode", `dehaze_canvas`).  BASELINE.json's config 3 tiles the canvas into
+train_ps=128 patches and shards the tiles over the GPUs of one box ("tiled mode", `dehaze_tiled`): every
+tile is an independent image (own zero padding in LeFF's depthwise conv, own cyclic-shift wrap), so the
+only inter-GPU traffic is the final gather of 3x128x128 outputs.  The two modes are different computations
+(SURVEY.md finding 7); parity is judged mode for mode.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def canvas_size(H, W, ps=128):
+    """test_long_GPU.py:79-80: L = (max(H, W) // ps + 1) * ps  (1664 for 1200x1600)."""
+    return (max(H, W) // ps + 1) * ps
+
+
+def wrap_pad(img, L=None, ps=128):
+    """test_long_GPU.py:85-89: zero canvas, image top-left, right strip <- image's first columns,
+    bottom strip <- the canvas's own first rows."""
+    B, C, H, W = img.shape
+    L = L or canvas_size(H, W, ps)
+    LH, LW = L - H, L - W
+    if LW > W or LH > H:
+        raise ValueError("wrap padding larger than the image itself")
+    big = torch.zeros((B, C, L, L), dtype=img.dtype, device=img.device)
+    big[:, :, :H, :W] = img
+    big[:, :, :H, W:W + LW] = img[:, :, :, :LW]
+    big[:, :, H:H + LH, :] = big[:, :, :LH, :]
+    return big
+
+
+def to_tiles(canvas, ps=128):
+    """[1, C, L, L] -> [T, C, ps, ps], tiles in row-major order."""
+    B, C, L, L2 = canvas.shape
+    assert B == 1 and L == L2 and L % ps == 0
+    n = L // ps
+    return canvas.view(C, n, ps, n, ps).permute(1, 3, 0, 2, 4).reshape(n * n, C, ps, ps).contiguous()
+
+
+def from_tiles(tiles, L, ps=128):
+    T, C, _, _ = tiles.shape
+    n = L // ps
+    assert T == n * n
+    return tiles.view(n, n, C, ps, ps).permute(2, 0, 3, 1, 4).reshape(1, C, L, L).contiguous()
+
+
+def shard_range(T, rank, world):
+    """Contiguous tile range of `rank` (the first T % world ranks get one extra tile)."""
+    base, extra = divmod(T, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+@torch.no_grad()
+def dehaze_canvas(model, img, ps=128, index_samples=None):
+    """Reference semantics (test_long_GPU.py:85-93): one forward over the whole padded canvas."""
+    B, C, H, W = img.shape
+    canvas = wrap_pad(img, ps=ps)
+    out = model(canvas, index_samples=index_samples) if index_samples is not None else model(canvas)
+    return out[:, :, :H, :W].clamp(0, 1)
+
+
+@torch.no_grad()
+def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=None):
+    """Tiled mode, sharded over the ranks of `group` (torch.distributed) when initialised.
+
+    Every rank receives the full image, processes its contiguous tile range and all ranks end with the full
+    restored image (all_gather of the padded shards).  The 18 index_sample draws are made on rank 0 and
+    broadcast so that the sharded result is bit-identical to the single-GPU tile-batch result."""
+    import torch.distributed as dist
+
+    B, C, H, W = img.shape
+    assert B == 1
+    canvas = wrap_pad(img, ps=ps)
+    L = canvas.shape[-1]
+    tiles = to_tiles(canvas, ps)
+    T = tiles.shape[0]
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+
+    if index_samples is None and hasattr(model, "draw_index_samples"):
+        index_samples = model.draw_index_samples()
+    if distributed and index_samples is not None:
+        idx = index_samples.to(img.device)
+        dist.broadcast(idx, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        index_samples = idx
+
+    s, e = shard_range(T, rank, world)
+    mine = tiles[s:e]
+    outs = []
+    step = tile_batch or max(e - s, 1)
+    for i in range(0, e - s, step):
+        chunk = mine[i:i + step]
+        outs.append(model(chunk, index_samples=index_samples) if index_samples is not None else model(chunk))
+    out = torch.cat(outs, 0) if outs else mine.new_zeros((0, C, ps, ps))
+
+    if distributed:
+        per = (T + world - 1) // world
+        padded = out.new_zeros((per, C, ps, ps))
+        padded[:e - s] = out
+        gathered = out.new_empty((world * per, C, ps, ps))
+        dist.all_gather_into_tensor(gathered, padded, group=group)
+        parts = []
+        for r in range(world):
+            rs, re = shard_range(T, r, world)
+            parts.append(gathered[r * per:r * per + (re - rs)])
+        out = torch.cat(parts, 0)
+    restored = from_tiles(out, L, ps)
+    return restored[:, :, :H, :W].clamp(0, 1)

@@ -1,0 +1,233 @@
+"""PyTorch custom ops (autograd.Function) over the C ABI of include/lewin_b200.h.
+
+PyTorch is plumbing here: it owns device memory, the current stream and autograd bookkeeping; every
+FLOP of the LeWin block is executed by the sm_100a kernels behind the ABI.  No fallback path exists.
+
+Ops
+---
+lewin_attn(x, ...)   attention half of LeWinTransformerBlock.forward (My_model_1.py:803-872) or, with
+                     ``windowed=True``, WindowAttention.forward (My_model_1.py:400-415).
+lewin_leff(y, ...)   LeFF half (My_model_1.py:873) or, with ``fused=False``, LeFF.forward (:496-534).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: "f32", torch.bfloat16: "bf16"}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t):
+    """Parameters cross the ABI as contiguous fp32 (the state_dict dtype)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype_tag(x):
+    if not x.is_cuda:
+        raise RuntimeError("lewin_b200 ops run on CUDA tensors only (sm_100a kernels, no CPU fallback)")
+    try:
+        return _DT[x.dtype]
+    except KeyError:
+        raise RuntimeError(f"lewin_b200: unsupported activation dtype {x.dtype} (float32 or bfloat16)") from None
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def prepare_index_sample(index_sample, device):
+    """int64 CPU tensor drawn as attn.py:91 -> int32 device tensor [64, 25]."""
+    if index_sample.dtype != torch.int32 or index_sample.device != device:
+        index_sample = index_sample.to(device=device, dtype=torch.int32, non_blocking=True)
+    return index_sample.contiguous()
+
+
+class _AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
+                drop_scale, geom):
+        B, H, W, nH, shift, windowed, use_rpb, analytic = geom
+        lib = _lib.load()
+        dt = _dtype_tag(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        tokens = B * H * W
+        assert x.numel() == tokens * C, (x.shape, B, H, W, C)
+        dev = x.device
+        need_grad = any(ctx.needs_input_grad)
+        y = torch.empty_like(x)
+        qkv = torch.empty((tokens, 3 * C), dtype=x.dtype, device=dev)
+        cbuf = torch.empty((tokens, C), dtype=x.dtype, device=dev)
+        top = torch.empty((tokens // 64, nH, 25), dtype=torch.uint8, device=dev)
+        params = [_f32c(t) for t in (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, mask, drop_scale)]
+        ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, mask_, ds_ = params
+        idx = prepare_index_sample(index_sample, dev)
+        a = _lib.LewinAttnFwdArgs(
+            B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
+            analytic_shift_mask=int(analytic), nW_mask=0 if mask_ is None else mask_.shape[0],
+            save_for_backward=int(need_grad), reserved=0,
+            x=_ptr(x), y=_ptr(y), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w_qkv=_ptr(w_qkv_), b_qkv=_ptr(b_qkv_),
+            w_out=_ptr(w_out_), b_out=_ptr(b_out_), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
+            index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
+            qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
+        ws = _workspace(lib.lewin_attn_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+        fn = getattr(lib, f"lewin_attn_fwd_{dt}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_attn_fwd_{dt}")
+        ctx.geom = geom
+        ctx.dt = dt
+        ctx.save_for_backward(x, ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, idx, mask_, ds_, qkv, cbuf, top)
+        ctx.mark_non_differentiable(top)
+        return y, top
+
+    @staticmethod
+    def backward(ctx, dy, _dtop):
+        (x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense, idx, mask, ds, qkv, cbuf, top) = ctx.saved_tensors
+        B, H, W, nH, shift, windowed, use_rpb, analytic = ctx.geom
+        lib = _lib.load()
+        dt = ctx.dt
+        dev = x.device
+        C = x.shape[-1]
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        z = lambda t: None if t is None else torch.zeros_like(t, dtype=torch.float32)
+        d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out = z(ln_w), z(ln_b), z(w_qkv), z(b_qkv), z(w_out), z(b_out)
+        d_tab = z(tab) if tab is not None else (torch.zeros((225, nH), dtype=torch.float32, device=dev) if dense is not None else None)
+        fwd = _lib.LewinAttnFwdArgs(
+            B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
+            analytic_shift_mask=int(analytic), nW_mask=0 if mask is None else mask.shape[0],
+            save_for_backward=1, reserved=0,
+            x=_ptr(x), y=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w_qkv=_ptr(w_qkv), b_qkv=_ptr(b_qkv),
+            w_out=_ptr(w_out), b_out=_ptr(b_out), rpb_table=_ptr(tab), rpb_dense=_ptr(dense),
+            index_sample=_ptr(idx), mask=_ptr(mask), drop_scale=_ptr(ds),
+            qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
+        a = _lib.LewinAttnBwdArgs(
+            fwd=fwd, dy=_ptr(dy), dx=_ptr(dx), d_ln_w=_ptr(d_ln_w), d_ln_b=_ptr(d_ln_b),
+            d_w_qkv=_ptr(d_w_qkv), d_b_qkv=_ptr(d_b_qkv), d_w_out=_ptr(d_w_out), d_b_out=_ptr(d_b_out),
+            d_rpb_table=_ptr(d_tab))
+        ws = _workspace(lib.lewin_attn_bwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+        fn = getattr(lib, f"lewin_attn_bwd_{dt}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_attn_bwd_{dt}")
+        if dense is not None and tab is None:
+            d_dense, d_tab_out = None, None   # dense bias path: gradient w.r.t. the gathered bias is not provided
+        else:
+            d_dense, d_tab_out = None, d_tab
+        return (dx, d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab_out, d_dense, None, None, None, None)
+
+
+class _LeffFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom):
+        B, H, W, fused = geom
+        lib = _lib.load()
+        dt = _dtype_tag(y)
+        y = y.contiguous()
+        C = y.shape[-1]
+        hidden = w1.shape[0]
+        tokens = B * H * W
+        assert y.numel() == tokens * C, (y.shape, B, H, W, C)
+        dev = y.device
+        need_grad = any(ctx.needs_input_grad)
+        out = torch.empty_like(y)
+        h1 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
+        h2 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
+        a1 = torch.empty_like(h1) if need_grad else None
+        a2 = torch.empty_like(h2) if need_grad else None
+        ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_ = [_f32c(t) for t in (ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale)]
+        a = _lib.LewinLeffFwdArgs(
+            B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=int(need_grad), reserved=0,
+            y=_ptr(y), out=_ptr(out), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w1=_ptr(w1_), b1=_ptr(b1_),
+            w_dw=_ptr(wdw_), b_dw=_ptr(bdw_), w2=_ptr(w2_), b2=_ptr(b2_), drop_scale=_ptr(ds_),
+            h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
+        ws = _workspace(lib.lewin_leff_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+        fn = getattr(lib, f"lewin_leff_fwd_{dt}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_leff_fwd_{dt}")
+        ctx.geom = geom
+        ctx.dt = dt
+        if need_grad:
+            ctx.save_for_backward(y, ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_, h1, h2, a1, a2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (y, ln_w, ln_b, w1, b1, wdw, bdw, w2, b2, ds, h1, h2, a1, a2) = ctx.saved_tensors
+        B, H, W, fused = ctx.geom
+        lib = _lib.load()
+        dt = ctx.dt
+        dev = y.device
+        C = y.shape[-1]
+        hidden = w1.shape[0]
+        dout = dout.contiguous()
+        dy = torch.empty_like(y)
+        z = lambda t: None if t is None else torch.zeros_like(t, dtype=torch.float32)
+        d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2 = z(ln_w), z(ln_b), z(w1), z(b1), z(wdw), z(bdw), z(w2), z(b2)
+        fwd = _lib.LewinLeffFwdArgs(
+            B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=1, reserved=0,
+            y=_ptr(y), out=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w1=_ptr(w1), b1=_ptr(b1),
+            w_dw=_ptr(wdw), b_dw=_ptr(bdw), w2=_ptr(w2), b2=_ptr(b2), drop_scale=_ptr(ds),
+            h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
+        a = _lib.LewinLeffBwdArgs(
+            fwd=fwd, dout=_ptr(dout), dy=_ptr(dy), d_ln_w=_ptr(d_ln_w), d_ln_b=_ptr(d_ln_b),
+            d_w1=_ptr(d_w1), d_b1=_ptr(d_b1), d_w_dw=_ptr(d_wdw), d_b_dw=_ptr(d_bdw), d_w2=_ptr(d_w2), d_b2=_ptr(d_b2))
+        ws = _workspace(lib.lewin_leff_bwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+        fn = getattr(lib, f"lewin_leff_bwd_{dt}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_leff_bwd_{dt}")
+        return (dy, d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2, None, None)
+
+
+def lewin_attn(x, *, B, H, W, num_heads, shift, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out,
+               rpb_table=None, rpb_dense=None, index_sample, mask=None, drop_scale=None,
+               windowed=False, use_rpb=True, analytic_shift_mask=True, return_top=False):
+    """Attention half of a LeWin block.  Returns y (same shape as x) [and the selected top-u indices]."""
+    geom = (int(B), int(H), int(W), int(num_heads), int(shift), bool(windowed), bool(use_rpb), bool(analytic_shift_mask))
+    y, top = _AttnFn.apply(x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
+                           drop_scale, geom)
+    return (y, top) if return_top else y
+
+
+def lewin_leff(y, *, B, H, W, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale=None, fused=True):
+    """LeFF half of a LeWin block (fused=True: out = y + s * LeFF(LN2(y)); fused=False: out = LeFF(y))."""
+    geom = (int(B), int(H), int(W), bool(fused))
+    return _LeffFn.apply(y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom)
+
+
+def probsparse_core(qkv, *, num_heads, index_sample, rpb_table=None, rpb_dense=None, mask=None, use_rpb=True,
+                    return_top=False):
+    """ProbAttention.forward (attn.py:287-342) on projected q|k|v [B_, 64, 3C] -> context [B_, 64, C].
+    Forward only (the trainable paths go through lewin_attn)."""
+    lib = _lib.load()
+    dt = _dtype_tag(qkv)
+    if torch.is_grad_enabled() and qkv.requires_grad:
+        raise RuntimeError("lewin_b200.probsparse_core is forward-only; use lewin_attn for training")
+    qkv = qkv.contiguous()
+    B_, L, C3 = qkv.shape
+    C = C3 // 3
+    dev = qkv.device
+    out = torch.empty((B_, L, C), dtype=qkv.dtype, device=dev)
+    top = torch.empty((B_, num_heads, 25), dtype=torch.uint8, device=dev)
+    tab_, dense_, mask_ = _f32c(rpb_table), _f32c(rpb_dense), _f32c(mask)
+    idx = prepare_index_sample(index_sample, dev)
+    a = _lib.LewinCoreFwdArgs(B_=B_, nH=num_heads, use_rpb=int(use_rpb), nW_mask=0 if mask_ is None else mask_.shape[0],
+                              qkv=_ptr(qkv), ctx=_ptr(out), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
+                              index_sample=_ptr(idx), mask=_ptr(mask_), top=_ptr(top))
+    ws = _workspace(lib.lewin_probsparse_core_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+    fn = getattr(lib, f"lewin_probsparse_core_fwd_{dt}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_probsparse_core_fwd_{dt}")
+    return (out, top) if return_top else out

@@ -1,0 +1,217 @@
+"""Host-side model graph that CALLS the hot path: Uformer (My_model_1.py:955-1230).
+
+Out of the hot-path scope: InputProj / OutputProj / Downsample /
+Upsample are stock PyTorch convolutions (cuDNN), exactly as in the reference; only the 18
+LeWinTransformerBlocks run on the sm_100a kernels.  This file exists because the reference source
+cannot travel to the GPU box; it keeps the reference's constructor arguments, forward signature and
+the 488-key state_dict layout (tests/golden/uformer32_state_dict_keys.txt) so checkpoints load
+strictly (utils/model_utils.py:28-40).
+
+One deliberate host-side difference: the 18 ``index_sample`` draws (attn.py:91) of a forward are made
+up-front, in module order, from the same CPU generator — the RNG stream is identical to the
+reference's, but the 18 small host->device copies collapse into one.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from .modules import LeWinTransformerBlock, draw_index_sample
+
+
+class Downsample(nn.Module):
+    """My_model_1.py:606-622: 4x4 stride-2 conv on the token map."""
+
+    def __init__(self, in_channel, out_channel):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(in_channel, out_channel, kernel_size=4, stride=2, padding=1))
+        self.in_channel, self.out_channel = in_channel, out_channel
+
+    def forward(self, x):
+        B, L, C = x.shape
+        H = W = int(math.sqrt(L))
+        x = x.transpose(1, 2).contiguous().view(B, C, H, W)
+        return self.conv(x).flatten(2).transpose(1, 2).contiguous()
+
+
+class Upsample(nn.Module):
+    """My_model_1.py:633-648: 2x2 stride-2 transposed conv."""
+
+    def __init__(self, in_channel, out_channel):
+        super().__init__()
+        self.deconv = nn.Sequential(nn.ConvTranspose2d(in_channel, out_channel, kernel_size=2, stride=2))
+        self.in_channel, self.out_channel = in_channel, out_channel
+
+    def forward(self, x):
+        B, L, C = x.shape
+        H = W = int(math.sqrt(L))
+        x = x.transpose(1, 2).contiguous().view(B, C, H, W)
+        return self.deconv(x).flatten(2).transpose(1, 2).contiguous()
+
+
+class InputProj(nn.Module):
+    """My_model_1.py:659-682: 3x3 conv + LeakyReLU -> tokens."""
+
+    def __init__(self, in_channel=3, out_channel=64, kernel_size=3, stride=1, norm_layer=None, act_layer=nn.LeakyReLU):
+        super().__init__()
+        self.proj = nn.Sequential(
+            nn.Conv2d(in_channel, out_channel, kernel_size=3, stride=stride, padding=kernel_size // 2),
+            act_layer(inplace=True))
+        self.norm = norm_layer(out_channel) if norm_layer is not None else None
+        self.in_channel, self.out_channel = in_channel, out_channel
+
+    def forward(self, x):
+        x = self.proj(x).flatten(2).transpose(1, 2).contiguous()
+        return self.norm(x) if self.norm is not None else x
+
+
+class OutputProj(nn.Module):
+    """My_model_1.py:696-723: tokens -> 3x3 conv."""
+
+    def __init__(self, in_channel=64, out_channel=3, kernel_size=3, stride=1, norm_layer=None, act_layer=None):
+        super().__init__()
+        self.proj = nn.Sequential(
+            nn.Conv2d(in_channel, out_channel, kernel_size=3, stride=stride, padding=kernel_size // 2))
+        self.norm = norm_layer(out_channel) if norm_layer is not None else None
+        self.in_channel, self.out_channel = in_channel, out_channel
+
+    def forward(self, x):
+        B, L, C = x.shape
+        H = W = int(math.sqrt(L))
+        x = x.transpose(1, 2).reshape(B, C, H, W)
+        x = self.proj(x)
+        return self.norm(x) if self.norm is not None else x
+
+
+class BasicUformerLayer(nn.Module):
+    """My_model_1.py:894-946: ``depth`` LeWin blocks, shift 0 / win//2 alternating."""
+
+    def __init__(self, dim, output_dim, input_resolution, depth, num_heads, win_size, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, use_checkpoint=False,
+                 token_projection='linear', token_mlp='ffn', se_layer=False):
+        super().__init__()
+        self.dim, self.input_resolution, self.depth = dim, input_resolution, depth
+        self.use_checkpoint = use_checkpoint
+        self.blocks = nn.ModuleList([
+            LeWinTransformerBlock(dim=dim, input_resolution=input_resolution, num_heads=num_heads, win_size=win_size,
+                                  shift_size=0 if (i % 2 == 0) else win_size // 2, mlp_ratio=mlp_ratio,
+                                  qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                                  drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+                                  norm_layer=norm_layer, token_projection=token_projection, token_mlp=token_mlp,
+                                  se_layer=se_layer)
+            for i in range(depth)])
+
+    def forward(self, x, mask=None, index_samples=None):
+        for i, blk in enumerate(self.blocks):
+            x = blk(x, mask, None if index_samples is None else index_samples[i])
+        return x
+
+
+class Uformer(nn.Module):
+    """My_model_1.py:955-1207.  ``forward(x[B,3,H,W], mask=None) -> [B,3,H,W]`` (H == W, multiple of 128)."""
+
+    def __init__(self, img_size=128, in_chans=3, embed_dim=32, depths=[2, 2, 2, 2, 2, 2, 2, 2, 2],
+                 num_heads=[1, 2, 4, 8, 16, 16, 8, 4, 2], win_size=8, mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm, patch_norm=True,
+                 use_checkpoint=False, token_projection='linear', token_mlp='ffn', se_layer=False,
+                 dowsample=Downsample, upsample=Upsample, **kwargs):
+        super().__init__()
+        self.num_enc_layers = len(depths) // 2
+        self.num_dec_layers = len(depths) // 2
+        self.embed_dim, self.patch_norm, self.mlp_ratio = embed_dim, patch_norm, mlp_ratio
+        self.token_projection, self.mlp, self.win_size, self.reso = token_projection, token_mlp, win_size, img_size
+        self.depths = list(depths)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+
+        enc_dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths[:self.num_enc_layers]))]
+        conv_dpr = [drop_path_rate] * depths[4]
+        dec_dpr = enc_dpr[::-1]
+
+        self.input_proj = InputProj(in_channel=in_chans, out_channel=embed_dim, kernel_size=3, stride=1,
+                                    act_layer=nn.LeakyReLU)
+        self.output_proj = OutputProj(in_channel=2 * embed_dim, out_channel=in_chans, kernel_size=3, stride=1)
+
+        def layer(mult, res_div, i, dpr):
+            return BasicUformerLayer(dim=embed_dim * mult, output_dim=embed_dim * mult,
+                                     input_resolution=(img_size // res_div, img_size // res_div), depth=depths[i],
+                                     num_heads=num_heads[i], win_size=win_size, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                                     qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate, drop_path=dpr,
+                                     norm_layer=norm_layer, use_checkpoint=use_checkpoint,
+                                     token_projection=token_projection, token_mlp=token_mlp, se_layer=se_layer)
+
+        d = depths
+        self.encoderlayer_0 = layer(1, 1, 0, enc_dpr[sum(d[:0]):sum(d[:1])])
+        self.dowsample_0 = dowsample(embed_dim, embed_dim * 2)
+        self.encoderlayer_1 = layer(2, 2, 1, enc_dpr[sum(d[:1]):sum(d[:2])])
+        self.dowsample_1 = dowsample(embed_dim * 2, embed_dim * 4)
+        self.encoderlayer_2 = layer(4, 4, 2, enc_dpr[sum(d[:2]):sum(d[:3])])
+        self.dowsample_2 = dowsample(embed_dim * 4, embed_dim * 8)
+        self.encoderlayer_3 = layer(8, 8, 3, enc_dpr[sum(d[:3]):sum(d[:4])])
+        self.dowsample_3 = dowsample(embed_dim * 8, embed_dim * 16)
+        self.conv = layer(16, 16, 4, conv_dpr)
+        self.upsample_0 = upsample(embed_dim * 16, embed_dim * 8)
+        self.decoderlayer_0 = layer(16, 8, 5, dec_dpr[:d[5]])
+        self.upsample_1 = upsample(embed_dim * 16, embed_dim * 4)
+        self.decoderlayer_1 = layer(8, 4, 6, dec_dpr[sum(d[5:6]):sum(d[5:7])])
+        self.upsample_2 = upsample(embed_dim * 8, embed_dim * 2)
+        self.decoderlayer_2 = layer(4, 2, 7, dec_dpr[sum(d[5:7]):sum(d[5:8])])
+        self.upsample_3 = upsample(embed_dim * 4, embed_dim)
+        self.decoderlayer_3 = layer(2, 1, 8, dec_dpr[sum(d[5:8]):sum(d[5:9])])
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        """My_model_1.py:1149-1156."""
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'absolute_pos_embed'}
+
+    @torch.jit.ignore
+    def no_weight_decay_keywords(self):
+        return {'relative_position_bias_table'}
+
+    def extra_repr(self) -> str:
+        return (f"embed_dim={self.embed_dim}, token_projection={self.token_projection}, "
+                f"token_mlp={self.mlp},win_size={self.win_size}")
+
+    def draw_index_samples(self):
+        """The 18 (sum(depths)) draws of attn.py:91 in module execution order; one stacked CPU tensor."""
+        return torch.stack([draw_index_sample(64, 64) for _ in range(sum(self.depths))])
+
+    def forward(self, x, mask=None, index_samples=None):
+        if index_samples is None:
+            index_samples = self.draw_index_samples()
+        idx = index_samples.to(device=x.device, dtype=torch.int32, non_blocking=True)
+        d = self.depths
+        offs = [sum(d[:i]) for i in range(len(d) + 1)]
+        sl = lambda i: idx[offs[i]:offs[i + 1]]
+
+        y = self.pos_drop(self.input_proj(x))
+        conv0 = self.encoderlayer_0(y, mask, sl(0))
+        pool0 = self.dowsample_0(conv0)
+        conv1 = self.encoderlayer_1(pool0, mask, sl(1))
+        pool1 = self.dowsample_1(conv1)
+        conv2 = self.encoderlayer_2(pool1, mask, sl(2))
+        pool2 = self.dowsample_2(conv2)
+        conv3 = self.encoderlayer_3(pool2, mask, sl(3))
+        pool3 = self.dowsample_3(conv3)
+        conv4 = self.conv(pool3, mask, sl(4))
+        up0 = self.upsample_0(conv4)
+        deconv0 = self.decoderlayer_0(torch.cat([up0, conv3], -1), mask, sl(5))
+        up1 = self.upsample_1(deconv0)
+        deconv1 = self.decoderlayer_1(torch.cat([up1, conv2], -1), mask, sl(6))
+        up2 = self.upsample_2(deconv1)
+        deconv2 = self.decoderlayer_2(torch.cat([up2, conv1], -1), mask, sl(7))
+        up3 = self.upsample_3(deconv2)
+        deconv3 = self.decoderlayer_3(torch.cat([up3, conv0], -1), mask, sl(8))
+        y = self.output_proj(deconv3)
+        return x + y.to(x.dtype)

@@ -1,0 +1,82 @@
+"""CPU: the numpy oracle is pinned against the golden vectors generated from the UNMODIFIED reference
+(oracle/make_golden.py, run in the build container)."""
+import numpy as np
+import pytest
+
+from oracle import lewin_oracle as O
+from tests.util import BLOCK_FIXTURES, load_fixture
+
+
+@pytest.mark.parametrize("name", BLOCK_FIXTURES)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_oracle_forward_backward_matches_reference(name, dtype):
+    fx = load_fixture(name)
+    p = O.as_dtype(fx["params"], dtype)
+    x = fx["x"].astype(dtype)
+    out, aux = O.lewin_block(x, p, fx["shift"], fx["idx"], fx.get("input_mask"), True, fx.get("drop_scale"),
+                             return_aux=True)
+    same = np.array_equal(aux["top"], fx["top"])
+    if not same:   # only near-tie rows may differ
+        bad = (aux["top"] != fx["top"]).any(-1)
+        assert (aux["rel_gap"][bad] < 1e-5).all()
+        out = O.lewin_block(x, p, fx["shift"], fx["idx"], fx.get("input_mask"), True, fx.get("drop_scale"), top=fx["top"])
+    scale = max(1.0, np.abs(fx["out"]).max())
+    assert np.abs(out - fx["out"]).max() < 2e-4 * scale
+    dx, g = O.lewin_block_bwd(fx["dout"].astype(dtype), x, p, fx["shift"], fx["idx"], fx.get("input_mask"), True,
+                              fx.get("drop_scale"), top=fx["top"])
+    assert np.abs(dx - fx["dx"]).max() < 1e-3 * np.abs(fx["dx"]).max()
+    gscale = max(np.abs(v).max() for v in fx["grads"].values())
+    assert sorted(g) == sorted(fx["grads"]) == sorted(O.GRAD_KEYS)
+    for k in O.GRAD_KEYS:
+        ref = fx["grads"][k]
+        assert np.abs(g[k] - ref).max() < 1e-3 * max(np.abs(ref).max(), 1e-4 * gscale), k
+
+
+def test_prob_sizes():
+    assert O.prob_sizes(64, 64) == (25, 25)      # attn.py:310-315
+
+
+def test_shift_mask_only_on_last_window_row_and_column():
+    m = O.shift_attn_mask(32, 32, 8, 4)
+    nz = np.abs(m).reshape(16, -1).sum(1) > 0
+    expect = np.array([(w // 4 == 3) or (w % 4 == 3) for w in range(16)])
+    assert np.array_equal(nz, expect)
+    assert set(np.unique(m)) <= {0.0, -100.0}
+
+
+def test_mask_none_equals_shift0_and_window_permutation_equivariance():
+    rng = np.random.default_rng(0)
+    p = O.random_block_params(32, 1, rng, dtype=np.float64)
+    idx = rng.integers(0, 64, (64, 25))
+    xw = rng.standard_normal((6, 64, 32))
+    out = O.window_attention(xw, p, None, idx)
+    perm = rng.permutation(6)
+    out_p = O.window_attention(xw[perm], p, None, idx)
+    assert np.allclose(out[perm], out_p, atol=1e-12)
+    zero_mask = np.zeros((3, 64, 64))
+    assert np.allclose(O.window_attention(xw, p, zero_mask, idx), out, atol=1e-12)
+
+
+def test_numeric_gradient_spot_check():
+    """Finite differences on the fp64 oracle at a few coordinates (independent of the reference)."""
+    rng = np.random.default_rng(3)
+    C, nH, hw = 32, 1, 8
+    p = O.random_block_params(C, nH, rng, dtype=np.float64)
+    idx = rng.integers(0, 64, (64, 25))
+    x = rng.standard_normal((1, hw * hw, C))
+    dout = rng.standard_normal(x.shape)
+    _, aux = O.lewin_block(x, p, 0, idx, return_aux=True)
+    top = aux["top"]
+    dx, g = O.lewin_block_bwd(dout, x, p, 0, idx, top=top)
+    eps = 1e-6
+    for (i, j) in [(3, 5), (40, 17), (63, 31)]:
+        xp = x.copy(); xp[0, i, j] += eps
+        xm = x.copy(); xm[0, i, j] -= eps
+        num = ((O.lewin_block(xp, p, 0, idx, top=top) - O.lewin_block(xm, p, 0, idx, top=top)) * dout).sum() / (2 * eps)
+        assert abs(num - dx[0, i, j]) < 1e-5 * max(1.0, abs(num))
+    k = "attn.relative_position_bias_table"
+    for r in (0, 112, 224):
+        pp = dict(p); pp[k] = p[k].copy(); pp[k][r, 0] += eps
+        pm = dict(p); pm[k] = p[k].copy(); pm[k][r, 0] -= eps
+        num = ((O.lewin_block(x, pp, 0, idx, top=top) - O.lewin_block(x, pm, 0, idx, top=top)) * dout).sum() / (2 * eps)
+        assert abs(num - g[k][r, 0]) < 1e-5 * max(1.0, abs(num))

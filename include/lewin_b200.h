@@ -37,6 +37,7 @@ extern "C" {
 #endif
 
 typedef struct CUstream_st* lewin_stream_t; /* == cudaStream_t */
+typedef struct CUevent_st*  lewin_event_t;  /* == cudaEvent_t  */
 
 #define LEWIN_ABI_VERSION 1
 
@@ -101,7 +102,18 @@ typedef struct {
     void*    qkv;                  /* [B_*64, 3C] activations dtype */
     void*    ctx;                  /* [B_*64, C]  activations dtype */
     uint8_t* top;                  /* [B_, nH, 25] selected query indices (M_top, attn.py:122), by descending M */
+
+    /* optional per-kernel timing: caller-owned events, 2 per kernel (begin, end) recorded on `stream`
+     * around each launch, in the order LEWIN_ATTN_K_*; NULL = off */
+    lewin_event_t* timing;
 } LewinAttnFwdArgs;
+
+#define LEWIN_ATTN_K_LNSTATS 0
+#define LEWIN_ATTN_K_CNT     1
+#define LEWIN_ATTN_K_QKV     2
+#define LEWIN_ATTN_K_CORE    3
+#define LEWIN_ATTN_K_OUT     4
+#define LEWIN_ATTN_NKERNELS  5
 
 int lewin_attn_fwd_f32 (const LewinAttnFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 int lewin_attn_fwd_bf16(const LewinAttnFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
@@ -166,7 +178,15 @@ typedef struct {
     void* h2;                      /* [B*H*W, hidden] GELU(dwconv) */
     void* a1;                      /* pre-GELU linear1 output (only if save_for_backward) */
     void* a2;                      /* pre-GELU dwconv output  (only if save_for_backward) */
+
+    lewin_event_t* timing;         /* optional, 2 events per kernel in the order LEWIN_LEFF_K_*; NULL = off */
 } LewinLeffFwdArgs;
+
+#define LEWIN_LEFF_K_LNSTATS 0
+#define LEWIN_LEFF_K_FC1     1
+#define LEWIN_LEFF_K_DWCONV  2
+#define LEWIN_LEFF_K_FC2     3
+#define LEWIN_LEFF_NKERNELS  4
 
 int lewin_leff_fwd_f32 (const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 int lewin_leff_fwd_bf16(const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
@@ -192,6 +212,7 @@ size_t lewin_leff_bwd_workspace_bytes(const LewinLeffBwdArgs* a, int dtype);
 
 /* Library / build identification. */
 int         lewin_abi_version(void);     /* == LEWIN_ABI_VERSION */
+long long   lewin_launch_count(void);    /* kernels launched by this library in this process (diagnostic counter) */
 const char* lewin_build_info(void);      /* "sm_100a nvcc <ver> ..." */
 const char* lewin_error_string(int code);/* text for a negative LEWIN_E_* code */
 

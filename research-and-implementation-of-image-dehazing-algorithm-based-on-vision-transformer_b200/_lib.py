@@ -27,6 +27,7 @@ class LewinAttnFwdArgs(C.Structure):
         ("rpb_table", c_ptr), ("rpb_dense", c_ptr), ("index_sample", c_ptr), ("mask", c_ptr),
         ("drop_scale", c_ptr),
         ("qkv", c_ptr), ("ctx", c_ptr), ("top", c_ptr),
+        ("timing", c_ptr),
     ]
 
 
@@ -55,6 +56,7 @@ class LewinLeffFwdArgs(C.Structure):
         ("w1", c_ptr), ("b1", c_ptr), ("w_dw", c_ptr), ("b_dw", c_ptr), ("w2", c_ptr), ("b2", c_ptr),
         ("drop_scale", c_ptr),
         ("h1", c_ptr), ("h2", c_ptr), ("a1", c_ptr), ("a2", c_ptr),
+        ("timing", c_ptr),
     ]
 
 
@@ -74,7 +76,7 @@ EXPORTS = (
     "lewin_attn_fwd_workspace_bytes", "lewin_attn_bwd_workspace_bytes",
     "lewin_leff_fwd_workspace_bytes", "lewin_leff_bwd_workspace_bytes",
     "lewin_probsparse_core_fwd_f32", "lewin_probsparse_core_fwd_bf16", "lewin_probsparse_core_fwd_workspace_bytes",
-    "lewin_abi_version", "lewin_build_info", "lewin_error_string",
+    "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count",
 )
 
 ABI_VERSION = 1
@@ -104,6 +106,7 @@ def load():
         ws.argtypes = [C.POINTER(args_t), C.c_int]
         ws.restype = C.c_size_t
     lib.lewin_abi_version.restype = C.c_int
+    lib.lewin_launch_count.restype = C.c_longlong
     lib.lewin_build_info.restype = C.c_char_p
     lib.lewin_error_string.argtypes = [C.c_int]
     lib.lewin_error_string.restype = C.c_char_p

@@ -7,6 +7,8 @@
 #include "probsparse_core.cuh"
 #include "backward.cuh"
 
+#include <atomic>
+
 using namespace lewin;
 
 namespace {
@@ -26,6 +28,19 @@ inline int device_info(DeviceInfo* d) {
     if (e != cudaSuccess) return static_cast<int>(e);
     return d->cc_major == 10 ? 0 : LEWIN_E_ARCH;
 }
+
+std::atomic<long long> g_launches{0};   // diagnostic only (lewin_launch_count)
+
+// Optional per-kernel timing with caller-owned events (LewinAttnFwdArgs::timing).
+struct KTimer {
+    lewin_event_t* ev;
+    cudaStream_t st;
+    void begin(int k) const { if (ev) cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev[2 * k]), st); }
+    void end(int k) const {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (ev) cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev[2 * k + 1]), st);
+    }
+};
 
 #define CK(expr)                                         \
     do {                                                 \
@@ -78,9 +93,16 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     WinMap map{a->H, a->W, a->W / 8, nWin, a->shift};
     const T* x = static_cast<const T*>(a->x);
 
-    if (!a->windowed) CK(launch_ln_stats<T>(x, tokens, C, mean, rstd, stream));
+    const KTimer kt{a->timing, stream};
+    if (!a->windowed) {
+        kt.begin(LEWIN_ATTN_K_LNSTATS);
+        CK(launch_ln_stats<T>(x, tokens, C, mean, rstd, stream));
+        kt.end(LEWIN_ATTN_K_LNSTATS);
+    }
+    kt.begin(LEWIN_ATTN_K_CNT);
     build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
     CK(cudaGetLastError());
+    kt.end(LEWIN_ATTN_K_CNT);
 
     {   // q | k | v projections (attn.py:420-422) with LN1 + roll + window_partition as the A prologue
         GemmArgs<T> g{};
@@ -91,7 +113,9 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         if (!a->windowed) { g.mean = mean; g.rstd = rstd; g.ln_w = a->ln_w; g.ln_b = a->ln_b; }
         g.mapA = a->windowed ? 0 : 1; g.mapY = 0; g.map = map;
         g.tokens_per_image = a->H * a->W;
+        kt.begin(LEWIN_ATTN_K_QKV);
         CK((launch_gemm<T, EPI_BIAS>(g, stream)));
+        kt.end(LEWIN_ATTN_K_QKV);
     }
     {   // ProbSparse core (attn.py:287-342)
         CoreFwdArgs<T> c{};
@@ -106,7 +130,9 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         c.use_rpb = a->use_rpb;
         c.shift = (a->analytic_shift_mask && !a->windowed) ? a->shift : 0;
         c.H = a->H; c.W = a->W; c.nWw = a->W / 8; c.nWin = nWin;
+        kt.begin(LEWIN_ATTN_K_CORE);
         CK(launch_core_fwd<T>(c, di.sms, stream));
+        kt.end(LEWIN_ATTN_K_CORE);
     }
     {   // out projection (attn.py:456) + window_reverse + un-roll + DropPath scale + residual
         GemmArgs<T> g{};
@@ -116,12 +142,14 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.M = tokens; g.N = C; g.K = C;
         g.mapA = 0; g.mapY = a->windowed ? 0 : 1; g.map = map;
         g.tokens_per_image = a->H * a->W;
+        kt.begin(LEWIN_ATTN_K_OUT);
         if (a->windowed) {
             CK((launch_gemm<T, EPI_BIAS>(g, stream)));
         } else {
             g.R = x; g.drop_scale = a->drop_scale;
             CK((launch_gemm<T, EPI_BIAS_RESID>(g, stream)));
         }
+        kt.end(LEWIN_ATTN_K_OUT);
     }
     return 0;
 }
@@ -152,6 +180,7 @@ int core_only_fwd(const LewinCoreFwdArgs* a, void* ws, size_t ws_bytes, cudaStre
     c.use_rpb = a->use_rpb;
     c.shift = 0; c.H = 8; c.W = 8; c.nWw = 1; c.nWin = 1;
     CK(launch_core_fwd<T>(c, di.sms, stream));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
     return 0;
 }
 
@@ -190,7 +219,12 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     const T* y = static_cast<const T*>(a->y);
     const bool save = a->save_for_backward != 0;
 
-    if (a->fused) CK(launch_ln_stats<T>(y, tokens, C, mean, rstd, stream));
+    const KTimer kt{a->timing, stream};
+    if (a->fused) {
+        kt.begin(LEWIN_LEFF_K_LNSTATS);
+        CK(launch_ln_stats<T>(y, tokens, C, mean, rstd, stream));
+        kt.end(LEWIN_LEFF_K_LNSTATS);
+    }
     {   // linear1 + GELU (My_model_1.py:508) with LN2 as the A prologue
         GemmArgs<T> g{};
         g.A = y; g.lda = C;
@@ -199,10 +233,14 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.M = tokens; g.N = Ch; g.K = C;
         if (a->fused) { g.mean = mean; g.rstd = rstd; g.ln_w = a->ln_w; g.ln_b = a->ln_b; }
         g.tokens_per_image = a->H * a->W;
+        kt.begin(LEWIN_LEFF_K_FC1);
         CK((launch_gemm<T, EPI_BIAS_GELU>(g, stream)));
+        kt.end(LEWIN_LEFF_K_FC1);
     }
+    kt.begin(LEWIN_LEFF_K_DWCONV);
     CK(launch_dwconv_gelu<T>(static_cast<const T*>(a->h1), static_cast<T*>(a->h2), save ? static_cast<T*>(a->a2) : nullptr,
                              a->w_dw, a->b_dw, a->B, a->H, a->W, Ch, stream));
+    kt.end(LEWIN_LEFF_K_DWCONV);
     {   // linear2 (My_model_1.py:529) + DropPath scale + residual (My_model_1.py:873)
         GemmArgs<T> g{};
         g.A = static_cast<const T*>(a->h2); g.lda = Ch;
@@ -210,12 +248,14 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.Y = static_cast<T*>(a->out); g.ldy = C;
         g.M = tokens; g.N = C; g.K = Ch;
         g.tokens_per_image = a->H * a->W;
+        kt.begin(LEWIN_LEFF_K_FC2);
         if (a->fused) {
             g.R = y; g.drop_scale = a->drop_scale;
             CK((launch_gemm<T, EPI_BIAS_RESID>(g, stream)));
         } else {
             CK((launch_gemm<T, EPI_BIAS>(g, stream)));
         }
+        kt.end(LEWIN_LEFF_K_FC2);
     }
     return 0;
 }
@@ -263,6 +303,7 @@ size_t lewin_attn_bwd_workspace_bytes(const LewinAttnBwdArgs* a, int dtype) { re
 size_t lewin_leff_bwd_workspace_bytes(const LewinLeffBwdArgs* a, int dtype) { return a ? lewin::leff_bwd_ws(a, dtype) : 0; }
 
 int lewin_abi_version(void) { return LEWIN_ABI_VERSION; }
+long long lewin_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* lewin_build_info(void) {
 #define LEWIN_STR2(x) #x

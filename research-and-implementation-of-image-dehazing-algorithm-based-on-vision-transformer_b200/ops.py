@@ -31,6 +31,11 @@ def _f32c(t):
     return t.contiguous()
 
 
+def ctypes_addr(arr):
+    import ctypes
+    return ctypes.cast(arr, ctypes.c_void_p).value
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -53,6 +58,46 @@ def prepare_index_sample(index_sample, device):
     if index_sample.dtype != torch.int32 or index_sample.device != device:
         index_sample = index_sample.to(device=device, dtype=torch.int32, non_blocking=True)
     return index_sample.contiguous()
+
+
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing through the ABI's `timing` field (used by bench.py).
+
+    with KernelTimer() as kt: ...forward...;  torch.cuda.synchronize();  kt.summary() ->
+    {(op, kernel): [ms, ...]} with the shape info of every launch in kt.launches."""
+
+    active = None
+    ATTN = ("ln_stats", "build_cnt", "gemm_qkv", "probsparse_core", "gemm_out")
+    LEFF = ("ln_stats", "gemm_fc1_gelu", "dwconv_gelu", "gemm_fc2")
+
+    def __init__(self):
+        self.launches = []     # (op, names, skip_first, info, events)
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def events_for(self, op, info, skip_first):
+        import ctypes
+        names = self.ATTN if op == "attn" else self.LEFF
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(names))]
+        for e in evs:
+            e.record()          # torch creates the cudaEvent lazily; force it so the handle is valid
+        arr = (ctypes.c_void_p * len(evs))(*[e.cuda_event for e in evs])
+        self.launches.append((op, names, skip_first, info, evs))
+        return arr
+
+    def summary(self):
+        out = []
+        for op, names, skip_first, info, evs in self.launches:
+            for k, name in enumerate(names):
+                if k == 0 and skip_first:
+                    continue
+                out.append((op, name, info, evs[2 * k].elapsed_time(evs[2 * k + 1])))
+        return out
 
 
 class _AttnFn(torch.autograd.Function):
@@ -83,6 +128,9 @@ class _AttnFn(torch.autograd.Function):
             w_out=_ptr(w_out_), b_out=_ptr(b_out_), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
             index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
             qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
+        if KernelTimer.active is not None:
+            tim = KernelTimer.active.events_for("attn", dict(tokens=tokens, C=C, nH=nH, dtype=dt), bool(windowed))
+            a.timing = ctypes_addr(tim)
         ws = _workspace(lib.lewin_attn_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_attn_fwd_{dt}")
         with torch.cuda.device(dev):
@@ -153,6 +201,9 @@ class _LeffFn(torch.autograd.Function):
             y=_ptr(y), out=_ptr(out), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w1=_ptr(w1_), b1=_ptr(b1_),
             w_dw=_ptr(wdw_), b_dw=_ptr(bdw_), w2=_ptr(w2_), b2=_ptr(b2_), drop_scale=_ptr(ds_),
             h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
+        if KernelTimer.active is not None:
+            tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt), not fused)
+            a.timing = ctypes_addr(tim)
         ws = _workspace(lib.lewin_leff_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_leff_fwd_{dt}")
         with torch.cuda.device(dev):

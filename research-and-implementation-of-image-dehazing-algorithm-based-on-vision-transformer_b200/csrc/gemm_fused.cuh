@@ -14,14 +14,14 @@
 
 namespace lewin {
 
-enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2 };
+enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_MUL_GELUGRAD = 3 };
 
 template <typename T>
 struct GemmArgs {
     const T* A;           // [rowsA, lda]
     long long lda;
     const float* Wt;      // [N, K] row-major (PyTorch Linear.weight)
-    const float* bias;    // [N]
+    const float* bias;    // [N] or null
     T* Y;                 // [rowsY, ldy]
     T* Y2;                // optional pre-activation copy (EPI_BIAS_GELU), may be null
     long long ldy;
@@ -37,8 +37,11 @@ struct GemmArgs {
     WinMap map;
     // residual epilogue
     const T* R;           // indexed like Y
-    const float* drop_scale;   // [B] or null
+    const float* drop_scale;   // [B] or null (EPI_BIAS_RESID: scales the GEMM result per sample)
     int tokens_per_image;
+    // backward helpers
+    const float* a_row_scale;  // [B] or null: A row (token) is multiplied by a_row_scale[token / tokens_per_image]
+    const T* aux;              // EPI_MUL_GELUGRAD: pre-activation, indexed like Y; result = acc * gelu'(aux)
 };
 
 constexpr int GEMM_BM = 128;
@@ -49,7 +52,7 @@ constexpr int GEMM_THREADS = 256;
 template <int BN>
 constexpr size_t gemm_smem_bytes() {
     return sizeof(float) * (2 * GEMM_BM * GEMM_LDS + 2 * BN * GEMM_LDS) + sizeof(long long) * 2 * GEMM_BM +
-           sizeof(float) * 3 * GEMM_BM;
+           sizeof(float) * 4 * GEMM_BM;
 }
 
 template <typename T, int BN, int EPI>
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_fused_kernel(const GemmArgs
     float* s_mean = reinterpret_cast<float*>(offY + GEMM_BM);
     float* s_rstd = s_mean + GEMM_BM;
     float* s_scale = s_rstd + GEMM_BM;
+    float* s_ascale = s_scale + GEMM_BM;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_fused_kernel(const GemmArgs
     for (int r = tid; r < GEMM_BM; r += GEMM_THREADS) {
         long long m = m0 + r;
         long long oa = -1, oy = -1;
-        float mu = 0.f, rs = 1.f, sc = 1.f;
+        float mu = 0.f, rs = 1.f, sc = 1.f, asc = 1.f;
         if (m < g.M) {
             long long tok = (g.mapA || g.mapY) ? g.map.token(m) : m;
             long long ra = g.mapA ? tok : m;
@@ -86,8 +90,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_fused_kernel(const GemmArgs
             oy = ry * g.ldy;
             if (has_ln) { mu = g.mean[ra]; rs = g.rstd[ra]; }
             if (EPI == EPI_BIAS_RESID && g.drop_scale) sc = g.drop_scale[ry / g.tokens_per_image];
+            if (g.a_row_scale) asc = g.a_row_scale[ra / g.tokens_per_image];
         }
-        offA[r] = oa; offY[r] = oy; s_mean[r] = mu; s_rstd[r] = rs; s_scale[r] = sc;
+        offA[r] = oa; offY[r] = oy; s_mean[r] = mu; s_rstd[r] = rs; s_scale[r] = sc; s_ascale[r] = asc;
     }
     __syncthreads();
 
@@ -112,6 +117,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_fused_kernel(const GemmArgs
             if (o >= 0) {
                 int k = kc * GEMM_BK + kq;
                 v = ld4(g.A + o + k);
+                if (g.a_row_scale) {
+                    const float asc = s_ascale[r];
+                    v.x *= asc; v.y *= asc; v.z *= asc; v.w *= asc;
+                }
                 if (has_ln) {
                     float mu = s_mean[r], rs = s_rstd[r];
                     float4 w = *reinterpret_cast<const float4*>(g.ln_w + k);
@@ -203,9 +212,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_fused_kernel(const GemmArgs
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int col = n0 + warp_n * (BN / 2) + j * 8 + 2 * tq;
-                float v0 = acc[i][j][half * 2 + 0] + g.bias[col];
-                float v1 = acc[i][j][half * 2 + 1] + g.bias[col + 1];
-                if (EPI == EPI_BIAS_GELU) {
+                float v0 = acc[i][j][half * 2 + 0];
+                float v1 = acc[i][j][half * 2 + 1];
+                if (g.bias) { v0 += g.bias[col]; v1 += g.bias[col + 1]; }
+                if (EPI == EPI_MUL_GELUGRAD) {
+                    const float2 pre = ld2(g.aux + oy + col);
+                    v0 *= gelu_erf_grad(pre.x);
+                    v1 *= gelu_erf_grad(pre.y);
+                } else if (EPI == EPI_BIAS_GELU) {
                     if (Act<T>::kIsBf16) { v0 = Act<T>::round(v0); v1 = Act<T>::round(v1); }
                     if (g.Y2) st2(g.Y2 + oy + col, v0, v1);
                     v0 = gelu_erf(v0);

@@ -1,0 +1,139 @@
+"""GPU parity of the LeWin block BACKWARD (C ABI path) against the reference autograd gradients stored in the
+golden fixtures, and against the numpy oracle's hand-derived backward on random shapes.
+Tolerance: 1e-3 of each gradient's scale (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lewin_oracle as O
+from tests.util import BLOCK_FIXTURES, TIE_TAU_F32, check_top, force_drop_scales, load_fixture, make_block
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+
+
+def _run_block_with_grads(blk, x, dout, idx, mask=None):
+    import lewin_b200.ops as ops
+    captured = {}
+    orig = ops.lewin_attn
+
+    def spy(*a, **k):
+        y, top = orig(*a, return_top=True, **k)
+        captured["top"] = top
+        return y
+
+    ops.lewin_attn = spy
+    try:
+        out = blk(x, mask, idx)
+    finally:
+        ops.lewin_attn = orig
+    out.backward(dout)
+    grads = {k: v.grad.detach().cpu().numpy() for k, v in blk.named_parameters() if v.grad is not None}
+    return out.detach().cpu().numpy(), x.grad.detach().cpu().numpy(), grads, captured["top"].cpu().numpy()
+
+
+def _compare(dx, grads, dx_ref, g_ref):
+    assert np.abs(dx - dx_ref).max() < RTOL * np.abs(dx_ref).max()
+    assert sorted(grads) == sorted(O.GRAD_KEYS)          # the 6 dead parameters get no gradient
+    gscale = max(np.abs(v).max() for v in g_ref.values())
+    for k in O.GRAD_KEYS:
+        ref = g_ref[k]
+        err = np.abs(grads[k] - ref).max()
+        assert err < RTOL * max(np.abs(ref).max(), 1e-3 * gscale), (k, err, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", BLOCK_FIXTURES)
+def test_block_backward_matches_reference_golden_f32(name):
+    fx = load_fixture(name)
+    dev = torch.device("cuda:0")
+    blk = make_block(fx, dev)
+    train = "drop_scale" in fx
+    blk.train(train)
+    if train:
+        force_drop_scales(blk, fx["drop_scale"], dev)
+    x = torch.from_numpy(fx["x"]).to(dev).requires_grad_(True)
+    mask = torch.from_numpy(fx["input_mask"]).to(dev) if "input_mask" in fx else None
+    out, dx, grads, top = _run_block_with_grads(blk, x, torch.from_numpy(fx["dout"]).to(dev), torch.from_numpy(fx["idx"]), mask)
+    _, aux = O.lewin_block(fx["x"].astype(np.float64), O.as_dtype(fx["params"], np.float64), fx["shift"], fx["idx"],
+                           fx.get("input_mask"), True, fx.get("drop_scale"), return_aux=True)
+    nbad, namb, nhard = check_top(top, fx["top"], aux["rel_gap"], TIE_TAU_F32)
+    assert nhard == 0
+    if nbad == 0:
+        _compare(dx, grads, fx["dx"], fx["grads"])
+    else:
+        dx_ref, g_ref = O.lewin_block_bwd(fx["dout"].astype(np.float64), fx["x"].astype(np.float64),
+                                          O.as_dtype(fx["params"], np.float64), fx["shift"], fx["idx"],
+                                          fx.get("input_mask"), True, fx.get("drop_scale"),
+                                          top=np.sort(top.astype(np.int64), -1))
+        _compare(dx, grads, dx_ref, g_ref)
+
+
+@pytest.mark.parametrize("C,nH,hw,B,shift", [(32, 1, 8, 2, 0), (32, 1, 24, 2, 4), (96, 3, 16, 1, 4),
+                                             (256, 8, 16, 2, 4), (512, 16, 8, 3, 0)])
+def test_block_backward_matches_oracle_f32(C, nH, hw, B, shift):
+    rng = np.random.default_rng(1000 + C + hw + shift)
+    p = O.random_block_params(C, nH, rng)
+    x = rng.standard_normal((B, hw * hw, C)).astype(np.float32)
+    dout = rng.standard_normal((B, hw * hw, C)).astype(np.float32)
+    idx = rng.integers(0, 64, size=(64, 25)).astype(np.int64)
+    dev = torch.device("cuda:0")
+    import lewin_b200 as L
+    blk = L.LeWinTransformerBlock(dim=C, input_resolution=(128, 128), num_heads=nH, win_size=8, shift_size=shift)
+    sd = blk.state_dict()
+    for k, v in p.items():
+        sd[k].copy_(torch.from_numpy(v))
+    blk = blk.to(dev).eval()
+    xs = torch.from_numpy(x).to(dev).requires_grad_(True)
+    out, dx, grads, top = _run_block_with_grads(blk, xs, torch.from_numpy(dout).to(dev), torch.from_numpy(idx))
+    p64 = O.as_dtype(p, np.float64)
+    _, aux = O.lewin_block(x.astype(np.float64), p64, shift, idx, return_aux=True)
+    nbad, namb, nhard = check_top(top, aux["top"], aux["rel_gap"], TIE_TAU_F32)
+    assert nhard == 0
+    dx_ref, g_ref = O.lewin_block_bwd(dout.astype(np.float64), x.astype(np.float64), p64, shift, idx,
+                                      top=np.sort(top.astype(np.int64), -1))
+    _compare(dx, grads, dx_ref, g_ref)
+
+
+def test_strict_dropin_modules_forward_backward_f32():
+    """WindowAttention.forward / LeFF.forward (the reference's module-level call sites) on pre-partitioned
+    windows, forward and backward, against the oracle."""
+    import lewin_b200 as L
+    rng = np.random.default_rng(5)
+    C, nH, B_ = 64, 2, 6
+    p = O.random_block_params(C, nH, rng)
+    dev = torch.device("cuda:0")
+    blk = L.LeWinTransformerBlock(dim=C, input_resolution=(128, 128), num_heads=nH, win_size=8, shift_size=4)
+    sd = blk.state_dict()
+    for k, v in p.items():
+        sd[k].copy_(torch.from_numpy(v))
+    blk = blk.to(dev)
+    xw = rng.standard_normal((B_, 64, C)).astype(np.float32)
+    dyw = rng.standard_normal((B_, 64, C)).astype(np.float32)
+    mask = np.where(rng.random((3, 64, 64)) < 0.2, -100.0, 0.0).astype(np.float32)
+    idx = rng.integers(0, 64, size=(64, 25)).astype(np.int64)
+    p64 = O.as_dtype(p, np.float64)
+    ref, aux = O.window_attention(xw.astype(np.float64), p64, mask.astype(np.float64), idx, return_aux=True)
+    xt = torch.from_numpy(xw).to(dev).requires_grad_(True)
+    out = blk.attn(xt, mask=torch.from_numpy(mask).to(dev), index_sample=torch.from_numpy(idx))
+    assert np.abs(out.detach().cpu().numpy() - ref).max() < 1e-3
+    out.backward(torch.from_numpy(dyw).to(dev))
+    dx_ref, g_ref = O.window_attention_bwd(dyw.astype(np.float64), xw.astype(np.float64), p64, mask.astype(np.float64), idx,
+                                           top=aux["top"])
+    assert np.abs(xt.grad.cpu().numpy() - dx_ref).max() < RTOL * np.abs(dx_ref).max()
+    for k, ref_g in g_ref.items():
+        got = dict(blk.named_parameters())[k].grad.cpu().numpy()
+        assert np.abs(got - ref_g).max() < RTOL * max(np.abs(ref_g).max(), 1e-3), k
+    # LeFF.forward
+    z = rng.standard_normal((2, 256, C)).astype(np.float32)
+    dz = rng.standard_normal((2, 256, C)).astype(np.float32)
+    ref = O.leff(z.astype(np.float64), p64)
+    zt = torch.from_numpy(z).to(dev).requires_grad_(True)
+    blk.zero_grad()
+    o = blk.mlp(zt)
+    assert np.abs(o.detach().cpu().numpy() - ref).max() < 1e-3
+    o.backward(torch.from_numpy(dz).to(dev))
+    dz_ref, g_ref = O.leff_bwd(dz.astype(np.float64), z.astype(np.float64), p64)
+    assert np.abs(zt.grad.cpu().numpy() - dz_ref).max() < RTOL * np.abs(dz_ref).max()
+    for k, ref_g in g_ref.items():
+        got = dict(blk.named_parameters())[k].grad.cpu().numpy()
+        assert np.abs(got - ref_g).max() < RTOL * max(np.abs(ref_g).max(), 1e-3), k

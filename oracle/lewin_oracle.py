@@ -28,6 +28,20 @@ WIN = 8
 N_TOK = WIN * WIN
 
 
+# --------------------------------------------------------------------------- bf16 emulation
+def rbf(x, on=True):
+    """Round-to-nearest-even to bfloat16 (returned in the input float dtype).  Used with ``bf16=True`` to
+    restate the rounding points of the reference under torch.autocast(cuda, bfloat16):
+    linear / matmul / conv outputs and their operands are bf16, layer_norm / softmax / sums are fp32."""
+    if not on:
+        return x
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    u = a.view(np.uint32)
+    r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    out = ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+    return out.astype(np.asarray(x).dtype) if np.asarray(x).dtype != np.float32 else out
+
+
 # --------------------------------------------------------------------------- basics
 def prob_sizes(L_K: int = N_TOK, L_Q: int = N_TOK, factor: int = 5):
     """U_part and u, attn.py:310-315 (both 25 for 8x8 windows)."""
@@ -126,13 +140,13 @@ def input_attn_mask(mask_img, H, W, ws, dtype=np.float32):
 
 
 # ------------------------------------------------------------------ ProbSparse attention
-def sparsity_measure(q, k, idx):
+def sparsity_measure(q, k, idx, bf16=False):
     """attn.py:88-117.  q,k [B_,nH,64,D]; idx [64,U] -> M [B_,nH,64].
 
     S~[n,t] = q_n . k_{idx[n,t]} (unscaled); M_n = max_t S~ - sum_t S~ / L_K (L_K = 64, not U)."""
     L_K = k.shape[2]
     k_sample = k[:, :, idx, :]                                # [B_,nH,64,U,D]  (attn.py:104)
-    qk_sample = np.einsum("bhnd,bhntd->bhnt", q, k_sample)     # attn.py:110
+    qk_sample = rbf(np.einsum("bhnd,bhntd->bhnt", q, k_sample), bf16)   # attn.py:110 (bf16 matmul output)
     return qk_sample.max(-1) - qk_sample.sum(-1) / L_K         # attn.py:117
 
 
@@ -149,7 +163,7 @@ def select_top(M, u):
     return top.astype(np.int64), rel_gap
 
 
-def prob_attention(q, k, v, rpb, mask, idx, use_rpb=True, top=None, return_aux=False):
+def prob_attention(q, k, v, rpb, mask, idx, use_rpb=True, top=None, return_aux=False, bf16=False):
     """ProbAttention.forward, attn.py:287-342 (with _prob_QK :71-152,
     _get_initial_context :154-176, _update_context :178-281).
 
@@ -161,16 +175,16 @@ def prob_attention(q, k, v, rpb, mask, idx, use_rpb=True, top=None, return_aux=F
     v = v.transpose(0, 2, 1, 3)                                # attn.py:301-303
     U_part, u = prob_sizes(L, L)
     assert idx.shape == (L, U_part)
-    M = sparsity_measure(q, k, idx)
+    M = sparsity_measure(q, k, idx, bf16)
     sel, rel_gap = select_top(M, u)
     if top is None:
         top = sel
     bi = np.arange(B_)[:, None, None]
     hi = np.arange(nH)[None, :, None]
     q_red = q[bi, hi, top]                                     # attn.py:129-131  [B_,nH,u,D]
-    scores = np.matmul(q_red, k.transpose(0, 1, 3, 2))          # attn.py:150
-    scores = scores * q.dtype.type(1.0 / math.sqrt(D))         # attn.py:327-329
-    ctx = np.broadcast_to(v.mean(2, keepdims=True), v.shape).copy()   # attn.py:168-172
+    scores = rbf(np.matmul(q_red, k.transpose(0, 1, 3, 2)), bf16)   # attn.py:150
+    scores = rbf(scores * q.dtype.type(1.0 / math.sqrt(D)), bf16)   # attn.py:327-329
+    ctx = np.broadcast_to(rbf(v.mean(2, keepdims=True), bf16), v.shape).copy()   # attn.py:168-172
     p1 = softmax(scores)                                       # attn.py:195  (first softmax)
     a = p1
     if use_rpb:                                                # attn.py:227-230
@@ -180,7 +194,7 @@ def prob_attention(q, k, v, rpb, mask, idx, use_rpb=True, top=None, return_aux=F
         wi = (np.arange(B_) % nW)[:, None, None]               # batch-major window order, attn.py:250
         a = a + mask[wi, top]
     p2 = softmax(a)                                            # attn.py:262/264 (second softmax)
-    ctx[bi, hi, top] = np.matmul(p2, v)                        # attn.py:271-272
+    ctx[bi, hi, top] = rbf(np.matmul(rbf(p2, bf16), v), bf16)  # attn.py:271-272 (autocast: P2 cast to bf16)
     out = np.ascontiguousarray(ctx.transpose(0, 2, 1, 3))      # attn.py:342
     if return_aux:
         return out, dict(M=M, top=top, rel_gap=rel_gap, p1=p1, p2=p2, q=q, k=k, v=v)
@@ -194,7 +208,7 @@ def rpb_from_table(table, ws=WIN):
     return np.ascontiguousarray(table[ri.reshape(-1)].reshape(n, n, -1).transpose(2, 0, 1))
 
 
-def window_attention(xw, p, mask, idx, use_rpb=True, top=None, return_aux=False):
+def window_attention(xw, p, mask, idx, use_rpb=True, top=None, return_aux=False, bf16=False):
     """WindowAttention.forward (My_model_1.py:400-415) -> AttentionLayer.forward (attn.py:385-461).
 
     xw [B_,64,C]; ``p`` holds the block parameters under their state_dict names."""
@@ -203,13 +217,14 @@ def window_attention(xw, p, mask, idx, use_rpb=True, top=None, return_aux=False)
     nH = table.shape[1]
     rpb = rpb_from_table(table)
     pre = "attn.ProbSpare."
-    x2 = xw.reshape(-1, C)
-    q = (x2 @ p[pre + "query_projection.weight"].T + p[pre + "query_projection.bias"]).reshape(B_, L, nH, -1)
-    k = (x2 @ p[pre + "key_projection.weight"].T + p[pre + "key_projection.bias"]).reshape(B_, L, nH, -1)
-    v = (x2 @ p[pre + "value_projection.weight"].T + p[pre + "value_projection.bias"]).reshape(B_, L, nH, -1)
-    res = prob_attention(q, k, v, rpb, mask, idx, use_rpb, top=top, return_aux=return_aux)
+    x2 = rbf(xw.reshape(-1, C), bf16)
+    lin = lambda a, n: rbf(a @ rbf(p[pre + n + ".weight"], bf16).T + rbf(p[pre + n + ".bias"], bf16), bf16)
+    q = lin(x2, "query_projection").reshape(B_, L, nH, -1)
+    k = lin(x2, "key_projection").reshape(B_, L, nH, -1)
+    v = lin(x2, "value_projection").reshape(B_, L, nH, -1)
+    res = prob_attention(q, k, v, rpb, mask, idx, use_rpb, top=top, return_aux=return_aux, bf16=bf16)
     ctx, aux = res if return_aux else (res, None)
-    out = ctx.reshape(-1, C) @ p[pre + "out_projection.weight"].T + p[pre + "out_projection.bias"]
+    out = lin(ctx.reshape(-1, C), "out_projection")
     out = out.reshape(B_, L, C)
     if return_aux:
         aux["ctx"] = ctx
@@ -231,15 +246,16 @@ def dwconv3x3(x, w, b):
     return out + b
 
 
-def leff(x, p, return_aux=False):
+def leff(x, p, return_aux=False, bf16=False):
     """LeFF.forward, My_model_1.py:496-534.  x [B,L,C] -> [B,L,C]."""
     B, L, C = x.shape
     hh = int(math.sqrt(L))
-    a1 = x.reshape(-1, C) @ p["mlp.linear1.0.weight"].T + p["mlp.linear1.0.bias"]      # :508
-    h1 = gelu(a1).reshape(B, hh, hh, -1)
-    a2 = dwconv3x3(h1, p["mlp.dwconv.0.weight"], p["mlp.dwconv.0.bias"])                # :517
-    h2 = gelu(a2)
-    out = h2.reshape(B * L, -1) @ p["mlp.linear2.0.weight"].T + p["mlp.linear2.0.bias"]  # :529
+    r = lambda t: rbf(t, bf16)
+    a1 = r(r(x.reshape(-1, C)) @ r(p["mlp.linear1.0.weight"]).T + r(p["mlp.linear1.0.bias"]))      # :508
+    h1 = r(gelu(a1)).reshape(B, hh, hh, -1)
+    a2 = r(dwconv3x3(h1, r(p["mlp.dwconv.0.weight"]), r(p["mlp.dwconv.0.bias"])))                   # :517
+    h2 = r(gelu(a2))
+    out = r(h2.reshape(B * L, -1) @ r(p["mlp.linear2.0.weight"]).T + r(p["mlp.linear2.0.bias"]))   # :529
     out = out.reshape(B, L, C)
     if return_aux:
         return out, dict(a1=a1.reshape(B, hh, hh, -1), h1=h1, a2=a2, h2=h2)
@@ -248,7 +264,7 @@ def leff(x, p, return_aux=False):
 
 # ------------------------------------------------------------------------ LeWin block
 def lewin_block(x, p, shift, idx, input_mask=None, use_rpb=True, drop_scale=None, top=None,
-                return_aux=False):
+                return_aux=False, bf16=False):
     """LeWinTransformerBlock.forward, My_model_1.py:785-875.
 
     x [B,L,C]; ``shift`` in {0,4}; ``input_mask`` [1,1,h,w] or None (test_in_any_resolution.py:106);
@@ -268,7 +284,7 @@ def lewin_block(x, p, shift, idx, input_mask=None, use_rpb=True, drop_scale=None
     if shift > 0:
         xn = np.roll(xn, (-shift, -shift), axis=(1, 2))                           # :846
     xw = window_partition(xn, ws).reshape(-1, ws * ws, C)                         # :851-852
-    res = window_attention(xw, p, attn_mask, idx, use_rpb, top=top, return_aux=return_aux)
+    res = window_attention(xw, p, attn_mask, idx, use_rpb, top=top, return_aux=return_aux, bf16=bf16)
     aw, aux = res if return_aux else (res, None)
     sx = window_reverse(aw.reshape(-1, ws, ws, C), ws, H, W)                      # :861
     if shift > 0:
@@ -276,9 +292,9 @@ def lewin_block(x, p, shift, idx, input_mask=None, use_rpb=True, drop_scale=None
     a = sx.reshape(B, L, C)
     s0 = dt(1.0) if drop_scale is None else np.asarray(drop_scale[0], dtype=x.dtype)[:, None, None]
     s1 = dt(1.0) if drop_scale is None else np.asarray(drop_scale[1], dtype=x.dtype)[:, None, None]
-    y = x + s0 * a                                                                # :872
+    y = rbf(x + s0 * a, bf16)                                                     # :872
     z = layer_norm(y, p["norm2.weight"], p["norm2.bias"])
-    out = y + s1 * leff(z, p)                                                     # :873
+    out = rbf(y + s1 * leff(z, p, bf16=bf16), bf16)                               # :873
     if return_aux:
         aux["y"] = y
         aux["mask"] = attn_mask

@@ -36,8 +36,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const T* __restrict
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) wk[i][t] = __ldg(w + (c + i) * 9 + t);
-    const float4 bz = *reinterpret_cast<const float4*>(bias + c);
+        for (int t = 0; t < 9; ++t) wk[i][t] = Act<T>::round(__ldg(w + (c + i) * 9 + t));   // autocast: conv weight/bias cast to bf16
+    float4 bz = *reinterpret_cast<const float4*>(bias + c);
+    bz.x = Act<T>::round(bz.x); bz.y = Act<T>::round(bz.y); bz.z = Act<T>::round(bz.z); bz.w = Act<T>::round(bz.w);
 
     const T* xb = x + static_cast<long long>(b) * H * W * Ch + c;
     auto ldpix = [&](int y, int xq) -> float4 {

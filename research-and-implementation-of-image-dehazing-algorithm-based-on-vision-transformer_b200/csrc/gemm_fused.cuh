@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_fused_kernel(const GemmArgs
                 const int col = n0 + warp_n * (BN / 2) + j * 8 + 2 * tq;
                 float v0 = acc[i][j][half * 2 + 0];
                 float v1 = acc[i][j][half * 2 + 1];
-                if (g.bias) { v0 += g.bias[col]; v1 += g.bias[col + 1]; }
+                if (g.bias) { v0 += Act<T>::round(g.bias[col]); v1 += Act<T>::round(g.bias[col + 1]); }   // autocast casts the bias too
                 if (EPI == EPI_MUL_GELUGRAD) {
                     const float2 pre = ld2(g.aux + oy + col);
                     v0 *= gelu_erf_grad(pre.x);

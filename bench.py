@@ -233,6 +233,15 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     agg = {}
+    if os.environ.get("LEWIN_BREAKDOWN") and rank == 0:
+        per = {}
+        for op, name, info, ms in kt.summary():
+            key = (name, info["C"], info["tokens"])
+            per[key] = per.get(key, 0.0) + ms / args.steps
+        for (name, C, tok), ms in sorted(per.items(), key=lambda kv: (kv[0][0], kv[0][1], kv[0][2])):
+            fl, by = kernel_work("", name, dict(tokens=tok, C=C, dtype=args.dtype))
+            print(f"[breakdown] {name:16s} C={C:4d} tokens={tok:8d} ms/step={ms:8.3f}  (2 blocks)  "
+                  f"{fl*2/ms/1e9:8.1f} TFLOP/s  {by*2/ms/1e6:8.1f} GB/s", file=sys.stderr)
     for op, name, info, ms in kt.summary():
         fl, by = kernel_work(op, name, info)
         a = agg.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))

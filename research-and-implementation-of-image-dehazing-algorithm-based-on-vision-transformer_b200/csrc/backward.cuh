@@ -11,6 +11,7 @@
 #include "../../include/lewin_b200.h"
 #include "common.cuh"
 #include "gemm_fused.cuh"
+#include "gemm_tc.cuh"
 #include "probsparse_core.cuh"
 
 namespace lewin {
@@ -822,7 +823,7 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.Y = dctx; g.ldy = C; g.M = tokens; g.N = C; g.K = C;
         g.mapA = mapped; g.mapY = 0; g.map = map; g.tokens_per_image = tpi;
         g.a_row_scale = f.windowed ? nullptr : f.drop_scale;
-        BCK((launch_gemm<T, EPI_BIAS>(g, st)));
+        BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
     }
     {   // dW_out += do^T ctx ; db_out += colsum(do)
         WgradArgs<T> w{};
@@ -856,7 +857,7 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.A = dqkv; g.lda = 3 * C; g.Wt = wqkvT; g.bias = nullptr;
         g.Y = f.windowed ? static_cast<T*>(a->dx) : dxh; g.ldy = C; g.M = tokens; g.N = C; g.K = 3 * C;
         g.mapA = 0; g.mapY = mapped; g.map = map; g.tokens_per_image = tpi;
-        BCK((launch_gemm<T, EPI_BIAS>(g, st)));
+        BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
     }
     if (!f.windowed)   // dx = dy + LN1_bwd(dxh)
         BCK(launch_ln_bwd<T>(dxh, x, dy, static_cast<T*>(a->dx), f.ln_w, a->d_ln_w, a->d_ln_b, tokens, C, sms, st));
@@ -915,7 +916,7 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.A = dout; g.lda = C; g.Wt = w2T; g.bias = nullptr;
         g.Y = dh2; g.ldy = Ch; g.M = tokens; g.N = Ch; g.K = C;
         g.tokens_per_image = tpi; g.a_row_scale = dscale;
-        BCK((launch_gemm<T, EPI_BIAS>(g, st)));
+        BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
     }
     // depthwise conv backward: da1 = conv^T(dh2 * gelu'(a2)) * gelu'(a1); dWdw, dbdw
     BCK(launch_dwconv_bwd<T>(dh2, static_cast<const T*>(f.a2), static_cast<const T*>(f.h1), static_cast<const T*>(f.a1),
@@ -933,7 +934,7 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.A = da1; g.lda = Ch; g.Wt = w1T; g.bias = nullptr;
         g.Y = f.fused ? dz : static_cast<T*>(a->dy); g.ldy = C; g.M = tokens; g.N = C; g.K = Ch;
         g.tokens_per_image = tpi;
-        BCK((launch_gemm<T, EPI_BIAS>(g, st)));
+        BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
     }
     if (f.fused)   // dy = dout + LN2_bwd(dz)
         BCK(launch_ln_bwd<T>(dz, y, dout, static_cast<T*>(a->dy), f.ln_w, a->d_ln_w, a->d_ln_b, tokens, C, sms, st));

@@ -1,0 +1,360 @@
+// tcgen05 (5th-gen tensor core) token GEMM for bf16 activations:  Y = epi( pro(A)[M,K] * W[N,K]^T + bias )
+//
+// Same contract, prologues and epilogues as gemm_fused_kernel (gemm_fused.cuh), Blackwell-native datapath:
+//   * A (tokens) and W (weights) tiles are staged in shared memory in the canonical K-major
+//     SWIZZLE_128B / SWIZZLE_64B UMMA layout by the CTA's threads (the LayerNorm + shift/window gather
+//     prologue and the fp32->bf16 weight cast happen on the way in, so no TMA descriptor is needed);
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) per 16-wide k-step,
+//     accumulating fp32 in TMEM; tcgen05.commit arrives on an mbarrier per smem stage (2-stage ring);
+//   * the epilogue reads the accumulator with tcgen05.ld.32x32b (one TMEM lane == one token row per thread),
+//     applies bias / exact GELU / DropPath scale + residual and writes bf16 rows (window_reverse + un-shift
+//     folded into the row address).
+// CTA = 128 threads, one 128 x BN output tile; smem <= 98 KB and TMEM <= 256 columns so two CTAs share an
+// SM and overlap each other's load / MMA / epilogue phases.
+#pragma once
+#include "common.cuh"
+#include "gemm_fused.cuh"
+
+#include <cstdlib>
+
+namespace lewin {
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, M=128
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread i of the warp gets lane (lane_base + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO | version=1 | layout
+template <int KC>   // KC = 64 -> SWIZZLE_128B (128-byte rows), KC = 32 -> SWIZZLE_64B (64-byte rows)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    constexpr uint64_t sbo = (KC == 64 ? 1024 : 512) >> 4;        // 8-row group stride
+    constexpr uint64_t layout = (KC == 64 ? 2 : 4);               // LayoutType::SWIZZLE_128B / SWIZZLE_64B
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// byte offset of 16-byte chunk `c` of row `r` inside a swizzled [rows x KC] bf16 tile
+template <int KC>
+__device__ __forceinline__ uint32_t swz_off(int r, int c) {
+    if (KC == 64) return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    return (r >> 3) * 512 + (r & 7) * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+}  // namespace tc
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 128;
+
+template <int BN, int KC>
+constexpr size_t tc_smem_bytes() {
+    return 1024 /*align slack*/ + 2 * (TC_BM * KC * 2) + 2 * (BN * KC * 2) + TC_BM * (2 * 8 + 3 * 4) + BN * 4 + 64;
+}
+
+template <int BN, int KC, int EPI>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv_bfloat16> g) {
+    using T = __nv_bfloat16;
+    constexpr int CPR = KC / 8;                       // 16-byte chunks per tile row
+    constexpr int A_STAGE = TC_BM * KC * 2;
+    constexpr int W_STAGE = BN * KC * 2;
+    constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* As = base;                         // [2][A_STAGE]
+    unsigned char* Ws = As + 2 * A_STAGE;             // [2][W_STAGE]
+    long long* offA = reinterpret_cast<long long*>(Ws + 2 * W_STAGE);
+    long long* offY = offA + TC_BM;
+    float* s_mean = reinterpret_cast<float*>(offY + TC_BM);
+    float* s_rstd = s_mean + TC_BM;
+    float* s_ascale = s_rstd + TC_BM;
+    float* s_bias = s_ascale + TC_BM;                 // [BN]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(s_bias + BN);   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long m0 = static_cast<long long>(blockIdx.x) * TC_BM;
+    const int n0 = blockIdx.y * BN;
+    const bool has_ln = g.mean != nullptr;
+
+    // ---- one-time setup
+    {
+        const int r = tid;
+        const long long m = m0 + r;
+        long long oa = -1, oy = -1;
+        float mu = 0.f, rs = 1.f, asc = 1.f;
+        if (m < g.M) {
+            const long long tok = (g.mapA || g.mapY) ? g.map.token(m) : m;
+            const long long ra = g.mapA ? tok : m, ry = g.mapY ? tok : m;
+            oa = ra * g.lda; oy = ry * g.ldy;
+            if (has_ln) { mu = g.mean[ra]; rs = g.rstd[ra]; }
+            if (g.a_row_scale) asc = g.a_row_scale[ra / g.tokens_per_image];
+        }
+        offA[r] = oa; offY[r] = oy; s_mean[r] = mu; s_rstd[r] = rs; s_ascale[r] = asc;
+        for (int i = tid; i < BN; i += TC_THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[n0 + i]) : 0.f;
+    }
+    if (tid == 0) {
+        tc::mbar_init(&mbar[0], 1);
+        tc::mbar_init(&mbar[1], 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    // ---- staging helpers (global -> registers -> swizzled smem)
+    constexpr int A_CH = TC_BM * CPR / TC_THREADS;    // chunks per thread per stage (8 for KC=64, 4 for KC=32)
+    constexpr int W_CH = BN * CPR / TC_THREADS;
+    uint4 areg[A_CH];
+    uint4 wreg[W_CH];
+    auto load_a = [&](int kc) {
+#pragma unroll
+        for (int i = 0; i < A_CH; ++i) {
+            const int c = tid + i * TC_THREADS;
+            const int r = c / CPR, ch = c % CPR;
+            const long long o = offA[r];
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (o >= 0) {
+                const int k = kc * KC + ch * 8;
+                v = *reinterpret_cast<const uint4*>(g.A + o + k);
+                if (has_ln || g.a_row_scale) {
+                    float f[8];
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(h[j]); f[2 * j] = t2.x; f[2 * j + 1] = t2.y; }
+                    if (g.a_row_scale) {
+                        const float asc = s_ascale[r];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] *= asc;
+                    }
+                    if (has_ln) {
+                        const float mu = s_mean[r], rs = s_rstd[r];
+                        const float4 w0 = *reinterpret_cast<const float4*>(g.ln_w + k);
+                        const float4 w1 = *reinterpret_cast<const float4*>(g.ln_w + k + 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(g.ln_b + k);
+                        const float4 b1 = *reinterpret_cast<const float4*>(g.ln_b + k + 4);
+                        f[0] = (f[0] - mu) * rs * w0.x + b0.x; f[1] = (f[1] - mu) * rs * w0.y + b0.y;
+                        f[2] = (f[2] - mu) * rs * w0.z + b0.z; f[3] = (f[3] - mu) * rs * w0.w + b0.w;
+                        f[4] = (f[4] - mu) * rs * w1.x + b1.x; f[5] = (f[5] - mu) * rs * w1.y + b1.y;
+                        f[6] = (f[6] - mu) * rs * w1.z + b1.z; f[7] = (f[7] - mu) * rs * w1.w + b1.w;
+                    }
+                    v.x = tc::pack_bf16(f[0], f[1]); v.y = tc::pack_bf16(f[2], f[3]);
+                    v.z = tc::pack_bf16(f[4], f[5]); v.w = tc::pack_bf16(f[6], f[7]);
+                }
+            }
+            areg[i] = v;
+        }
+    };
+    auto load_w = [&](int kc) {
+#pragma unroll
+        for (int i = 0; i < W_CH; ++i) {
+            const int c = tid + i * TC_THREADS;
+            const int r = c / CPR, ch = c % CPR;
+            const float* src = g.Wt + static_cast<long long>(n0 + r) * g.K + kc * KC + ch * 8;
+            const float4 a = *reinterpret_cast<const float4*>(src);
+            const float4 b = *reinterpret_cast<const float4*>(src + 4);
+            wreg[i] = make_uint4(tc::pack_bf16(a.x, a.y), tc::pack_bf16(a.z, a.w), tc::pack_bf16(b.x, b.y), tc::pack_bf16(b.z, b.w));
+        }
+    };
+    auto store_stage = [&](int s) {
+#pragma unroll
+        for (int i = 0; i < A_CH; ++i) {
+            const int c = tid + i * TC_THREADS;
+            *reinterpret_cast<uint4*>(As + s * A_STAGE + tc::swz_off<KC>(c / CPR, c % CPR)) = areg[i];
+        }
+#pragma unroll
+        for (int i = 0; i < W_CH; ++i) {
+            const int c = tid + i * TC_THREADS;
+            *reinterpret_cast<uint4*>(Ws + s * W_STAGE + tc::swz_off<KC>(c / CPR, c % CPR)) = wreg[i];
+        }
+    };
+    auto issue = [&](int kc, int s) {      // one elected thread
+        const uint64_t da = tc::make_desc<KC>(tc::smem_u32(As + s * A_STAGE));
+        const uint64_t db = tc::make_desc<KC>(tc::smem_u32(Ws + s * W_STAGE));
+#pragma unroll
+        for (int k16 = 0; k16 < KC / 16; ++k16)
+            tc::mma_bf16(tmem_d, da + 2 * k16, db + 2 * k16, IDESC, (kc > 0 || k16 > 0) ? 1u : 0u);
+        tc::mma_commit(&mbar[s]);
+    };
+
+    const int nk = g.K / KC;
+    for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc & 1;
+        load_a(kc);
+        load_w(kc);
+        if (kc >= 2) tc::mbar_wait(&mbar[s], ((kc - 2) >> 1) & 1);   // MMAs that read stage s have retired
+        store_stage(s);
+        tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            issue(kc, s);
+        }
+    }
+    tc::mbar_wait(&mbar[(nk - 1) & 1], ((nk - 1) >> 1) & 1);          // the last commit covers every MMA issued
+    tc::tc_fence_after();
+
+    // ---- epilogue: thread == TMEM lane == tile row
+    {
+        const int r = tid;
+        const long long oy = offY[r];
+        float sc = 1.f;
+        if (EPI == EPI_BIAS_RESID && g.drop_scale && oy >= 0) sc = g.drop_scale[(oy / g.ldy) / g.tokens_per_image];
+        const uint32_t lane_addr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tc::tmem_ld32(lane_addr + c0, v);
+            if (oy < 0) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
+            T* yrow = g.Y + oy + n0 + c0;
+            if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = Act<T>::round(v[j]);
+                if (g.Y2) {
+                    T* prow = g.Y2 + oy + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8)
+                        *reinterpret_cast<uint4*>(prow + j) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
+                                                                         tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (EPI == EPI_BIAS_RESID) {
+                const T* rrow = g.R + oy + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 rv = *reinterpret_cast<const uint4*>(rrow + j);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 t2 = __bfloat1622float2(h[q]);
+                        v[j + 2 * q] = t2.x + sc * Act<T>::round(v[j + 2 * q]);
+                        v[j + 2 * q + 1] = t2.y + sc * Act<T>::round(v[j + 2 * q + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(yrow + j) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
+                                                                 tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
+}
+
+template <int BN, int KC, int EPI>
+cudaError_t launch_gemm_tc_inst(const GemmArgs<__nv_bfloat16>& g, cudaStream_t stream) {
+    constexpr size_t smem = tc_smem_bytes<BN, KC>();
+    auto k = gemm_tc_kernel<BN, KC, EPI>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    dim3 grid(static_cast<unsigned>((g.M + TC_BM - 1) / TC_BM), g.N / BN);
+    k<<<grid, TC_THREADS, smem, stream>>>(g);
+    return cudaGetLastError();
+}
+
+template <int KC, int EPI>
+cudaError_t launch_gemm_tc_kc(const GemmArgs<__nv_bfloat16>& g, cudaStream_t stream) {
+    const int N = g.N;
+    if (N % 256 == 0) return launch_gemm_tc_inst<256, KC, EPI>(g, stream);
+    if (N % 192 == 0) return launch_gemm_tc_inst<192, KC, EPI>(g, stream);
+    if (N % 128 == 0) return launch_gemm_tc_inst<128, KC, EPI>(g, stream);
+    if (N % 96 == 0) return launch_gemm_tc_inst<96, KC, EPI>(g, stream);
+    if (N % 64 == 0) return launch_gemm_tc_inst<64, KC, EPI>(g, stream);
+    return launch_gemm_tc_inst<32, KC, EPI>(g, stream);
+}
+
+// bf16 GEMM dispatch: tcgen05 path (N % 32 == 0, K % 32 == 0 always hold for LeWin shapes)
+template <int EPI>
+cudaError_t launch_gemm_tc(const GemmArgs<__nv_bfloat16>& g, cudaStream_t stream) {
+    if (g.K % 64 == 0) return launch_gemm_tc_kc<64, EPI>(g, stream);
+    return launch_gemm_tc_kc<32, EPI>(g, stream);
+}
+
+// Dispatch used by the ABI: fp32 activations -> 3xTF32 mma.sync kernel; bf16 activations -> tcgen05 kernel
+// (LEWIN_NO_TCGEN05=1 in the environment selects the mma.sync kernel for A/B comparison).
+inline bool tcgen05_enabled() {
+    static const bool on = [] { const char* e = getenv("LEWIN_NO_TCGEN05"); return !(e && e[0] == '1'); }();
+    return on;
+}
+template <typename T, int EPI>
+cudaError_t launch_gemm_any(const GemmArgs<T>& g, cudaStream_t stream) {
+    if constexpr (Act<T>::kIsBf16) {
+        if (tcgen05_enabled()) return launch_gemm_tc<EPI>(g, stream);
+    }
+    return launch_gemm<T, EPI>(g, stream);
+}
+
+}  // namespace lewin

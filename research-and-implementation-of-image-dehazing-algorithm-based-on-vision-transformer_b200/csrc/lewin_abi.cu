@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "dwconv.cuh"
 #include "gemm_fused.cuh"
+#include "gemm_tc.cuh"
 #include "probsparse_core.cuh"
 #include "backward.cuh"
 
@@ -114,7 +115,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.mapA = a->windowed ? 0 : 1; g.mapY = 0; g.map = map;
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_ATTN_K_QKV);
-        CK((launch_gemm<T, EPI_BIAS>(g, stream)));
+        CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
         kt.end(LEWIN_ATTN_K_QKV);
     }
     {   // ProbSparse core (attn.py:287-342)
@@ -144,10 +145,10 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_ATTN_K_OUT);
         if (a->windowed) {
-            CK((launch_gemm<T, EPI_BIAS>(g, stream)));
+            CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
         } else {
             g.R = x; g.drop_scale = a->drop_scale;
-            CK((launch_gemm<T, EPI_BIAS_RESID>(g, stream)));
+            CK((launch_gemm_any<T, EPI_BIAS_RESID>(g, stream)));
         }
         kt.end(LEWIN_ATTN_K_OUT);
     }
@@ -234,7 +235,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         if (a->fused) { g.mean = mean; g.rstd = rstd; g.ln_w = a->ln_w; g.ln_b = a->ln_b; }
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_LEFF_K_FC1);
-        CK((launch_gemm<T, EPI_BIAS_GELU>(g, stream)));
+        CK((launch_gemm_any<T, EPI_BIAS_GELU>(g, stream)));
         kt.end(LEWIN_LEFF_K_FC1);
     }
     kt.begin(LEWIN_LEFF_K_DWCONV);
@@ -251,9 +252,9 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         kt.begin(LEWIN_LEFF_K_FC2);
         if (a->fused) {
             g.R = y; g.drop_scale = a->drop_scale;
-            CK((launch_gemm<T, EPI_BIAS_RESID>(g, stream)));
+            CK((launch_gemm_any<T, EPI_BIAS_RESID>(g, stream)));
         } else {
-            CK((launch_gemm<T, EPI_BIAS>(g, stream)));
+            CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
         }
         kt.end(LEWIN_LEFF_K_FC2);
     }
@@ -309,7 +310,7 @@ const char* lewin_build_info(void) {
 #define LEWIN_STR2(x) #x
 #define LEWIN_STR(x) LEWIN_STR2(x)
     return "lewin_b200 sm_100a; nvcc " LEWIN_STR(__CUDACC_VER_MAJOR__) "." LEWIN_STR(__CUDACC_VER_MINOR__)
-           "; mma.sync tf32 (3xTF32 for f32)";
+           "; f32: mma.sync 3xTF32; bf16: tcgen05.mma kind::f16 + TMEM";
 }
 
 const char* lewin_error_string(int code) {

@@ -142,9 +142,58 @@ def kernel_work(op, name, info):
         return 150.0 * t * C, 4 * t * C * s
     if name == "dwconv_gelu":
         return 72.0 * t * C, 8 * t * C * s
+    if name == "leff_fused":
+        return 2.0 * t * C * 4 * C * 2 + 72.0 * t * C, 2 * t * C * s + 8 * C * C * 4
     if name == "ln_stats":
         return 0.0, t * C * s
     return 0.0, 0.0
+
+
+LEVELS = [("enc0", 32, 128), ("enc1", 64, 64), ("enc2", 128, 32), ("enc3", 256, 16), ("bottleneck", 512, 8),
+          ("dec0", 512, 16), ("dec1", 256, 32), ("dec2", 128, 64), ("dec3", 64, 128)]
+
+
+def block_microbench(dev, dtype, batch=32, iters=5):
+    """Second half of BASELINE's metric: LeWin block forward and forward+backward microseconds per block, at the
+    training shapes of config 2 (batch 32 x 128^2 patches), one block per level, shift 4 (0 at the bottleneck)."""
+    import torch
+    import lewin_b200 as L
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    out = []
+    for name, C, hw in LEVELS:
+        torch.manual_seed(0)
+        blk = L.LeWinTransformerBlock(dim=C, input_resolution=(hw, hw), num_heads=C // 32, win_size=8,
+                                      shift_size=4 if hw > 8 else 0).to(dev)
+        x = torch.randn(batch, hw * hw, C, device=dev, dtype=tdt)
+        idx = torch.randint(64, (64, 25))
+        dy = torch.randn_like(x)
+
+        def fwd():
+            with torch.no_grad():
+                return blk(x, None, idx)
+
+        def fwd_bwd():
+            xr = x.detach().requires_grad_(True)
+            blk.zero_grad(set_to_none=True)
+            blk(xr, None, idx).backward(dy)
+
+        res = {}
+        for key, fn in (("fwd_us", fwd), ("fwd_bwd_us", fwd_bwd)):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[key] = e0.elapsed_time(e1) / iters * 1e3
+        out.append(dict(level=name, C=C, map=hw, windows=batch * (hw // 8) ** 2, **res))
+        del blk, x, dy
+    return dict(batch=batch, dtype=dtype, per_level=out,
+                mean_fwd_us=sum(o["fwd_us"] for o in out) / len(out),
+                mean_fwd_bwd_us=sum(o["fwd_bwd_us"] for o in out) / len(out))
 
 
 def main():
@@ -279,6 +328,7 @@ def main():
                     traffic=traffic, kernel=dom["kernel"], peak_source=peaks["source"],
                     note="aggregate over the launches of this kernel type in one step (all 18 blocks), CUDA events via ABI timing hook")
 
+    blocks = block_microbench(dev, args.dtype) if world == 1 else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sample = 24
@@ -303,6 +353,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "lewin_block_us": blocks,
         "kernels": kernels,
     }
     print(json.dumps(line), flush=True)

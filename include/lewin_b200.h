@@ -186,7 +186,12 @@ typedef struct {
 #define LEWIN_LEFF_K_FC1     1
 #define LEWIN_LEFF_K_DWCONV  2
 #define LEWIN_LEFF_K_FC2     3
-#define LEWIN_LEFF_NKERNELS  4
+#define LEWIN_LEFF_K_FUSED   4   /* single fused kernel (bf16 inference, C <= 128) replaces slots 0-3 */
+#define LEWIN_LEFF_NKERNELS  5
+
+/* 1 if lewin_leff_fwd_<dtype> will run the single fused kernel for these arguments (timing slot
+ * LEWIN_LEFF_K_FUSED), 0 if it runs the four-kernel pipeline (slots 0-3). */
+int lewin_leff_fwd_is_fused(const LewinLeffFwdArgs* a, int dtype);
 
 int lewin_leff_fwd_f32 (const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 int lewin_leff_fwd_bf16(const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);

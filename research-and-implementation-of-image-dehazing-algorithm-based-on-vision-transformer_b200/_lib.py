@@ -76,7 +76,7 @@ EXPORTS = (
     "lewin_attn_fwd_workspace_bytes", "lewin_attn_bwd_workspace_bytes",
     "lewin_leff_fwd_workspace_bytes", "lewin_leff_bwd_workspace_bytes",
     "lewin_probsparse_core_fwd_f32", "lewin_probsparse_core_fwd_bf16", "lewin_probsparse_core_fwd_workspace_bytes",
-    "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count",
+    "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count", "lewin_leff_fwd_is_fused",
 )
 
 ABI_VERSION = 1
@@ -106,6 +106,8 @@ def load():
         ws.argtypes = [C.POINTER(args_t), C.c_int]
         ws.restype = C.c_size_t
     lib.lewin_abi_version.restype = C.c_int
+    lib.lewin_leff_fwd_is_fused.argtypes = [C.POINTER(LewinLeffFwdArgs), C.c_int]
+    lib.lewin_leff_fwd_is_fused.restype = C.c_int
     lib.lewin_launch_count.restype = C.c_longlong
     lib.lewin_build_info.restype = C.c_char_p
     lib.lewin_error_string.argtypes = [C.c_int]

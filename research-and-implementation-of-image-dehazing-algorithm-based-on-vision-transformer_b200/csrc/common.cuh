@@ -117,6 +117,60 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
 }
 
+// GELU for bf16 outputs: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below a bf16 ulp) with one
+// MUFU.RCP and one MUFU.EX2 instead of the ~45-instruction erff; the fp32 path keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-z * z);      // erf(|x|/sqrt2)
+    return 0.5f * x + 0.5f * fabsf(x) * e;
+}
+
+// ---------------------------------------------------------------- exact bf16 GELU by table
+// In the bf16 path GELU always acts on a value that was just rounded to bf16 (the linear / conv output), and its
+// result is rounded to bf16 again, so it is a 16-bit -> 16-bit function.  Outside 2^-12 <= |x| < 16 the result is
+// 0.5*x (correction below a quarter ulp), x, or -0; inside, 16 exponents x 128 mantissas x 2 signs = 4096 entries
+// (8 KB) hold bf16(gelu_erf(x)) exactly as torch computes it (fp32 erf, one rounding).  A lookup costs ~8 ALU
+// instructions + one shared-memory load instead of ~45 (erff) — the element-wise GELUs, not the GEMMs, are the
+// instruction bottleneck of LeFF on B200.
+constexpr int kGeluTabSize = 4096;
+__device__ uint16_t g_gelu_tab[kGeluTabSize];
+
+__global__ void gelu_tab_init_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kGeluTabSize) return;
+    const uint32_t sign = (i >> 11) & 1, e = 115 + ((i >> 7) & 15), m = i & 127;
+    const float x = __uint_as_float((sign << 31) | (e << 23) | (m << 16));
+    g_gelu_tab[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf(x)));
+}
+inline cudaError_t launch_gelu_tab_init(cudaStream_t st) {       // idempotent; a few microseconds
+    gelu_tab_init_kernel<<<kGeluTabSize / 256, 256, 0, st>>>();
+    return cudaGetLastError();
+}
+__device__ __forceinline__ void gelu_tab_to_smem(uint16_t* dst, int tid, int nthreads) {
+    for (int i = tid; i < kGeluTabSize / 8; i += nthreads)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(g_gelu_tab)[i];
+}
+// bf16 bits of GELU(x) for x given as bf16 bits
+__device__ __forceinline__ uint32_t gelu_bits(const uint16_t* __restrict__ tab, uint32_t u) {
+    const uint32_t e = (u >> 7) & 0xFFu;
+    const uint32_t ec = min(max(e, 115u), 130u) - 115u;
+    const uint32_t idx = (ec << 7) | (u & 0x7Fu) | ((u & 0x8000u) >> 4);
+    uint32_t r = tab[idx];
+    if (e < 115u) r = (e > 1u) ? (u - 0x80u) : (u & 0x8000u);       // 0.5 * x (flush the last binade to signed zero)
+    if (e >= 131u) r = (u & 0x8000u) ? 0x8000u : u;                 // x, or -0 for large negative x
+    return r;
+}
+// GELU of a float that is rounded to bf16 first; returns the bf16-valued result as float
+__device__ __forceinline__ float gelu_tab(const uint16_t* __restrict__ tab, float x) {
+    const uint32_t u = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    return __uint_as_float(gelu_bits(tab, u) << 16);
+}
+
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {     // reduce over aligned groups of G lanes
 #pragma unroll

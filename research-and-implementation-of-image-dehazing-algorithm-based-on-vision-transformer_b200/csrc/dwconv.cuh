@@ -74,7 +74,11 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const T* __restrict
         }
         const long long o = (static_cast<long long>(b) * H * W + static_cast<long long>(y) * W + xx) * Ch + c;
         if (preact) st4(preact + o, acc);
-        st4(out + o, make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w)));
+        if (Act<T>::kIsBf16)
+            st4(out + o, make_float4(gelu_tab(g_gelu_tab, acc.x), gelu_tab(g_gelu_tab, acc.y), gelu_tab(g_gelu_tab, acc.z),
+                                     gelu_tab(g_gelu_tab, acc.w)));
+        else
+            st4(out + o, make_float4(gelu_erf(acc.x), gelu_erf(acc.y), gelu_erf(acc.z), gelu_erf(acc.w)));
 #pragma unroll
         for (int j = 0; j < 3; ++j) { win[0][j] = win[1][j]; win[1][j] = win[2][j]; }
     }

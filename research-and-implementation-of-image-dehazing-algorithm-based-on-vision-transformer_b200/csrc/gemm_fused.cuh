@@ -12,6 +12,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace lewin {
 
 enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_MUL_GELUGRAD = 3 };
@@ -237,29 +239,52 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_fused_kernel(const GemmArgs
 }
 
 // Per-token LayerNorm statistics (mean, 1/sqrt(var+eps)), biased variance, eps = 1e-5
-// (nn.LayerNorm, My_model_1.py:769/776).  One warp per row, two-pass from registers/L1.
-template <typename T>
+// (nn.LayerNorm, My_model_1.py:769/776).  G lanes per row (G = min(32, row bytes / 16)), 16-byte loads, so a warp
+// streams 512 contiguous bytes per load whatever C is; two-pass statistics from registers.  HBM-bound: C*sizeof(T)
+// bytes per token.
+template <typename T, int G>
 __global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, long long rows, int C,
                                                        float* __restrict__ mean, float* __restrict__ rstd) {
+    constexpr int EPL = 16 / sizeof(T);            // elements per 16-byte load
+    constexpr int RPW = 32 / G;                    // rows per warp
+    constexpr int MAXV = 4;                        // loads per lane: C <= G * EPL * MAXV
     const int lane = threadIdx.x & 31;
-    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const T* p = x + row * C;
+    const int sub = lane / G, gl = lane % G;
+    const long long warp_global = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long row = warp_global * RPW + sub;
+    const bool live = row < rows;
+    float v[MAXV][8];
     float s = 0.f;
-    for (int k = lane * 4; k < C; k += 128) {
-        float4 v = ld4(p + k);
-        s += (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int k = (gl + i * G) * EPL;
+        const bool ok = live && k < C;
+        if (sizeof(T) == 4) {
+            float4 t = ok ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + row * C + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+            v[i][4] = v[i][5] = v[i][6] = v[i][7] = 0.f;
+        } else {
+            uint4 t = ok ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * C + k) : make_uint4(0u, 0u, 0u, 0u);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[i][2 * j] = f.x; v[i][2 * j + 1] = f.y; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
     }
-    s = group_sum<32>(s);
+    s = group_sum<G>(s);
     const float mu = s / C;
     float q = 0.f;
-    for (int k = lane * 4; k < C; k += 128) {
-        float4 v = ld4(p + k);
-        float a = v.x - mu, b = v.y - mu, c = v.z - mu, d = v.w - mu;
-        q += (a * a + b * b) + (c * c + d * d);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int k = (gl + i * G) * EPL;
+        if (k < C) {
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) { const float d = v[i][j] - mu; q += d * d; }
+        }
     }
-    q = group_sum<32>(q);
-    if (lane == 0) {
+    q = group_sum<G>(q);
+    if (live && gl == 0) {
         mean[row] = mu;
         rstd[row] = rsqrtf(q / C + 1e-5f);
     }
@@ -287,10 +312,21 @@ cudaError_t launch_gemm(const GemmArgs<T>& g, cudaStream_t stream) {
 
 template <typename T>
 cudaError_t launch_ln_stats(const T* x, long long rows, int C, float* mean, float* rstd, cudaStream_t stream) {
+    constexpr int EPL = 16 / sizeof(T);
+    const int chunks = C / EPL;                 // 16-byte chunks per row (C % 32 == 0 => >= 4)
     const int wpb = 8;
-    const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
-    ln_stats_kernel<T><<<grid, wpb * 32, 0, stream>>>(x, rows, C, mean, rstd);
-    return cudaGetLastError();
+    auto go = [&](auto gtag) -> cudaError_t {
+        constexpr int G = decltype(gtag)::value;
+        const long long rows_per_block = static_cast<long long>(wpb) * (32 / G);
+        const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
+        ln_stats_kernel<T, G><<<grid, wpb * 32, 0, stream>>>(x, rows, C, mean, rstd);
+        return cudaGetLastError();
+    };
+    if (chunks > 128) return cudaErrorInvalidValue;      // C <= 32 lanes * 4 loads * EPL
+    if (chunks <= 4) return go(std::integral_constant<int, 4>{});
+    if (chunks <= 8) return go(std::integral_constant<int, 8>{});
+    if (chunks <= 16) return go(std::integral_constant<int, 16>{});
+    return go(std::integral_constant<int, 32>{});
 }
 
 }  // namespace lewin

@@ -108,15 +108,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }  // namespace tc
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;
 
 template <int BN, int KC>
 constexpr size_t tc_smem_bytes() {
-    return 1024 /*align slack*/ + 2 * (TC_BM * KC * 2) + 2 * (BN * KC * 2) + TC_BM * (2 * 8 + 3 * 4) + BN * 4 + 64;
+    return 1024 /*align slack*/ + 2 * (TC_BM * KC * 2) + 2 * (BN * KC * 2) + TC_BM * (2 * 8 + 3 * 4) + BN * 4 + 64 +
+           kGeluTabSize * 2;
 }
 
 template <int BN, int KC, int EPI>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv_bfloat16> g) {
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const GemmArgs<__nv_bfloat16> g) {
     using T = __nv_bfloat16;
     constexpr int CPR = KC / 8;                       // 16-byte chunks per tile row
     constexpr int A_STAGE = TC_BM * KC * 2;
@@ -137,6 +138,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv
     float* s_bias = s_ascale + TC_BM;                 // [BN]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(s_bias + BN);   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    uint16_t* gtab = reinterpret_cast<uint16_t*>(mbar + 4);          // EPI_BIAS_GELU only
+    if (EPI == EPI_BIAS_GELU) gelu_tab_to_smem(gtab, threadIdx.x, TC_THREADS);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long m0 = static_cast<long long>(blockIdx.x) * TC_BM;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv
     const bool has_ln = g.mean != nullptr;
 
     // ---- one-time setup
-    {
+    if (tid < TC_BM) {
         const int r = tid;
         const long long m = m0 + r;
         long long oa = -1, oy = -1;
@@ -157,8 +160,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv
             if (g.a_row_scale) asc = g.a_row_scale[ra / g.tokens_per_image];
         }
         offA[r] = oa; offY[r] = oy; s_mean[r] = mu; s_rstd[r] = rs; s_ascale[r] = asc;
-        for (int i = tid; i < BN; i += TC_THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[n0 + i]) : 0.f;
     }
+    for (int i = tid; i < BN; i += TC_THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[n0 + i]) : 0.f;
     if (tid == 0) {
         tc::mbar_init(&mbar[0], 1);
         tc::mbar_init(&mbar[1], 1);
@@ -171,8 +174,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv
     const uint32_t tmem_d = *tmem_slot;
 
     // ---- staging helpers (global -> registers -> swizzled smem)
-    constexpr int A_CH = TC_BM * CPR / TC_THREADS;    // chunks per thread per stage (8 for KC=64, 4 for KC=32)
-    constexpr int W_CH = BN * CPR / TC_THREADS;
+    constexpr int A_CH = TC_BM * CPR / TC_THREADS;    // chunks per thread per stage (4 for KC=64, 2 for KC=32)
+    constexpr int W_TOTAL = BN * CPR;
+    constexpr int W_CH = (W_TOTAL + TC_THREADS - 1) / TC_THREADS;
     uint4 areg[A_CH];
     uint4 wreg[W_CH];
     auto load_a = [&](int kc) {
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv
 #pragma unroll
         for (int i = 0; i < W_CH; ++i) {
             const int c = tid + i * TC_THREADS;
+            if (W_TOTAL % TC_THREADS != 0 && c >= W_TOTAL) break;
             const int r = c / CPR, ch = c % CPR;
             const float* src = g.Wt + static_cast<long long>(n0 + r) * g.K + kc * KC + ch * 8;
             const float4 a = *reinterpret_cast<const float4*>(src);
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv
 #pragma unroll
         for (int i = 0; i < W_CH; ++i) {
             const int c = tid + i * TC_THREADS;
+            if (W_TOTAL % TC_THREADS != 0 && c >= W_TOTAL) break;
             *reinterpret_cast<uint4*>(Ws + s * W_STAGE + tc::swz_off<KC>(c / CPR, c % CPR)) = wreg[i];
         }
     };
@@ -264,20 +270,33 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv
 
     // ---- epilogue: thread == TMEM lane == tile row
     {
-        const int r = tid;
+        const int r = (warp & 3) * 32 + (tid & 31);
+        const int half = warp >> 2;
         const long long oy = offY[r];
         float sc = 1.f;
         if (EPI == EPI_BIAS_RESID && g.drop_scale && oy >= 0) sc = g.drop_scale[(oy / g.ldy) / g.tokens_per_image];
-        const uint32_t lane_addr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+        const uint32_t lane_addr = tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
             float v[32];
             tc::tmem_ld32(lane_addr + c0, v);
             if (oy < 0) continue;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
             T* yrow = g.Y + oy + n0 + c0;
-            if (EPI == EPI_BIAS_GELU) {
+            if (EPI == EPI_BIAS_GELU && !g.Y2) {       // inference: bf16 bits in -> table -> bf16 bits out
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint32_t q[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const uint32_t in2 = tc::pack_bf16(v[j + 2 * h], v[j + 2 * h + 1]);
+                        q[h] = gelu_bits(gtab, in2 & 0xFFFFu) | (gelu_bits(gtab, in2 >> 16) << 16);
+                    }
+                    *reinterpret_cast<uint4*>(yrow + j) = make_uint4(q[0], q[1], q[2], q[3]);
+                }
+                continue;
+            } else if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = Act<T>::round(v[j]);
                 if (g.Y2) {
@@ -288,7 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const GemmArgs<__nv
                                                                          tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                for (int j = 0; j < 32; ++j) v[j] = gelu_tab(gtab, v[j]);
             } else if (EPI == EPI_BIAS_RESID) {
                 const T* rrow = g.R + oy + n0 + c0;
 #pragma unroll

@@ -5,6 +5,7 @@
 #include "dwconv.cuh"
 #include "gemm_fused.cuh"
 #include "gemm_tc.cuh"
+#include "leff_fused.cuh"
 #include "probsparse_core.cuh"
 #include "backward.cuh"
 
@@ -205,6 +206,12 @@ size_t leff_fwd_ws(const LewinLeffFwdArgs* a) {
     return 2 * align_up(tokens * sizeof(float), 256);
 }
 
+bool leff_use_fused(const LewinLeffFwdArgs* a, bool is_bf16) {
+    static const bool fused_on = [] { const char* e = getenv("LEWIN_NO_FUSED_LEFF"); return !(e && e[0] == '1'); }();
+    return is_bf16 && fused_on && a->fused && !a->save_for_backward && leff_fused_supported(a->C, a->hidden) &&
+           a->H % 8 == 0 && a->W % 8 == 0;
+}
+
 template <typename T>
 int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (int rc = check_leff(a)) return rc;
@@ -221,6 +228,22 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     const bool save = a->save_for_backward != 0;
 
     const KTimer kt{a->timing, stream};
+    if constexpr (Act<T>::kIsBf16) CK(launch_gelu_tab_init(stream));     // idempotent 8 KB table (common.cuh)
+    if constexpr (Act<T>::kIsBf16) {
+        // HBM-bound levels: one kernel, hidden activations stay on chip (leff_fused.cuh)
+        if (leff_use_fused(a, true)) {
+            LeffFusedArgs fa{};
+            fa.y = static_cast<const __nv_bfloat16*>(a->y);
+            fa.out = static_cast<__nv_bfloat16*>(a->out);
+            fa.ln_w = a->ln_w; fa.ln_b = a->ln_b; fa.w1 = a->w1; fa.b1 = a->b1;
+            fa.w_dw = a->w_dw; fa.b_dw = a->b_dw; fa.w2 = a->w2; fa.b2 = a->b2;
+            fa.drop_scale = a->drop_scale; fa.B = a->B; fa.H = a->H; fa.W = a->W;
+            kt.begin(LEWIN_LEFF_K_FUSED);
+            CK(launch_leff_fused(C, fa, stream));
+            kt.end(LEWIN_LEFF_K_FUSED);
+            return 0;
+        }
+    }
     if (a->fused) {
         kt.begin(LEWIN_LEFF_K_LNSTATS);
         CK(launch_ln_stats<T>(y, tokens, C, mean, rstd, stream));
@@ -278,6 +301,9 @@ int lewin_probsparse_core_fwd_bf16(const LewinCoreFwdArgs* a, void* ws, size_t n
     return core_only_fwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
 }
 size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs*, int) { return kTok * kTok; }
+int lewin_leff_fwd_is_fused(const LewinLeffFwdArgs* a, int dtype) {
+    return (a && check_leff(a) == 0 && leff_use_fused(a, dtype == LEWIN_DTYPE_BF16)) ? 1 : 0;
+}
 int lewin_leff_fwd_f32(const LewinLeffFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
     return leff_fwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
 }

@@ -68,10 +68,10 @@ class KernelTimer:
 
     active = None
     ATTN = ("ln_stats", "build_cnt", "gemm_qkv", "probsparse_core", "gemm_out")
-    LEFF = ("ln_stats", "gemm_fc1_gelu", "dwconv_gelu", "gemm_fc2")
+    LEFF = ("ln_stats", "gemm_fc1_gelu", "dwconv_gelu", "gemm_fc2", "leff_fused")
 
     def __init__(self):
-        self.launches = []     # (op, names, skip_first, info, events)
+        self.launches = []     # (op, names, live_slots, info, events)
 
     def __enter__(self):
         KernelTimer.active = self
@@ -80,23 +80,21 @@ class KernelTimer:
     def __exit__(self, *exc):
         KernelTimer.active = None
 
-    def events_for(self, op, info, skip_first):
+    def events_for(self, op, info, live_slots):
         import ctypes
         names = self.ATTN if op == "attn" else self.LEFF
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(names))]
         for e in evs:
             e.record()          # torch creates the cudaEvent lazily; force it so the handle is valid
         arr = (ctypes.c_void_p * len(evs))(*[e.cuda_event for e in evs])
-        self.launches.append((op, names, skip_first, info, evs))
+        self.launches.append((op, names, tuple(live_slots), info, evs))
         return arr
 
     def summary(self):
         out = []
-        for op, names, skip_first, info, evs in self.launches:
-            for k, name in enumerate(names):
-                if k == 0 and skip_first:
-                    continue
-                out.append((op, name, info, evs[2 * k].elapsed_time(evs[2 * k + 1])))
+        for op, names, live, info, evs in self.launches:
+            for k in live:
+                out.append((op, names[k], info, evs[2 * k].elapsed_time(evs[2 * k + 1])))
         return out
 
 
@@ -104,7 +102,7 @@ class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
                 drop_scale, geom):
-        B, H, W, nH, shift, windowed, use_rpb, analytic = geom
+        B, H, W, nH, shift, windowed, use_rpb, analytic, need_grad = geom
         lib = _lib.load()
         dt = _dtype_tag(x)
         x = x.contiguous()
@@ -112,7 +110,6 @@ class _AttnFn(torch.autograd.Function):
         tokens = B * H * W
         assert x.numel() == tokens * C, (x.shape, B, H, W, C)
         dev = x.device
-        need_grad = any(ctx.needs_input_grad)
         y = torch.empty_like(x)
         qkv = torch.empty((tokens, 3 * C), dtype=x.dtype, device=dev)
         cbuf = torch.empty((tokens, C), dtype=x.dtype, device=dev)
@@ -129,7 +126,8 @@ class _AttnFn(torch.autograd.Function):
             index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
             qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
         if KernelTimer.active is not None:
-            tim = KernelTimer.active.events_for("attn", dict(tokens=tokens, C=C, nH=nH, dtype=dt), bool(windowed))
+            tim = KernelTimer.active.events_for("attn", dict(tokens=tokens, C=C, nH=nH, dtype=dt),
+                                                (1, 2, 3, 4) if windowed else (0, 1, 2, 3, 4))
             a.timing = ctypes_addr(tim)
         ws = _workspace(lib.lewin_attn_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_attn_fwd_{dt}")
@@ -144,7 +142,7 @@ class _AttnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dtop):
         (x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense, idx, mask, ds, qkv, cbuf, top) = ctx.saved_tensors
-        B, H, W, nH, shift, windowed, use_rpb, analytic = ctx.geom
+        B, H, W, nH, shift, windowed, use_rpb, analytic, _ = ctx.geom
         lib = _lib.load()
         dt = ctx.dt
         dev = x.device
@@ -180,7 +178,7 @@ class _AttnFn(torch.autograd.Function):
 class _LeffFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom):
-        B, H, W, fused = geom
+        B, H, W, fused, need_grad = geom
         lib = _lib.load()
         dt = _dtype_tag(y)
         y = y.contiguous()
@@ -189,10 +187,14 @@ class _LeffFn(torch.autograd.Function):
         tokens = B * H * W
         assert y.numel() == tokens * C, (y.shape, B, H, W, C)
         dev = y.device
-        need_grad = any(ctx.needs_input_grad)
         out = torch.empty_like(y)
-        h1 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
-        h2 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
+        probe = _lib.LewinLeffFwdArgs(B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=int(need_grad),
+                                      y=1 << 8, out=1 << 8, ln_w=1 << 8, ln_b=1 << 8, w1=1 << 8, b1=1 << 8, w_dw=1 << 8,
+                                      b_dw=1 << 8, w2=1 << 8, b2=1 << 8, h1=1 << 8, h2=1 << 8, a1=1 << 8, a2=1 << 8)
+        single = bool(lib.lewin_leff_fwd_is_fused(probe, _lib.DTYPE_TAG[dt]))
+        hshape = (16,) if single else (tokens, hidden)        # the fused kernel keeps the hidden activations on chip
+        h1 = torch.empty(hshape, dtype=y.dtype, device=dev)
+        h2 = torch.empty(hshape, dtype=y.dtype, device=dev)
         a1 = torch.empty_like(h1) if need_grad else None
         a2 = torch.empty_like(h2) if need_grad else None
         ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_ = [_f32c(t) for t in (ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale)]
@@ -202,7 +204,8 @@ class _LeffFn(torch.autograd.Function):
             w_dw=_ptr(wdw_), b_dw=_ptr(bdw_), w2=_ptr(w2_), b2=_ptr(b2_), drop_scale=_ptr(ds_),
             h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
         if KernelTimer.active is not None:
-            tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt), not fused)
+            tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt),
+                                                (4,) if single else ((1, 2, 3) if not fused else (0, 1, 2, 3)))
             a.timing = ctypes_addr(tim)
         ws = _workspace(lib.lewin_leff_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_leff_fwd_{dt}")
@@ -217,7 +220,7 @@ class _LeffFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         (y, ln_w, ln_b, w1, b1, wdw, bdw, w2, b2, ds, h1, h2, a1, a2) = ctx.saved_tensors
-        B, H, W, fused = ctx.geom
+        B, H, W, fused, _ = ctx.geom
         lib = _lib.load()
         dt = ctx.dt
         dev = y.device
@@ -246,7 +249,9 @@ def lewin_attn(x, *, B, H, W, num_heads, shift, ln_w, ln_b, w_qkv, b_qkv, w_out,
                rpb_table=None, rpb_dense=None, index_sample, mask=None, drop_scale=None,
                windowed=False, use_rpb=True, analytic_shift_mask=True, return_top=False):
     """Attention half of a LeWin block.  Returns y (same shape as x) [and the selected top-u indices]."""
-    geom = (int(B), int(H), int(W), int(num_heads), int(shift), bool(windowed), bool(use_rpb), bool(analytic_shift_mask))
+    need = torch.is_grad_enabled() and any(
+        isinstance(t, torch.Tensor) and t.requires_grad for t in (x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense))
+    geom = (int(B), int(H), int(W), int(num_heads), int(shift), bool(windowed), bool(use_rpb), bool(analytic_shift_mask), need)
     y, top = _AttnFn.apply(x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
                            drop_scale, geom)
     return (y, top) if return_top else y
@@ -254,7 +259,9 @@ def lewin_attn(x, *, B, H, W, num_heads, shift, ln_w, ln_b, w_qkv, b_qkv, w_out,
 
 def lewin_leff(y, *, B, H, W, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale=None, fused=True):
     """LeFF half of a LeWin block (fused=True: out = y + s * LeFF(LN2(y)); fused=False: out = LeFF(y))."""
-    geom = (int(B), int(H), int(W), bool(fused))
+    need = torch.is_grad_enabled() and any(
+        isinstance(t, torch.Tensor) and t.requires_grad for t in (y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2))
+    geom = (int(B), int(H), int(W), bool(fused), need)
     return _LeffFn.apply(y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom)
 
 

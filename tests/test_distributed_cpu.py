@@ -1,0 +1,106 @@
+"""CPU, world_size 2, gloo: the host-side multi-GPU logic (tile sharding + final gather of config 3, index_sample
+broadcast, DDP with the dead parameters frozen).  The CUDA ops have no CPU fallback, so a stand-in per-tile function
+is used where a model forward is needed; what is under test is the sharding / collective plumbing."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _TileModel(nn.Module):
+    """Per-tile stand-in: depends on the tile content AND on index_samples (so a missing broadcast is caught)."""
+
+    def draw_index_samples(self):
+        return torch.stack([torch.randint(64, (64, 25)) for _ in range(18)])
+
+    def forward(self, x, index_samples=None):
+        k = index_samples.float().mean() / 64.0
+        return x.flip(-1) * 0.5 + k + x.mean(dim=(1, 2, 3), keepdim=True)
+
+
+def _tiled_worker(rank, world, port, ref_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lewin_b200 import fullres
+    torch.manual_seed(7)
+    img = torch.rand(1, 3, 250, 380)
+    torch.manual_seed(100 + rank)                 # ranks would draw DIFFERENT index_samples without the broadcast
+    out = fullres.dehaze_tiled(_TileModel(), img, ps=128)
+    ref = torch.load(ref_path)
+    assert torch.equal(out, ref), f"rank {rank}: sharded result differs from the single-process result"
+    dist.destroy_process_group()
+
+
+def test_tiled_sharding_matches_single_process(tmp_path):
+    from lewin_b200 import fullres
+    torch.manual_seed(7)
+    img = torch.rand(1, 3, 250, 380)
+    torch.manual_seed(100)                        # == rank 0's generator state in the workers
+    ref = fullres.dehaze_tiled(_TileModel(), img, ps=128)
+    assert ref.shape == img.shape
+    path = str(tmp_path / "ref.pt")
+    torch.save(ref, path)
+    mp.spawn(_tiled_worker, args=(2, _free_port(), path), nprocs=2, join=True)
+
+
+class _BlockLike(nn.Module):
+    """Module tree with the reference's dead-parameter layout (attn.qkv.to_q / to_kv / attn.proj never used)."""
+
+    def __init__(self):
+        super().__init__()
+        self.attn = nn.Module()
+        self.attn.qkv = nn.Module()
+        self.attn.qkv.to_q = nn.Linear(8, 8)
+        self.attn.qkv.to_kv = nn.Linear(8, 16)
+        self.attn.proj = nn.Linear(8, 8)
+        self.live = nn.Linear(8, 8)
+
+    def forward(self, x):
+        return self.live(x)
+
+
+def _ddp_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lewin_b200 import parallel
+    torch.manual_seed(0)
+    model = _BlockLike()
+    ddp = parallel.wrap_ddp(model)               # would hang / raise on the unused parameters without the freeze
+    torch.manual_seed(0)
+    x = torch.randn(4, 8)
+    ddp(x[rank * 2:(rank + 1) * 2]).sum().backward()
+    torch.manual_seed(0)
+    single = _BlockLike()
+    single(x).sum().backward()
+    assert torch.allclose(model.live.weight.grad * world, single.live.weight.grad, atol=1e-6)
+    assert model.attn.proj.weight.grad is None and not model.attn.proj.weight.requires_grad
+    assert "attn.proj.weight" in model.state_dict()
+    dist.destroy_process_group()
+
+
+def test_ddp_with_dead_parameters_gloo():
+    mp.spawn(_ddp_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_dead_parameter_inventory():
+    import lewin_b200 as L
+    from lewin_b200 import parallel
+    blk = L.LeWinTransformerBlock(dim=32, input_resolution=(128, 128), num_heads=1)
+    dead = parallel.dead_parameter_names(blk)
+    assert len(dead) == 6
+    assert parallel.freeze_dead_parameters(blk) == 6
+    assert sum(p.requires_grad for p in blk.parameters()) == 19      # the 19 live parameters of SURVEY Appendix B

@@ -155,15 +155,14 @@ __device__ __forceinline__ void gelu_tab_to_smem(uint16_t* dst, int tid, int nth
     for (int i = tid; i < kGeluTabSize / 8; i += nthreads)
         reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(g_gelu_tab)[i];
 }
-// bf16 bits of GELU(x) for x given as bf16 bits
+// bf16 bits of GELU(x) for x given as bf16 bits.  Fast path (2^-12 <= |x| < 16): 5 integer ops + one 16-bit load;
+// the out-of-range cases are rare (|x| < 2.4e-4 or >= 16) and take a divergent slow path.
 __device__ __forceinline__ uint32_t gelu_bits(const uint16_t* __restrict__ tab, uint32_t u) {
-    const uint32_t e = (u >> 7) & 0xFFu;
-    const uint32_t ec = min(max(e, 115u), 130u) - 115u;
-    const uint32_t idx = (ec << 7) | (u & 0x7Fu) | ((u & 0x8000u) >> 4);
-    uint32_t r = tab[idx];
-    if (e < 115u) r = (e > 1u) ? (u - 0x80u) : (u & 0x8000u);       // 0.5 * x (flush the last binade to signed zero)
-    if (e >= 131u) r = (u & 0x8000u) ? 0x8000u : u;                 // x, or -0 for large negative x
-    return r;
+    const uint32_t r = (u & 0x7FFFu) - 0x3980u;                    // |x| bits relative to 2^-12 (exponent 115)
+    if (__builtin_expect(r < 2048u, 1)) return tab[r + ((u >> 15) << 11)];
+    if (static_cast<int32_t>(r) < 0)                               // tiny: 0.5 * x (last binades flush to signed zero)
+        return ((u & 0x7F80u) > 0x0080u) ? (u - 0x80u) : (u & 0x8000u);
+    return (u & 0x8000u) ? 0x8000u : u;                            // huge: x, or -0 for negative x
 }
 // GELU of a float that is rounded to bf16 first; returns the bf16-valued result as float
 __device__ __forceinline__ float gelu_tab(const uint16_t* __restrict__ tab, float x) {

@@ -108,17 +108,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }  // namespace tc
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS_MAX = 256;
 
-template <int BN, int KC>
+template <int BN, int KC, int STAGES, int EPI>
 constexpr size_t tc_smem_bytes() {
-    return 1024 /*align slack*/ + 2 * (TC_BM * KC * 2) + 2 * (BN * KC * 2) + TC_BM * (2 * 8 + 3 * 4) + BN * 4 + 64 +
-           kGeluTabSize * 2;
+    return 1024 /*align slack*/ + STAGES * (TC_BM * KC * 2) + STAGES * (BN * KC * 2) + TC_BM * (2 * 8 + 3 * 4) + BN * 4 + 64 +
+           (EPI == EPI_BIAS_GELU ? kGeluTabSize * 2 : 0);
 }
 
-template <int BN, int KC, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const GemmArgs<__nv_bfloat16> g) {
+template <int BN, int KC, int EPI, int TC_THREADS, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, (TC_THREADS == 128 ? (STAGES == 1 ? 4 : 2) : 2)) gemm_tc_kernel(const GemmArgs<__nv_bfloat16> g) {
     using T = __nv_bfloat16;
+    constexpr int NWG = TC_THREADS / 128;             // epilogue warpgroups (each warp reads its own 32 TMEM lanes)
     constexpr int CPR = KC / 8;                       // 16-byte chunks per tile row
     constexpr int A_STAGE = TC_BM * KC * 2;
     constexpr int W_STAGE = BN * KC * 2;
@@ -128,9 +129,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const GemmArgs<_
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* As = base;                         // [2][A_STAGE]
-    unsigned char* Ws = As + 2 * A_STAGE;             // [2][W_STAGE]
-    long long* offA = reinterpret_cast<long long*>(Ws + 2 * W_STAGE);
+    unsigned char* As = base;                         // [STAGES][A_STAGE]
+    unsigned char* Ws = As + STAGES * A_STAGE;        // [STAGES][W_STAGE]
+    long long* offA = reinterpret_cast<long long*>(Ws + STAGES * W_STAGE);
     long long* offY = offA + TC_BM;
     float* s_mean = reinterpret_cast<float*>(offY + TC_BM);
     float* s_rstd = s_mean + TC_BM;
@@ -253,10 +254,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const GemmArgs<_
 
     const int nk = g.K / KC;
     for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc & 1;
+        const int s = kc % STAGES;
         load_a(kc);
         load_w(kc);
-        if (kc >= 2) tc::mbar_wait(&mbar[s], ((kc - 2) >> 1) & 1);   // MMAs that read stage s have retired
+        if (kc >= STAGES) tc::mbar_wait(&mbar[s], ((kc / STAGES) - 1) & 1);   // MMAs that read stage s have retired
         store_stage(s);
         tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncthreads();
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const GemmArgs<_
             issue(kc, s);
         }
     }
-    tc::mbar_wait(&mbar[(nk - 1) & 1], ((nk - 1) >> 1) & 1);          // the last commit covers every MMA issued
+    tc::mbar_wait(&mbar[(nk - 1) % STAGES], ((nk - 1) / STAGES) & 1);   // the last commit covers every MMA issued
     tc::tc_fence_after();
 
     // ---- epilogue: thread == TMEM lane == tile row
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const GemmArgs<_
         if (EPI == EPI_BIAS_RESID && g.drop_scale && oy >= 0) sc = g.drop_scale[(oy / g.ldy) / g.tokens_per_image];
         const uint32_t lane_addr = tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        for (int c0 = half * 32; c0 < BN; c0 += 32 * NWG) {
             float v[32];
             tc::tmem_ld32(lane_addr + c0, v);
             if (oy < 0) continue;
@@ -333,22 +334,35 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const GemmArgs<_
     if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
 }
 
-template <int BN, int KC, int EPI>
-cudaError_t launch_gemm_tc_inst(const GemmArgs<__nv_bfloat16>& g, cudaStream_t stream) {
-    constexpr size_t smem = tc_smem_bytes<BN, KC>();
-    auto k = gemm_tc_kernel<BN, KC, EPI>;
+template <int BN, int KC, int EPI, int STAGES>
+cudaError_t launch_gemm_tc_stages(const GemmArgs<__nv_bfloat16>& g, cudaStream_t stream) {
+    constexpr size_t smem = tc_smem_bytes<BN, KC, STAGES, EPI>();
+    // narrow tiles: 128-thread CTAs, up to 4 per SM (TMEM 4 x 128 columns) -> more independent load / MMA / epilogue
+    // phases in flight; a single k-chunk (K == KC) needs no second smem stage
+    constexpr int THREADS = BN <= 128 ? 128 : 256;
+    auto k = gemm_tc_kernel<BN, KC, EPI, THREADS, STAGES>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     dim3 grid(static_cast<unsigned>((g.M + TC_BM - 1) / TC_BM), g.N / BN);
-    k<<<grid, TC_THREADS, smem, stream>>>(g);
+    k<<<grid, THREADS, smem, stream>>>(g);
     return cudaGetLastError();
+}
+
+template <int BN, int KC, int EPI>
+cudaError_t launch_gemm_tc_inst(const GemmArgs<__nv_bfloat16>& g, cudaStream_t stream) {
+    if (g.K == KC) return launch_gemm_tc_stages<BN, KC, EPI, 1>(g, stream);
+    return launch_gemm_tc_stages<BN, KC, EPI, 2>(g, stream);
 }
 
 template <int KC, int EPI>
 cudaError_t launch_gemm_tc_kc(const GemmArgs<__nv_bfloat16>& g, cudaStream_t stream) {
     const int N = g.N;
-    if (N % 256 == 0) return launch_gemm_tc_inst<256, KC, EPI>(g, stream);
-    if (N % 192 == 0) return launch_gemm_tc_inst<192, KC, EPI>(g, stream);
+    // wide (192/256-column, 256-thread) tiles measured faster than 128-column / 128-thread tiles on every shape
+    static const bool wide = [] { const char* e = getenv("LEWIN_TC_NARROW"); return !(e && e[0] == '1'); }();
+    if (wide) {
+        if (N % 256 == 0) return launch_gemm_tc_inst<256, KC, EPI>(g, stream);
+        if (N % 192 == 0) return launch_gemm_tc_inst<192, KC, EPI>(g, stream);
+    }
     if (N % 128 == 0) return launch_gemm_tc_inst<128, KC, EPI>(g, stream);
     if (N % 96 == 0) return launch_gemm_tc_inst<96, KC, EPI>(g, stream);
     if (N % 64 == 0) return launch_gemm_tc_inst<64, KC, EPI>(g, stream);

@@ -7,6 +7,7 @@
 #include "gemm_tc.cuh"
 #include "leff_fused.cuh"
 #include "probsparse_core.cuh"
+#include "probsparse_core_bf16.cuh"
 #include "backward.cuh"
 
 #include <atomic>
@@ -72,7 +73,7 @@ int check_attn(const LewinAttnFwdArgs* a) {
 
 size_t attn_fwd_ws(const LewinAttnFwdArgs* a) {
     const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
-    return 2 * align_up(tokens * sizeof(float), 256) + align_up(kTok * kTok, 256);
+    return 2 * align_up(tokens * sizeof(float), 256) + align_up(kTok * kTok, 256) + align_up(kTok * kTok * 4, 256);
 }
 
 template <typename T>
@@ -91,6 +92,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     float* mean = reinterpret_cast<float*>(wsp);
     float* rstd = reinterpret_cast<float*>(wsp + align_up(tokens * sizeof(float), 256));
     uint8_t* cnt = wsp + 2 * align_up(tokens * sizeof(float), 256);
+    __half2* cw = reinterpret_cast<__half2*>(cnt + align_up(kTok * kTok, 256));
 
     WinMap map{a->H, a->W, a->W / 8, nWin, a->shift};
     const T* x = static_cast<const T*>(a->x);
@@ -102,7 +104,8 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         kt.end(LEWIN_ATTN_K_LNSTATS);
     }
     kt.begin(LEWIN_ATTN_K_CNT);
-    build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
+    if constexpr (Act<T>::kIsBf16) build_cw_kernel<<<1, 64, 0, stream>>>(a->index_sample, cw);
+    else build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
     CK(cudaGetLastError());
     kt.end(LEWIN_ATTN_K_CNT);
 
@@ -133,7 +136,15 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         c.shift = (a->analytic_shift_mask && !a->windowed) ? a->shift : 0;
         c.H = a->H; c.W = a->W; c.nWw = a->W / 8; c.nWin = nWin;
         kt.begin(LEWIN_ATTN_K_CORE);
-        CK(launch_core_fwd<T>(c, di.sms, stream));
+        if constexpr (Act<T>::kIsBf16) {
+            CoreBf16Args b{};
+            b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense; b.cw = cw;
+            b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
+            b.shift = c.shift; b.H = c.H; b.W = c.W; b.nWw = c.nWw; b.nWin = c.nWin;
+            CK(launch_core_bf16(b, di.sms, stream));
+        } else {
+            CK(launch_core_fwd<T>(c, di.sms, stream));
+        }
         kt.end(LEWIN_ATTN_K_CORE);
     }
     {   // out projection (attn.py:456) + window_reverse + un-roll + DropPath scale + residual
@@ -165,10 +176,12 @@ int core_only_fwd(const LewinCoreFwdArgs* a, void* ws, size_t ws_bytes, cudaStre
     if (!aligned16(a->qkv) || !aligned16(a->ctx) || (a->mask && !aligned16(a->mask))) return LEWIN_E_ALIGN;
     DeviceInfo di;
     if (int rc = device_info(&di)) return rc;
-    if (!ws || ws_bytes < static_cast<size_t>(kTok * kTok)) return LEWIN_E_WORKSPACE;
+    if (!ws || ws_bytes < static_cast<size_t>(kTok * kTok * 5)) return LEWIN_E_WORKSPACE;
     if (!aligned16(ws)) return LEWIN_E_ALIGN;
     uint8_t* cnt = static_cast<uint8_t*>(ws);
-    build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
+    __half2* cw = reinterpret_cast<__half2*>(cnt + kTok * kTok);
+    if constexpr (Act<T>::kIsBf16) build_cw_kernel<<<1, 64, 0, stream>>>(a->index_sample, cw);
+    else build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
     CK(cudaGetLastError());
     CoreFwdArgs<T> c{};
     c.qkv = static_cast<const T*>(a->qkv);
@@ -181,6 +194,13 @@ int core_only_fwd(const LewinCoreFwdArgs* a, void* ws, size_t ws_bytes, cudaStre
     c.B_ = a->B_; c.nH = a->nH; c.C = a->nH * kHeadDim;
     c.use_rpb = a->use_rpb;
     c.shift = 0; c.H = 8; c.W = 8; c.nWw = 1; c.nWin = 1;
+    if constexpr (Act<T>::kIsBf16) {
+        CoreBf16Args b{};
+        b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense; b.cw = cw;
+        b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
+        b.shift = 0; b.H = 8; b.W = 8; b.nWw = 1; b.nWin = 1;
+        CK(launch_core_bf16(b, di.sms, stream));
+    } else
     CK(launch_core_fwd<T>(c, di.sms, stream));
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return 0;
@@ -300,7 +320,7 @@ int lewin_probsparse_core_fwd_f32(const LewinCoreFwdArgs* a, void* ws, size_t n,
 int lewin_probsparse_core_fwd_bf16(const LewinCoreFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
     return core_only_fwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
 }
-size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs*, int) { return kTok * kTok; }
+size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs*, int) { return kTok * kTok * 5; }
 int lewin_leff_fwd_is_fused(const LewinLeffFwdArgs* a, int dtype) {
     return (a && check_leff(a) == 0 && leff_use_fused(a, dtype == LEWIN_DTYPE_BF16)) ? 1 : 0;
 }

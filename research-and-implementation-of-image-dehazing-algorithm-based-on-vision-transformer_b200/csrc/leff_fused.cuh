@@ -38,6 +38,20 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
 }
 
+// packed fp32x2 FMA (Blackwell FFMA2): d.{x,y} += a.{x,y} * b.{x,y} in one instruction
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+__device__ __forceinline__ void unpack8_2(const uint4& u, float2 (&f)[4]) {
+    f[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u));
+    f[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+    f[2] = make_float2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xFFFF0000u));
+    f[3] = make_float2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xFFFF0000u));
+}
+
 }  // namespace lf
 
 struct LeffFusedArgs {
@@ -230,26 +244,26 @@ __global__ void __launch_bounds__(LF_THREADS, (C <= 64 ? 3 : 2)) leff_fused_kern
         {
             const int c8 = (tid & 7) * 8;
             const int p_a = tid >> 3, p_b = p_a + 32;          // interior pixel ids
-            float o0[8], o1[8];
+            float2 o0[4], o1[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { o0[j] = s.dwb[c8 + j]; o1[j] = o0[j]; }
+            for (int j = 0; j < 4; ++j) { o0[j] = make_float2(s.dwb[c8 + 2 * j], s.dwb[c8 + 2 * j + 1]); o1[j] = o0[j]; }
             const int ra = (p_a >> 3) * 10 + (p_a & 7), rb = (p_b >> 3) * 10 + (p_b & 7);   // halo row of tap (0,0)
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const int d = (tap / 3) * 10 + (tap % 3);
                 const float4 w0 = *reinterpret_cast<const float4*>(s.dww + tap * LF_CH + c8);
                 const float4 w1 = *reinterpret_cast<const float4*>(s.dww + tap * LF_CH + c8 + 4);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                float fa[8], fb[8];
-                lf::unpack8(*reinterpret_cast<const uint4*>(s.h1s + (ra + d) * LF_HS_LD + c8), fa);
-                lf::unpack8(*reinterpret_cast<const uint4*>(s.h1s + (rb + d) * LF_HS_LD + c8), fb);
+                const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+                float2 fa[4], fb[4];
+                lf::unpack8_2(*reinterpret_cast<const uint4*>(s.h1s + (ra + d) * LF_HS_LD + c8), fa);
+                lf::unpack8_2(*reinterpret_cast<const uint4*>(s.h1s + (rb + d) * LF_HS_LD + c8), fb);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { o0[j] = fmaf(fa[j], wv[j], o0[j]); o1[j] = fmaf(fb[j], wv[j], o1[j]); }
+                for (int j = 0; j < 4; ++j) { lf::ffma2(o0[j], fa[j], wv[j]); lf::ffma2(o1[j], fb[j], wv[j]); }
             }
             uint32_t qa[4], qb[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t ia = lf::pack2(o0[2 * j], o0[2 * j + 1]), ib = lf::pack2(o1[2 * j], o1[2 * j + 1]);
+                const uint32_t ia = lf::pack2(o0[j].x, o0[j].y), ib = lf::pack2(o1[j].x, o1[j].y);
                 qa[j] = gelu_bits(s.gtab, ia & 0xFFFFu) | (gelu_bits(s.gtab, ia >> 16) << 16);
                 qb[j] = gelu_bits(s.gtab, ib & 0xFFFFu) | (gelu_bits(s.gtab, ib >> 16) << 16);
             }

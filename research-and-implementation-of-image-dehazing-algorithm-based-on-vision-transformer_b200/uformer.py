@@ -1,8 +1,9 @@
 """Host-side model graph that CALLS the hot path: Uformer (My_model_1.py:955-1230).
 
-Out of the hot-path scope (SURVEY.md section 2, rows 3): InputProj / OutputProj / Downsample /
-Upsample are stock PyTorch convolutions (cuDNN), exactly as in the reference; only the 18
-LeWinTransformerBlocks run on the sm_100a kernels.  This file exists because the reference source
+Out of the hot-path scope (SURVEY.md section 2, row 3): InputProj / OutputProj / Downsample /
+Upsample are stock PyTorch convolutions (cuDNN) with the reference's parameters; only the 18
+LeWinTransformerBlocks run on the sm_100a kernels.  The convolutions are fed channels_last VIEWS of the
+token-major residual stream, so the reference's NCHW <-> token transposes disappear (same arithmetic).  This file exists because the reference source
 cannot travel to the GPU box; it keeps the reference's constructor arguments, forward signature and
 the 488-key state_dict layout (tests/golden/uformer32_state_dict_keys.txt) so checkpoints load
 strictly (utils/model_utils.py:28-40).
@@ -21,6 +22,25 @@ import torch.nn as nn
 from .modules import LeWinTransformerBlock, draw_index_sample
 
 
+def _tokens_to_nchw(x):
+    """[B, L, C] token-major -> [B, C, H, W] VIEW with channels_last strides (no copy): the residual stream is already
+    NHWC, so cuDNN's NHWC kernels consume it directly (the reference transposes to NCHW and back around every
+    convolution, My_model_1.py:620-621, 646-647, 679, 719)."""
+    B, L, C = x.shape
+    H = W = int(math.sqrt(L))
+    return x.reshape(B, H, W, C).permute(0, 3, 1, 2)
+
+
+def _nchw_to_tokens(y):
+    """[B, C, H, W] (channels_last after an NHWC convolution) -> [B, H*W, C]; a copy only if y is not channels_last."""
+    B, C, H, W = y.shape
+    return y.permute(0, 2, 3, 1).reshape(B, H * W, C)
+
+
+def _cl(w):
+    return w.contiguous(memory_format=torch.channels_last)
+
+
 class Downsample(nn.Module):
     """My_model_1.py:606-622: 4x4 stride-2 conv on the token map."""
 
@@ -30,10 +50,9 @@ class Downsample(nn.Module):
         self.in_channel, self.out_channel = in_channel, out_channel
 
     def forward(self, x):
-        B, L, C = x.shape
-        H = W = int(math.sqrt(L))
-        x = x.transpose(1, 2).contiguous().view(B, C, H, W)
-        return self.conv(x).flatten(2).transpose(1, 2).contiguous()
+        c = self.conv[0]
+        y = torch.nn.functional.conv2d(_tokens_to_nchw(x), _cl(c.weight), c.bias, stride=2, padding=1)
+        return _nchw_to_tokens(y)
 
 
 class Upsample(nn.Module):
@@ -45,10 +64,9 @@ class Upsample(nn.Module):
         self.in_channel, self.out_channel = in_channel, out_channel
 
     def forward(self, x):
-        B, L, C = x.shape
-        H = W = int(math.sqrt(L))
-        x = x.transpose(1, 2).contiguous().view(B, C, H, W)
-        return self.deconv(x).flatten(2).transpose(1, 2).contiguous()
+        d = self.deconv[0]
+        y = torch.nn.functional.conv_transpose2d(_tokens_to_nchw(x), _cl(d.weight), d.bias, stride=2)
+        return _nchw_to_tokens(y)
 
 
 class InputProj(nn.Module):
@@ -63,7 +81,7 @@ class InputProj(nn.Module):
         self.in_channel, self.out_channel = in_channel, out_channel
 
     def forward(self, x):
-        x = self.proj(x).flatten(2).transpose(1, 2).contiguous()
+        x = _nchw_to_tokens(self.proj(x.contiguous(memory_format=torch.channels_last)))
         return self.norm(x) if self.norm is not None else x
 
 
@@ -78,10 +96,7 @@ class OutputProj(nn.Module):
         self.in_channel, self.out_channel = in_channel, out_channel
 
     def forward(self, x):
-        B, L, C = x.shape
-        H = W = int(math.sqrt(L))
-        x = x.transpose(1, 2).reshape(B, C, H, W)
-        x = self.proj(x)
+        x = self.proj(_tokens_to_nchw(x))
         return self.norm(x) if self.norm is not None else x
 
 

@@ -282,7 +282,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         kt.end(LEWIN_LEFF_K_FC1);
     }
     kt.begin(LEWIN_LEFF_K_DWCONV);
-    CK(launch_dwconv_gelu<T>(static_cast<const T*>(a->h1), static_cast<T*>(a->h2), save ? static_cast<T*>(a->a2) : nullptr,
+    CK(launch_dwconv_gelu_auto<T>(static_cast<const T*>(a->h1), static_cast<T*>(a->h2), save ? static_cast<T*>(a->a2) : nullptr,
                              a->w_dw, a->b_dw, a->B, a->H, a->W, Ch, stream));
     kt.end(LEWIN_LEFF_K_DWCONV);
     {   // linear2 (My_model_1.py:529) + DropPath scale + residual (My_model_1.py:873)

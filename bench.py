@@ -206,6 +206,7 @@ def main():
                     help="compute dtype of the headline number (bf16 = BASELINE's compute dtype; f32 = the reference's "
                          "inference precision, always reported as well under 'fp32')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,12 +238,24 @@ def main():
     idx = model.draw_index_samples()            # 18 draws of attn.py:91 (identical on every rank: same seed)
 
     cur_dtype = [args.dtype]
+    graphs = {}
+
+    def graphed_for(dt):
+        """CUDA graph of this rank's tile-batch forward (static shape), captured once per precision."""
+        if args.no_graph or ops.KernelTimer.active is not None:
+            return None
+        if dt not in graphs:
+            s0, e0 = fullres.shard_range(N_TILES, rank, world)
+            ex = torch.zeros(e0 - s0, 3, PS, PS, device=dev)
+            graphs[dt] = fullres.GraphedForward(model, ex, idx, torch.bfloat16 if dt == "bf16" else None)
+        return graphs[dt]
 
     def forward(img):
-        if cur_dtype[0] == "bf16":
+        g = graphed_for(cur_dtype[0])
+        if g is None and cur_dtype[0] == "bf16":
             with torch.autocast("cuda", torch.bfloat16):
                 return fullres.dehaze_tiled(model, img, ps=PS, index_samples=idx)
-        return fullres.dehaze_tiled(model, img, ps=PS, index_samples=idx)
+        return fullres.dehaze_tiled(model, img, ps=PS, index_samples=idx, graphed=g)
 
     def barrier():
         if world > 1:
@@ -279,6 +292,8 @@ def main():
     n0 = lib.lewin_launch_count()
     ms_total = timed(step_resident, args.steps)
     launches = lib.lewin_launch_count() - n0
+    if args.dtype in graphs:          # graph replay: the captured library launches run once per replay
+        launches += graphs[args.dtype].launches_per_replay * args.steps
     ms_e2e = timed(step_e2e, args.steps)
     # second pass with per-kernel events (roofline of the dominant kernel type)
     with ops.KernelTimer() as kt:
@@ -359,6 +374,7 @@ def main():
                                f"{world} rank(s), Uformer_ProbSparse embed_dim=32 random init, tiled mode, final all_gather",
                    "tiles_per_rank_max": -(-N_TILES // world), "l2": "working set (>=354 MB per level-0 tensor) exceeds the 126 MB L2",
                    "convs": "in/out/down/up projections are stock cuDNN (out of hot-path scope)",
+                   "launch": "python launches" if args.no_graph else "CUDA graph replay of the per-rank tile-batch forward",
                    "lewin_compute": "3xTF32 mma.sync (fp32-grade)" if args.dtype == "f32" else "bf16 operands, fp32 accumulate"},
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "images/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo},
         "gpu_launches": int(lt.item()),

@@ -54,6 +54,48 @@ def shard_range(T, rank, world):
     return start, start + base + (1 if rank < extra else 0)
 
 
+class GraphedForward:
+    """CUDA-graph replay of ``model(tiles, index_samples=idx)`` for one fixed tile-batch shape.
+
+    The per-rank tile batch of config 3 has a static shape, and a forward is ~230 kernel launches (18 blocks x 4-9
+    kernels + 10 cuDNN convolutions + glue); at 8 GPUs the per-rank GPU time drops below the CPU launch time, so the
+    launch sequence is captured once and replayed (inputs are copied into static buffers; ``index_samples`` is a
+    static device tensor refreshed before every replay, so the reference's per-forward RNG draws are preserved)."""
+
+    def __init__(self, model, tiles, index_samples, autocast_dtype=None, warmup=2):
+        self.model = model
+        self.autocast_dtype = autocast_dtype
+        self.x = tiles.clone()
+        self.idx = index_samples.to(device=tiles.device, dtype=torch.int32).clone()
+        side = torch.cuda.Stream(device=tiles.device)
+        side.wait_stream(torch.cuda.current_stream(tiles.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._run()
+        torch.cuda.current_stream(tiles.device).wait_stream(side)
+        from . import _lib
+        lib = _lib.load()
+        n0 = lib.lewin_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.y = self._run()
+        self.launches_per_replay = int(lib.lewin_launch_count() - n0)    # library kernels captured in the graph
+
+    @torch.no_grad()
+    def _run(self):
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", self.autocast_dtype):
+                return self.model(self.x, index_samples=self.idx)
+        return self.model(self.x, index_samples=self.idx)
+
+    @torch.no_grad()
+    def __call__(self, tiles, index_samples):
+        self.x.copy_(tiles, non_blocking=True)
+        self.idx.copy_(index_samples.to(dtype=torch.int32), non_blocking=True)
+        self.graph.replay()
+        return self.y
+
+
 @torch.no_grad()
 def dehaze_canvas(model, img, ps=128, index_samples=None):
     """Reference semantics (test_long_GPU.py:85-93): one forward over the whole padded canvas."""
@@ -64,7 +106,7 @@ def dehaze_canvas(model, img, ps=128, index_samples=None):
 
 
 @torch.no_grad()
-def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=None):
+def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=None, graphed=None):
     """Tiled mode, sharded over the ranks of `group` (torch.distributed) when initialised.
 
     Every rank receives the full image, processes its contiguous tile range and all ranks end with the full
@@ -91,12 +133,15 @@ def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=
 
     s, e = shard_range(T, rank, world)
     mine = tiles[s:e]
-    outs = []
-    step = tile_batch or max(e - s, 1)
-    for i in range(0, e - s, step):
-        chunk = mine[i:i + step]
-        outs.append(model(chunk, index_samples=index_samples) if index_samples is not None else model(chunk))
-    out = torch.cat(outs, 0) if outs else mine.new_zeros((0, C, ps, ps))
+    if graphed is not None:                      # GraphedForward captured for exactly this rank's tile-batch shape
+        out = graphed(mine, index_samples)
+    else:
+        outs = []
+        step = tile_batch or max(e - s, 1)
+        for i in range(0, e - s, step):
+            chunk = mine[i:i + step]
+            outs.append(model(chunk, index_samples=index_samples) if index_samples is not None else model(chunk))
+        out = torch.cat(outs, 0) if outs else mine.new_zeros((0, C, ps, ps))
 
     if distributed:
         per = (T + world - 1) // world

@@ -63,7 +63,47 @@ struct LeffFusedArgs {
     const float* w2; const float* b2;        // [C, 4C], [C]
     const float* drop_scale;                 // [B] or null
     int B, H, W;
+    const unsigned char* wimg;               // per-chunk bf16/fp32 weight images written by leff_prep_weights_kernel
 };
+
+// Per-chunk weight image (exactly the shared-memory layout, so staging is plain 16-byte cp.async copies):
+//   w1 [64][C+8] bf16 | b1 [64] f32 | w2 [C][72] bf16 | dww [9][64] f32 | dwb [64] f32      (autocast-rounded values)
+template <int C> struct LeffImg {
+    static constexpr int W1 = 0;
+    static constexpr int B1 = 64 * (C + 8) * 2;
+    static constexpr int W2 = B1 + 256;
+    static constexpr int DWW = W2 + C * 72 * 2;
+    static constexpr int DWB = DWW + 9 * 64 * 4;
+    static constexpr int BYTES = DWB + 256;
+};
+inline size_t leff_img_bytes(int C) { return static_cast<size_t>(4 * C / 64) * (64 * (C + 8) * 2 + 256 + C * 144 + 2304 + 256); }
+
+template <int C>
+__global__ void leff_prep_weights_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                         const float* __restrict__ w2, const float* __restrict__ w_dw,
+                                         const float* __restrict__ b_dw, unsigned char* __restrict__ img) {
+    using I = LeffImg<C>;
+    const int ch = blockIdx.x, h0 = ch * 64, HID = 4 * C;
+    unsigned char* base = img + static_cast<size_t>(ch) * I::BYTES;
+    __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(base + I::W1);
+    for (int i = threadIdx.x; i < 64 * (C + 8); i += blockDim.x) {
+        const int r = i / (C + 8), c = i - r * (C + 8);
+        o1[i] = __float2bfloat16_rn(c < C ? w1[static_cast<long long>(h0 + r) * C + c] : 0.f);
+    }
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(base + I::W2);
+    for (int i = threadIdx.x; i < C * 72; i += blockDim.x) {
+        const int r = i / 72, c = i - r * 72;
+        o2[i] = __float2bfloat16_rn(c < 64 ? w2[static_cast<long long>(r) * HID + h0 + c] : 0.f);
+    }
+    float* ob1 = reinterpret_cast<float*>(base + I::B1);
+    float* odw = reinterpret_cast<float*>(base + I::DWW);
+    float* odb = reinterpret_cast<float*>(base + I::DWB);
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int tap = i / 64, c = i - tap * 64;
+        odw[i] = lf::rbf(w_dw[static_cast<long long>(h0 + c) * 9 + tap]);
+    }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { ob1[i] = lf::rbf(b1[h0 + i]); odb[i] = lf::rbf(b_dw[h0 + i]); }
+}
 
 constexpr int LF_THREADS = 256;
 constexpr int LF_CH = 64;          // hidden channels per chunk
@@ -87,7 +127,7 @@ struct LeffFusedSmem {
 };
 
 template <int C>
-__global__ void __launch_bounds__(LF_THREADS, (C <= 64 ? 3 : 2)) leff_fused_kernel(const LeffFusedArgs a) {
+__global__ void __launch_bounds__(LF_THREADS, (C == 32 ? 4 : C == 64 ? 3 : 2)) leff_fused_kernel(const LeffFusedArgs a) {
     using S = LeffFusedSmem<C>;
     constexpr int XS_LD = S::XS_LD;
     constexpr int HID = 4 * C;
@@ -166,31 +206,25 @@ __global__ void __launch_bounds__(LF_THREADS, (C <= 64 ? 3 : 2)) leff_fused_kern
     const int mg = warp & 1, ng = warp >> 1;           // GEMM1: m-group (tiles 0-3 / 4-6), n-group (16 hidden channels)
     const int m2 = warp & 3, nh = warp >> 2;           // GEMM2 roles
 
+    using I = LeffImg<C>;
+    auto stage = [&](void* dst, const unsigned char* src, int bytes) {     // 16-byte async copies, all threads
+        for (int i = tid * 16; i < bytes; i += LF_THREADS * 16)
+            cp_async16(static_cast<unsigned char*>(dst) + i, src + i);
+    };
+    // chunk 0: GEMM1 operands (group A) then the dwconv / GEMM2 operands (group B)
+    stage(s.w1s, a.wimg + I::W1, 64 * XS_LD * 2);
+    stage(s.b1s, a.wimg + I::B1, 256);
+    cp_async_commit();
+
 #pragma unroll 1
     for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int h0 = ch * LF_CH;
-        __syncthreads();                               // previous chunk's consumers are done with w1s/w2s/h1s/h2s
-        // ---- stage weights of this chunk (fp32 -> bf16; autocast casts the weights)
-        for (int i = tid; i < LF_CH * (C / 8); i += LF_THREADS) {
-            const int r = i / (C / 8), c8 = (i % (C / 8)) * 8;
-            const float* src = a.w1 + static_cast<long long>(h0 + r) * C + c8;
-            const float4 u = *reinterpret_cast<const float4*>(src), v = *reinterpret_cast<const float4*>(src + 4);
-            *reinterpret_cast<uint4*>(s.w1s + r * XS_LD + c8) =
-                make_uint4(lf::pack2(u.x, u.y), lf::pack2(u.z, u.w), lf::pack2(v.x, v.y), lf::pack2(v.z, v.w));
-        }
-        for (int i = tid; i < C * (LF_CH / 8); i += LF_THREADS) {
-            const int r = i / (LF_CH / 8), c8 = (i % (LF_CH / 8)) * 8;
-            const float* src = a.w2 + static_cast<long long>(r) * HID + h0 + c8;
-            const float4 u = *reinterpret_cast<const float4*>(src), v = *reinterpret_cast<const float4*>(src + 4);
-            *reinterpret_cast<uint4*>(s.w2s + r * LF_HS_LD + c8) =
-                make_uint4(lf::pack2(u.x, u.y), lf::pack2(u.z, u.w), lf::pack2(v.x, v.y), lf::pack2(v.z, v.w));
-        }
-        for (int i = tid; i < 9 * LF_CH; i += LF_THREADS) {
-            const int tap = i / LF_CH, c = i - tap * LF_CH;
-            s.dww[i] = lf::rbf(a.w_dw[static_cast<long long>(h0 + c) * 9 + tap]);
-        }
-        if (tid < LF_CH) { s.dwb[tid] = lf::rbf(a.b_dw[h0 + tid]); s.b1s[tid] = lf::rbf(a.b1[h0 + tid]); }
-        __syncthreads();
+        const unsigned char* img = a.wimg + static_cast<size_t>(ch) * I::BYTES;
+        cp_async_wait<0>();                            // this chunk's w1s / b1s (issued during the previous chunk) landed
+        __syncthreads();                               // ... for every thread; previous chunk's GEMM2 / dwconv are done
+        stage(s.w2s, img + I::W2, C * LF_HS_LD * 2);   // consumed after GEMM1 + epilogue 1: latency hidden
+        stage(s.dww, img + I::DWW, 9 * LF_CH * 4);
+        stage(s.dwb, img + I::DWB, 256);
+        cp_async_commit();
 
         // ---- GEMM1: h1[112 x 64] = xs[112 x C] . w1s^T ; warp: 4 (or 3) m-tiles x 2 n-tiles
         {
@@ -238,6 +272,13 @@ __global__ void __launch_bounds__(LF_THREADS, (C <= 64 ? 3 : 2)) leff_fused_kern
                 }
             }
         }
+        __syncthreads();                               // h1s complete; every warp is done reading w1s / b1s
+        if (ch + 1 < NCHUNK) {
+            stage(s.w1s, img + I::BYTES + I::W1, 64 * XS_LD * 2);
+            stage(s.b1s, img + I::BYTES + I::B1, 256);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();                            // w2s / dww / dwb of this chunk landed (newest group may still fly)
         __syncthreads();
 
         // ---- depthwise 3x3 + bias -> bf16 -> GELU -> bf16 on the 8x8 interior: thread = (8-channel group, 2 pixels)
@@ -309,6 +350,8 @@ __global__ void __launch_bounds__(LF_THREADS, (C <= 64 ? 3 : 2)) leff_fused_kern
 
 template <int C>
 cudaError_t launch_leff_fused_c(const LeffFusedArgs& a, cudaStream_t stream) {
+    leff_prep_weights_kernel<C><<<4 * C / 64, 256, 0, stream>>>(a.w1, a.b1, a.w2, a.w_dw, a.b_dw,
+                                                              const_cast<unsigned char*>(a.wimg));
     auto k = leff_fused_kernel<C>;
     const size_t smem = sizeof(LeffFusedSmem<C>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

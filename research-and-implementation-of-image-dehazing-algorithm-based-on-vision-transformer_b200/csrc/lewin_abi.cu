@@ -223,7 +223,7 @@ int check_leff(const LewinLeffFwdArgs* a) {
 
 size_t leff_fwd_ws(const LewinLeffFwdArgs* a) {
     const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
-    return 2 * align_up(tokens * sizeof(float), 256);
+    return 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(a->C), 256);
 }
 
 bool leff_use_fused(const LewinLeffFwdArgs* a, bool is_bf16) {
@@ -258,6 +258,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
             fa.ln_w = a->ln_w; fa.ln_b = a->ln_b; fa.w1 = a->w1; fa.b1 = a->b1;
             fa.w_dw = a->w_dw; fa.b_dw = a->b_dw; fa.w2 = a->w2; fa.b2 = a->b2;
             fa.drop_scale = a->drop_scale; fa.B = a->B; fa.H = a->H; fa.W = a->W;
+            fa.wimg = wsp + 2 * align_up(tokens * sizeof(float), 256);
             kt.begin(LEWIN_LEFF_K_FUSED);
             CK(launch_leff_fused(C, fa, stream));
             kt.end(LEWIN_LEFF_K_FUSED);

@@ -202,88 +202,112 @@ cudaError_t launch_wgrad(WgradArgs<T> g, int num_sms, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------ LayerNorm backward
 // dx[row] = dres[row] + LNbwd(dz[row]; x[row], gamma);  dgamma += sum dz * xhat;  dbeta += sum dz.
-// One warp per row (C <= 512), grid-stride over rows, per-lane register partials for dgamma/dbeta.
-template <typename T>
+// G lanes per row with 16-byte loads (a warp streams 32/G rows at once), grid-stride over rows, per-lane register
+// partials for dgamma / dbeta reduced through shuffles + shared memory, one global atomic per column per block.
+template <typename T, int G, int MAXV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ x,
                                                      const T* __restrict__ dres, T* __restrict__ dx,
                                                      const float* __restrict__ gamma, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, long long rows, int C) {
-    constexpr int MAXV = 4;                       // float4 chunks per lane: C <= 512
-    const int lane = threadIdx.x & 31;
+    constexpr int EPL = 16 / sizeof(T);
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
     const long long warp_global = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-    const int nv = C / 128 + ((C % 128) ? 1 : 0);
-    float4 gacc[MAXV], bacc[MAXV], gm[MAXV];
+    float gacc[MAXV][EPL], bacc[MAXV][EPL], gm[MAXV][EPL];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        gacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        bacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int k = lane * 4 + i * 128;
-        gm[i] = (i < nv && k < C) ? *reinterpret_cast<const float4*>(gamma + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k = (gl + i * G) * EPL;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) { gacc[i][j] = 0.f; bacc[i][j] = 0.f; gm[i][j] = (k < C) ? gamma[k + j] : 0.f; }
     }
-    for (long long row = warp_global; row < rows; row += nwarps) {
-        float4 xv[MAXV], dv[MAXV];
+    auto load = [&](const T* p, float (&f)[EPL]) {
+        if (sizeof(T) == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(p);
+            f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+        } else {
+            const uint4 u = *reinterpret_cast<const uint4*>(p);
+            f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xFFFF0000u);
+            f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xFFFF0000u);
+            f[EPL - 4] = __uint_as_float(u.z << 16); f[EPL - 3] = __uint_as_float(u.z & 0xFFFF0000u);
+            f[EPL - 2] = __uint_as_float(u.w << 16); f[EPL - 1] = __uint_as_float(u.w & 0xFFFF0000u);
+        }
+    };
+    for (long long row0 = warp_global * RPW; row0 < rows; row0 += nwarps * RPW) {
+        const long long row = row0 + sub;
+        const bool live = row < rows;
+        float xv[MAXV][EPL], dv[MAXV][EPL];
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
-            const int k = lane * 4 + i * 128;
-            const bool ok = i < nv && k < C;
-            xv[i] = ok ? ld4(x + row * C + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            dv[i] = ok ? ld4(dz + row * C + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+            const int k = (gl + i * G) * EPL;
+            if (live && k < C) { load(x + row * C + k, xv[i]); load(dz + row * C + k, dv[i]); }
+            else {
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) { xv[i][j] = 0.f; dv[i][j] = 0.f; }
+            }
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) s += xv[i][j];
         }
-        const float mu = group_sum<32>(s) / C;
+        const float mu = group_sum<G>(s) / C;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
-            const int k = lane * 4 + i * 128;
-            if (i < nv && k < C) {
-                xv[i].x -= mu; xv[i].y -= mu; xv[i].z -= mu; xv[i].w -= mu;
-                q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+            const int k = (gl + i * G) * EPL;
+            if (k < C) {
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) { xv[i][j] -= mu; q += xv[i][j] * xv[i][j]; }
             }
         }
-        const float rs = rsqrtf(group_sum<32>(q) / C + 1e-5f);
-        float s1 = 0.f, s2 = 0.f;       // sum(dxh), sum(dxh * xhat)
+        const float rs = rsqrtf(group_sum<G>(q) / C + 1e-5f);
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
-            const int k = lane * 4 + i * 128;
-            if (i < nv && k < C) {
-                xv[i].x *= rs; xv[i].y *= rs; xv[i].z *= rs; xv[i].w *= rs;     // xhat
-                gacc[i].x += dv[i].x * xv[i].x; gacc[i].y += dv[i].y * xv[i].y;
-                gacc[i].z += dv[i].z * xv[i].z; gacc[i].w += dv[i].w * xv[i].w;
-                bacc[i].x += dv[i].x; bacc[i].y += dv[i].y; bacc[i].z += dv[i].z; bacc[i].w += dv[i].w;
-                dv[i].x *= gm[i].x; dv[i].y *= gm[i].y; dv[i].z *= gm[i].z; dv[i].w *= gm[i].w;   // dxh
-                s1 += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
-                s2 += (dv[i].x * xv[i].x + dv[i].y * xv[i].y) + (dv[i].z * xv[i].z + dv[i].w * xv[i].w);
+            const int k = (gl + i * G) * EPL;
+            if (live && k < C) {
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    xv[i][j] *= rs;                                   // xhat
+                    gacc[i][j] += dv[i][j] * xv[i][j];
+                    bacc[i][j] += dv[i][j];
+                    dv[i][j] *= gm[i][j];                             // dxhat
+                    s1 += dv[i][j];
+                    s2 += dv[i][j] * xv[i][j];
+                }
             }
         }
-        s1 = group_sum<32>(s1) / C;
-        s2 = group_sum<32>(s2) / C;
+        s1 = group_sum<G>(s1) / C;
+        s2 = group_sum<G>(s2) / C;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
-            const int k = lane * 4 + i * 128;
-            if (i < nv && k < C) {
-                float4 r = dres ? ld4(dres + row * C + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                r.x += rs * (dv[i].x - s1 - xv[i].x * s2);
-                r.y += rs * (dv[i].y - s1 - xv[i].y * s2);
-                r.z += rs * (dv[i].z - s1 - xv[i].z * s2);
-                r.w += rs * (dv[i].w - s1 - xv[i].w * s2);
-                st4(dx + row * C + k, r);
+            const int k = (gl + i * G) * EPL;
+            if (live && k < C) {
+                float r[EPL];
+                if (dres) load(dres + row * C + k, r);
+                else {
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) r[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) r[j] += rs * (dv[i][j] - s1 - xv[i][j] * s2);
+#pragma unroll
+                for (int j = 0; j < EPL; j += 4) st4(dx + row * C + k + j, make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]));
             }
         }
     }
-    // block reduction of the per-lane partials through shared memory, then one atomic per column per block
-    __shared__ float sg[512], sb[512];
+    // combine the row sub-groups of the warp, then the block, then one atomic per column
+    __shared__ float sg[1024], sb[1024];
     for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int k = lane * 4 + i * 128;
-        if (i < nv && k < C) {
-            atomicAdd(&sg[k], gacc[i].x); atomicAdd(&sg[k + 1], gacc[i].y);
-            atomicAdd(&sg[k + 2], gacc[i].z); atomicAdd(&sg[k + 3], gacc[i].w);
-            atomicAdd(&sb[k], bacc[i].x); atomicAdd(&sb[k + 1], bacc[i].y);
-            atomicAdd(&sb[k + 2], bacc[i].z); atomicAdd(&sb[k + 3], bacc[i].w);
+        const int k = (gl + i * G) * EPL;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            float gv = gacc[i][j], bv = bacc[i][j];
+#pragma unroll
+            for (int o = G; o < 32; o <<= 1) { gv += __shfl_xor_sync(0xffffffffu, gv, o); bv += __shfl_xor_sync(0xffffffffu, bv, o); }
+            if (sub == 0 && k < C) { atomicAdd(&sg[k + j], gv); atomicAdd(&sb[k + j], bv); }
         }
     }
     __syncthreads();
@@ -296,11 +320,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dz, c
 template <typename T>
 cudaError_t launch_ln_bwd(const T* dz, const T* x, const T* dres, T* dx, const float* gamma, float* dgamma,
                           float* dbeta, long long rows, int C, int num_sms, cudaStream_t st) {
-    long long blocks = (rows + 7) / 8;
-    const long long cap = static_cast<long long>(num_sms) * 8;
-    if (blocks > cap) blocks = cap;
-    ln_bwd_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, st>>>(dz, x, dres, dx, gamma, dgamma, dbeta, rows, C);
-    return cudaGetLastError();
+    constexpr int EPL = 16 / sizeof(T);
+    const int chunks = C / EPL;
+    auto go = [&](auto gtag, auto vtag) -> cudaError_t {
+        constexpr int G = decltype(gtag)::value, MAXV = decltype(vtag)::value;
+        long long blocks = (rows + 8 * (32 / G) - 1) / (8 * (32 / G));
+        const long long cap = static_cast<long long>(num_sms) * 8;
+        if (blocks > cap) blocks = cap;
+        ln_bwd_kernel<T, G, MAXV><<<static_cast<unsigned>(blocks), 256, 0, st>>>(dz, x, dres, dx, gamma, dgamma, dbeta, rows, C);
+        return cudaGetLastError();
+    };
+    using std::integral_constant;
+    if (C > 1024 || chunks > 128) return cudaErrorInvalidValue;
+    if (chunks <= 4) return go(integral_constant<int, 4>{}, integral_constant<int, 1>{});
+    if (chunks <= 8) return go(integral_constant<int, 8>{}, integral_constant<int, 1>{});
+    if (chunks <= 16) return go(integral_constant<int, 16>{}, integral_constant<int, 1>{});
+    if (chunks <= 32) return go(integral_constant<int, 32>{}, integral_constant<int, 1>{});
+    if (chunks <= 64) return go(integral_constant<int, 32>{}, integral_constant<int, 2>{});
+    return go(integral_constant<int, 32>{}, integral_constant<int, 4>{});
 }
 
 // ------------------------------------------------------------------------------ depthwise conv backward
@@ -316,9 +353,12 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const T* __restrict__ g
                                                          int B, int H, int W, int Ch) {
     const int cgl = threadIdx.x & 31;          // channel group within the slab
     const int pl = threadIdx.x >> 5;           // pixel lane 0..7
+    constexpr int STRIP = 16;                  // rows per work item
     const int slabs = (Ch + 127) / 128;
     const int xgroups = (W + 7) / 8;
-    const long long items = static_cast<long long>(B) * slabs * xgroups;
+    const int strips = (H + STRIP - 1) / STRIP;
+    const long long per_slab = static_cast<long long>(B) * xgroups * strips;
+    const long long items = per_slab * slabs;       // slab-major: a CTA's item sequence is monotone in the slab index
     __shared__ float red[8][32][41];
 
     float wacc[4][9], bacc[4];
@@ -360,10 +400,13 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const T* __restrict__ g
     };
 
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-        const int xg = static_cast<int>(item % xgroups);
-        long long rest = item / xgroups;
-        const int slab = static_cast<int>(rest % slabs);
-        const int b = static_cast<int>(rest / slabs);
+        const int slab = static_cast<int>(item / per_slab);
+        long long rest = item - slab * per_slab;
+        const int xg = static_cast<int>(rest % xgroups);
+        rest /= xgroups;
+        const int strip = static_cast<int>(rest % strips);
+        const int b = static_cast<int>(rest / strips);
+        const int ys = strip * STRIP, ye = min(ys + STRIP, H);
         if (slab != cur_slab) {
             if (cur_slab >= 0) flush(cur_slab);
             cur_slab = slab;
@@ -391,8 +434,8 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const T* __restrict__ g
         };
         float4 dwin[3][3];      // da2 at rows y-1..y+1, cols x-1..x+1
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { dwin[0][j] = make_float4(0.f, 0.f, 0.f, 0.f); dwin[1][j] = ld_da2(0, xx - 1 + j); }
-        for (int y = 0; y < H; ++y) {
+        for (int j = 0; j < 3; ++j) { dwin[0][j] = ld_da2(ys - 1, xx - 1 + j); dwin[1][j] = ld_da2(ys, xx - 1 + j); }
+        for (int y = ys; y < ye; ++y) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) dwin[2][j] = ld_da2(y + 1, xx - 1 + j);
             // data gradient: dh1[y,x] = sum_{ky,kx} da2[y-ky+1, x-kx+1] * w[ky,kx]
@@ -435,8 +478,8 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const T* __restrict__ g
 template <typename T>
 cudaError_t launch_dwconv_bwd(const T* g2, const T* a2, const T* h1, const T* a1, T* da1, const float* w, float* dw,
                               float* dbias, int B, int H, int W, int Ch, int num_sms, cudaStream_t st) {
-    const long long items = static_cast<long long>(B) * ((Ch + 127) / 128) * ((W + 7) / 8);
-    long long grid = static_cast<long long>(num_sms) * 4;
+    const long long items = static_cast<long long>(B) * ((Ch + 127) / 128) * ((W + 7) / 8) * ((H + 15) / 16);
+    long long grid = static_cast<long long>(num_sms) * 8;
     if (grid > items) grid = items;
     dwconv_bwd_kernel<T><<<static_cast<unsigned>(grid), 256, 0, st>>>(g2, a2, h1, a1, da1, w, dw, dbias, B, H, W, Ch);
     return cudaGetLastError();

@@ -108,7 +108,76 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }  // namespace tc
 
 constexpr int TC_BM = 128;
+
 constexpr int TC_THREADS_MAX = 256;
+
+// Epilogue shared by the tcgen05 GEMM kernels: thread == TMEM lane == tile row; the two warpgroups (if present) split the
+// 32-column chunks.  bias -> {store | bf16 table GELU | DropPath scale + residual} -> 16-byte bf16 row stores.
+template <int BN, int EPI, int NWG>
+__device__ __forceinline__ void tc_epilogue(const GemmArgs<__nv_bfloat16>& g, uint32_t tmem_d, const long long* offY,
+                                            const float* s_bias, const uint16_t* gtab, int n0) {
+    using T = __nv_bfloat16;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    {
+        const int r = (warp & 3) * 32 + (tid & 31);
+        const int half = warp >> 2;
+        const long long oy = offY[r];
+        float sc = 1.f;
+        if (EPI == EPI_BIAS_RESID && g.drop_scale && oy >= 0) sc = g.drop_scale[(oy / g.ldy) / g.tokens_per_image];
+        const uint32_t lane_addr = tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 32 * NWG) {
+            float v[32];
+            tc::tmem_ld32(lane_addr + c0, v);
+            if (oy < 0) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
+            T* yrow = g.Y + oy + n0 + c0;
+            if (EPI == EPI_BIAS_GELU && !g.Y2) {       // inference: bf16 bits in -> table -> bf16 bits out
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint32_t q[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const uint32_t in2 = tc::pack_bf16(v[j + 2 * h], v[j + 2 * h + 1]);
+                        q[h] = gelu_bits(gtab, in2 & 0xFFFFu) | (gelu_bits(gtab, in2 >> 16) << 16);
+                    }
+                    *reinterpret_cast<uint4*>(yrow + j) = make_uint4(q[0], q[1], q[2], q[3]);
+                }
+                continue;
+            } else if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = Act<T>::round(v[j]);
+                if (g.Y2) {
+                    T* prow = g.Y2 + oy + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8)
+                        *reinterpret_cast<uint4*>(prow + j) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
+                                                                         tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_tab(gtab, v[j]);
+            } else if (EPI == EPI_BIAS_RESID) {
+                const T* rrow = g.R + oy + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 rv = *reinterpret_cast<const uint4*>(rrow + j);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 t2 = __bfloat1622float2(h[q]);
+                        v[j + 2 * q] = t2.x + sc * Act<T>::round(v[j + 2 * q]);
+                        v[j + 2 * q + 1] = t2.y + sc * Act<T>::round(v[j + 2 * q + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(yrow + j) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
+                                                                 tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
+        }
+    }
+}
 
 template <int BN, int KC, int STAGES, int EPI>
 constexpr size_t tc_smem_bytes() {
@@ -270,68 +339,193 @@ __global__ void __launch_bounds__(TC_THREADS, (TC_THREADS == 128 ? (STAGES == 1 
     tc::tc_fence_after();
 
     // ---- epilogue: thread == TMEM lane == tile row
-    {
-        const int r = (warp & 3) * 32 + (tid & 31);
-        const int half = warp >> 2;
-        const long long oy = offY[r];
-        float sc = 1.f;
-        if (EPI == EPI_BIAS_RESID && g.drop_scale && oy >= 0) sc = g.drop_scale[(oy / g.ldy) / g.tokens_per_image];
-        const uint32_t lane_addr = tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-#pragma unroll 1
-        for (int c0 = half * 32; c0 < BN; c0 += 32 * NWG) {
-            float v[32];
-            tc::tmem_ld32(lane_addr + c0, v);
-            if (oy < 0) continue;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
-            T* yrow = g.Y + oy + n0 + c0;
-            if (EPI == EPI_BIAS_GELU && !g.Y2) {       // inference: bf16 bits in -> table -> bf16 bits out
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    uint32_t q[4];
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const uint32_t in2 = tc::pack_bf16(v[j + 2 * h], v[j + 2 * h + 1]);
-                        q[h] = gelu_bits(gtab, in2 & 0xFFFFu) | (gelu_bits(gtab, in2 >> 16) << 16);
-                    }
-                    *reinterpret_cast<uint4*>(yrow + j) = make_uint4(q[0], q[1], q[2], q[3]);
-                }
-                continue;
-            } else if (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = Act<T>::round(v[j]);
-                if (g.Y2) {
-                    T* prow = g.Y2 + oy + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8)
-                        *reinterpret_cast<uint4*>(prow + j) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
-                                                                         tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = gelu_tab(gtab, v[j]);
-            } else if (EPI == EPI_BIAS_RESID) {
-                const T* rrow = g.R + oy + n0 + c0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const uint4 rv = *reinterpret_cast<const uint4*>(rrow + j);
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 t2 = __bfloat1622float2(h[q]);
-                        v[j + 2 * q] = t2.x + sc * Act<T>::round(v[j + 2 * q]);
-                        v[j + 2 * q + 1] = t2.y + sc * Act<T>::round(v[j + 2 * q + 1]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-                *reinterpret_cast<uint4*>(yrow + j) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
-                                                                 tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
-        }
-    }
+    tc_epilogue<BN, EPI, NWG>(g, tmem_d, offY, s_bias, gtab, n0);
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent variant for K <= 2*KC (the HBM-heavy levels): the weight tile W[BN x K] is converted once and stays
+// resident in shared memory, the CTA walks row tiles (stride gridDim.x) and the global loads of the NEXT tile's A rows
+// (with their LayerNorm / gather prologue) are issued before the current tile's accumulator is drained, so DRAM
+// latency is hidden behind the TMEM epilogue instead of being exposed once per tile.
+template <int BN, int KC, int NKC, int EPI>
+constexpr size_t tcp_smem_bytes() {
+    return 1024 + NKC * (TC_BM * KC * 2) + NKC * (BN * KC * 2) + 2 * TC_BM * (2 * 8 + 3 * 4) + BN * 4 + 64 +
+           (EPI == EPI_BIAS_GELU ? kGeluTabSize * 2 : 0);
+}
+
+template <int BN, int KC, int NKC, int EPI>
+__global__ void __launch_bounds__(256, 2) gemm_tcp_kernel(const GemmArgs<__nv_bfloat16> g, int row_tiles) {
+    using T = __nv_bfloat16;
+    constexpr int THREADS = 256;
+    constexpr int CPR = KC / 8;
+    constexpr int A_CHUNK = TC_BM * KC * 2;
+    constexpr int W_CHUNK = BN * KC * 2;
+    constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* As = base;                          // [NKC][A_CHUNK]
+    unsigned char* Ws = As + NKC * A_CHUNK;            // [NKC][W_CHUNK] resident
+    long long* offA = reinterpret_cast<long long*>(Ws + NKC * W_CHUNK);     // [2][128] double-buffered row info
+    long long* offY = offA + 2 * TC_BM;
+    float* s_mean = reinterpret_cast<float*>(offY + 2 * TC_BM);
+    float* s_rstd = s_mean + 2 * TC_BM;
+    float* s_ascale = s_rstd + 2 * TC_BM;
+    float* s_bias = s_ascale + 2 * TC_BM;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(s_bias + BN);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    uint16_t* gtab = reinterpret_cast<uint16_t*>(mbar + 4);
+    if (EPI == EPI_BIAS_GELU) gelu_tab_to_smem(gtab, threadIdx.x, THREADS);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int n0 = blockIdx.y * BN;
+    const bool has_ln = g.mean != nullptr;
+
+    auto rowinfo = [&](long long tile, int buf) {
+        if (tid < TC_BM) {
+            const long long m = tile * TC_BM + tid;
+            long long oa = -1, oy = -1;
+            float mu = 0.f, rs = 1.f, asc = 1.f;
+            if (m < g.M) {
+                const long long tok = (g.mapA || g.mapY) ? g.map.token(m) : m;
+                const long long ra = g.mapA ? tok : m, ry = g.mapY ? tok : m;
+                oa = ra * g.lda; oy = ry * g.ldy;
+                if (has_ln) { mu = g.mean[ra]; rs = g.rstd[ra]; }
+                if (g.a_row_scale) asc = g.a_row_scale[ra / g.tokens_per_image];
+            }
+            const int o = buf * TC_BM + tid;
+            offA[o] = oa; offY[o] = oy; s_mean[o] = mu; s_rstd[o] = rs; s_ascale[o] = asc;
+        }
+    };
+    constexpr int A_CH = TC_BM * CPR / THREADS;
+    uint4 areg[NKC][A_CH];
+    auto load_a = [&](int buf) {
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+            for (int i = 0; i < A_CH; ++i) {
+                const int c = tid + i * THREADS;
+                const int r = c / CPR, ch = c % CPR;
+                const long long o = offA[buf * TC_BM + r];
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (o >= 0) {
+                    const int k = kc * KC + ch * 8;
+                    v = *reinterpret_cast<const uint4*>(g.A + o + k);
+                    if (has_ln || g.a_row_scale) {
+                        float f[8];
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(h[j]); f[2 * j] = t2.x; f[2 * j + 1] = t2.y; }
+                        if (g.a_row_scale) {
+                            const float asc = s_ascale[buf * TC_BM + r];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] *= asc;
+                        }
+                        if (has_ln) {
+                            const float mu = s_mean[buf * TC_BM + r], rs = s_rstd[buf * TC_BM + r];
+                            const float4 w0 = *reinterpret_cast<const float4*>(g.ln_w + k);
+                            const float4 w1 = *reinterpret_cast<const float4*>(g.ln_w + k + 4);
+                            const float4 b0 = *reinterpret_cast<const float4*>(g.ln_b + k);
+                            const float4 b1 = *reinterpret_cast<const float4*>(g.ln_b + k + 4);
+                            f[0] = (f[0] - mu) * rs * w0.x + b0.x; f[1] = (f[1] - mu) * rs * w0.y + b0.y;
+                            f[2] = (f[2] - mu) * rs * w0.z + b0.z; f[3] = (f[3] - mu) * rs * w0.w + b0.w;
+                            f[4] = (f[4] - mu) * rs * w1.x + b1.x; f[5] = (f[5] - mu) * rs * w1.y + b1.y;
+                            f[6] = (f[6] - mu) * rs * w1.z + b1.z; f[7] = (f[7] - mu) * rs * w1.w + b1.w;
+                        }
+                        v.x = tc::pack_bf16(f[0], f[1]); v.y = tc::pack_bf16(f[2], f[3]);
+                        v.z = tc::pack_bf16(f[4], f[5]); v.w = tc::pack_bf16(f[6], f[7]);
+                    }
+                }
+                areg[kc][i] = v;
+            }
+    };
+    auto store_a = [&]() {
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+            for (int i = 0; i < A_CH; ++i) {
+                const int c = tid + i * THREADS;
+                *reinterpret_cast<uint4*>(As + kc * A_CHUNK + tc::swz_off<KC>(c / CPR, c % CPR)) = areg[kc][i];
+            }
+    };
+    auto issue = [&]() {
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+            const uint64_t da = tc::make_desc<KC>(tc::smem_u32(As + kc * A_CHUNK));
+            const uint64_t db = tc::make_desc<KC>(tc::smem_u32(Ws + kc * W_CHUNK));
+#pragma unroll
+            for (int k16 = 0; k16 < KC / 16; ++k16)
+                tc::mma_bf16(*tmem_slot, da + 2 * k16, db + 2 * k16, IDESC, (kc > 0 || k16 > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&mbar[0]);
+    };
+
+    // ---- one-time setup: bias, barrier, TMEM, resident weight tile
+    for (int i = tid; i < BN; i += THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[n0 + i]) : 0.f;
+    if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    for (int c = tid; c < NKC * BN * CPR; c += THREADS) {
+        const int kc = c / (BN * CPR), rem = c - kc * (BN * CPR);
+        const int r = rem / CPR, ch = rem % CPR;
+        const float* src = g.Wt + static_cast<long long>(n0 + r) * g.K + kc * KC + ch * 8;
+        const float4 a4 = *reinterpret_cast<const float4*>(src);
+        const float4 b4 = *reinterpret_cast<const float4*>(src + 4);
+        *reinterpret_cast<uint4*>(Ws + kc * W_CHUNK + tc::swz_off<KC>(r, ch)) =
+            make_uint4(tc::pack_bf16(a4.x, a4.y), tc::pack_bf16(a4.z, a4.w), tc::pack_bf16(b4.x, b4.y), tc::pack_bf16(b4.z, b4.w));
+    }
+    long long tile = blockIdx.x;
+    int buf = 0;
+    rowinfo(tile, 0);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    load_a(0);
+    store_a();
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) { tc::tc_fence_after(); issue(); }
+    uint32_t phase = 0;
+    while (true) {
+        const long long next = tile + gridDim.x;
+        const bool has_next = next < row_tiles;
+        if (has_next) rowinfo(next, buf ^ 1);
+        __syncthreads();
+        if (has_next) load_a(buf ^ 1);                 // DRAM loads of the next tile fly during the wait + epilogue
+        tc::mbar_wait(&mbar[0], phase);
+        phase ^= 1;
+        tc::tc_fence_after();
+        tc_epilogue<BN, EPI, 2>(g, tmem_d, offY + buf * TC_BM, s_bias, gtab, n0);
+        tc::tc_fence_before();
+        __syncthreads();                               // accumulator drained, A tile free (its MMAs completed)
+        if (!has_next) break;
+        store_a();
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { tc::tc_fence_after(); issue(); }
+        tile = next;
+        buf ^= 1;
+    }
+    if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
+}
+
+template <int BN, int KC, int NKC, int EPI>
+cudaError_t launch_gemm_tcp(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaStream_t stream) {
+    constexpr size_t smem = tcp_smem_bytes<BN, KC, NKC, EPI>();
+    auto k = gemm_tcp_kernel<BN, KC, NKC, EPI>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const int row_tiles = static_cast<int>((g.M + TC_BM - 1) / TC_BM);
+    const int col_tiles = g.N / BN;
+    int gx = (2 * num_sms + col_tiles - 1) / col_tiles;
+    if (gx > row_tiles) gx = row_tiles;
+    k<<<dim3(gx, col_tiles), 256, smem, stream>>>(g, row_tiles);
+    return cudaGetLastError();
 }
 
 template <int BN, int KC, int EPI, int STAGES>
@@ -348,8 +542,19 @@ cudaError_t launch_gemm_tc_stages(const GemmArgs<__nv_bfloat16>& g, cudaStream_t
     return cudaGetLastError();
 }
 
+inline int tc_num_sms() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
 template <int BN, int KC, int EPI>
 cudaError_t launch_gemm_tc_inst(const GemmArgs<__nv_bfloat16>& g, cudaStream_t stream) {
+    static const bool persist = [] { const char* e = getenv("LEWIN_NO_PERSIST_GEMM"); return !(e && e[0] == '1'); }();
+    if (persist && g.M >= 4 * TC_BM) {
+        if (g.K == KC) return launch_gemm_tcp<BN, KC, 1, EPI>(g, tc_num_sms(), stream);
+        if (g.K == 2 * KC) return launch_gemm_tcp<BN, KC, 2, EPI>(g, tc_num_sms(), stream);
+    }
     if (g.K == KC) return launch_gemm_tc_stages<BN, KC, EPI, 1>(g, stream);
     return launch_gemm_tc_stages<BN, KC, EPI, 2>(g, stream);
 }

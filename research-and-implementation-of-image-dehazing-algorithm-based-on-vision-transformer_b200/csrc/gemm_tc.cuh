@@ -403,6 +403,8 @@ __global__ void __launch_bounds__(256, 2) gemm_tcp_kernel(const GemmArgs<__nv_bf
     };
     constexpr int A_CH = TC_BM * CPR / THREADS;
     uint4 areg[NKC][A_CH];
+    // raw 16-byte loads only: nothing consumes the registers until store_a, so the loads stay in flight across the
+    // mbarrier wait and the whole TMEM epilogue of the previous tile
     auto load_a = [&](int buf) {
 #pragma unroll
         for (int kc = 0; kc < NKC; ++kc)
@@ -411,45 +413,44 @@ __global__ void __launch_bounds__(256, 2) gemm_tcp_kernel(const GemmArgs<__nv_bf
                 const int c = tid + i * THREADS;
                 const int r = c / CPR, ch = c % CPR;
                 const long long o = offA[buf * TC_BM + r];
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (o >= 0) {
-                    const int k = kc * KC + ch * 8;
-                    v = *reinterpret_cast<const uint4*>(g.A + o + k);
-                    if (has_ln || g.a_row_scale) {
-                        float f[8];
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(h[j]); f[2 * j] = t2.x; f[2 * j + 1] = t2.y; }
-                        if (g.a_row_scale) {
-                            const float asc = s_ascale[buf * TC_BM + r];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] *= asc;
-                        }
-                        if (has_ln) {
-                            const float mu = s_mean[buf * TC_BM + r], rs = s_rstd[buf * TC_BM + r];
-                            const float4 w0 = *reinterpret_cast<const float4*>(g.ln_w + k);
-                            const float4 w1 = *reinterpret_cast<const float4*>(g.ln_w + k + 4);
-                            const float4 b0 = *reinterpret_cast<const float4*>(g.ln_b + k);
-                            const float4 b1 = *reinterpret_cast<const float4*>(g.ln_b + k + 4);
-                            f[0] = (f[0] - mu) * rs * w0.x + b0.x; f[1] = (f[1] - mu) * rs * w0.y + b0.y;
-                            f[2] = (f[2] - mu) * rs * w0.z + b0.z; f[3] = (f[3] - mu) * rs * w0.w + b0.w;
-                            f[4] = (f[4] - mu) * rs * w1.x + b1.x; f[5] = (f[5] - mu) * rs * w1.y + b1.y;
-                            f[6] = (f[6] - mu) * rs * w1.z + b1.z; f[7] = (f[7] - mu) * rs * w1.w + b1.w;
-                        }
-                        v.x = tc::pack_bf16(f[0], f[1]); v.y = tc::pack_bf16(f[2], f[3]);
-                        v.z = tc::pack_bf16(f[4], f[5]); v.w = tc::pack_bf16(f[6], f[7]);
-                    }
-                }
-                areg[kc][i] = v;
+                areg[kc][i] = o >= 0 ? *reinterpret_cast<const uint4*>(g.A + o + kc * KC + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
             }
     };
-    auto store_a = [&]() {
+    // LayerNorm / row-scale prologue applied on the way into the swizzled smem tile
+    auto store_a = [&](int buf) {
 #pragma unroll
         for (int kc = 0; kc < NKC; ++kc)
 #pragma unroll
             for (int i = 0; i < A_CH; ++i) {
                 const int c = tid + i * THREADS;
-                *reinterpret_cast<uint4*>(As + kc * A_CHUNK + tc::swz_off<KC>(c / CPR, c % CPR)) = areg[kc][i];
+                const int r = c / CPR, ch = c % CPR;
+                uint4 v = areg[kc][i];
+                if ((has_ln || g.a_row_scale) && offA[buf * TC_BM + r] >= 0) {
+                    const int k = kc * KC + ch * 8;
+                    float f[8];
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { float2 t2 = __bfloat1622float2(h[j]); f[2 * j] = t2.x; f[2 * j + 1] = t2.y; }
+                    if (g.a_row_scale) {
+                        const float asc = s_ascale[buf * TC_BM + r];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] *= asc;
+                    }
+                    if (has_ln) {
+                        const float mu = s_mean[buf * TC_BM + r], rs = s_rstd[buf * TC_BM + r];
+                        const float4 w0 = *reinterpret_cast<const float4*>(g.ln_w + k);
+                        const float4 w1 = *reinterpret_cast<const float4*>(g.ln_w + k + 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(g.ln_b + k);
+                        const float4 b1 = *reinterpret_cast<const float4*>(g.ln_b + k + 4);
+                        f[0] = (f[0] - mu) * rs * w0.x + b0.x; f[1] = (f[1] - mu) * rs * w0.y + b0.y;
+                        f[2] = (f[2] - mu) * rs * w0.z + b0.z; f[3] = (f[3] - mu) * rs * w0.w + b0.w;
+                        f[4] = (f[4] - mu) * rs * w1.x + b1.x; f[5] = (f[5] - mu) * rs * w1.y + b1.y;
+                        f[6] = (f[6] - mu) * rs * w1.z + b1.z; f[7] = (f[7] - mu) * rs * w1.w + b1.w;
+                    }
+                    v.x = tc::pack_bf16(f[0], f[1]); v.y = tc::pack_bf16(f[2], f[3]);
+                    v.z = tc::pack_bf16(f[4], f[5]); v.w = tc::pack_bf16(f[6], f[7]);
+                }
+                *reinterpret_cast<uint4*>(As + kc * A_CHUNK + tc::swz_off<KC>(r, ch)) = v;
             }
     };
     auto issue = [&]() {
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(256, 2) gemm_tcp_kernel(const GemmArgs<__nv_bf
     const uint32_t tmem_d = *tmem_slot;
 
     load_a(0);
-    store_a();
+    store_a(0);
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == 0) { tc::tc_fence_after(); issue(); }
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(256, 2) gemm_tcp_kernel(const GemmArgs<__nv_bf
         tc::tc_fence_before();
         __syncthreads();                               // accumulator drained, A tile free (its MMAs completed)
         if (!has_next) break;
-        store_a();
+        store_a(buf ^ 1);
         tc::fence_proxy_async();
         __syncthreads();
         if (tid == 0) { tc::tc_fence_after(); issue(); }

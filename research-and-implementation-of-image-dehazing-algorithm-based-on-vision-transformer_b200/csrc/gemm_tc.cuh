@@ -115,7 +115,8 @@ constexpr int TC_THREADS_MAX = 256;
 // 32-column chunks.  bias -> {store | bf16 table GELU | DropPath scale + residual} -> 16-byte bf16 row stores.
 template <int BN, int EPI, int NWG>
 __device__ __forceinline__ void tc_epilogue(const GemmArgs<__nv_bfloat16>& g, uint32_t tmem_d, const long long* offY,
-                                            const float* s_bias, const uint16_t* gtab, int n0) {
+                                            const float* s_bias, const uint16_t* gtab, int n0,
+                                            const float* s_rowscale = nullptr) {
     using T = __nv_bfloat16;
     const int tid = threadIdx.x, warp = tid >> 5;
     {
@@ -130,6 +131,11 @@ __device__ __forceinline__ void tc_epilogue(const GemmArgs<__nv_bfloat16>& g, ui
             float v[32];
             tc::tmem_ld32(lane_addr + c0, v);
             if (oy < 0) continue;
+            if (s_rowscale) {                      // (s * a) . W == s * (a . W): per-row DropPath factor of the A operand
+                const float rsc = s_rowscale[r];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= rsc;
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += s_bias[c0 + j];
             T* yrow = g.Y + oy + n0 + c0;
@@ -527,6 +533,210 @@ cudaError_t launch_gemm_tcp(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaS
     if (gx > row_tiles) gx = row_tiles;
     k<<<dim3(gx, col_tiles), 256, smem, stream>>>(g, row_tiles);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Asynchronous multi-stage variant for the tensor-bound levels (K > 128): both operands are plain bf16 in global
+// memory (weights pre-converted once per call by convert_w_kernel, LayerNorm applied by ln_apply_kernel), so every
+// 16-byte chunk goes global -> swizzled shared memory with cp.async (no register staging, no conversion in the main
+// loop) through a STAGES-deep ring; tcgen05.commit on a per-stage mbarrier releases a stage back to the loaders.
+__global__ void convert_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, long long n) {
+    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(w + i);
+        *reinterpret_cast<uint2*>(o + i) = make_uint2(tc::pack_bf16(v.x, v.y), tc::pack_bf16(v.z, v.w));
+    } else {
+        for (long long j = i; j < n; ++j) o[j] = __float2bfloat16_rn(w[j]);
+    }
+}
+inline cudaError_t launch_convert_w(const float* w, __nv_bfloat16* o, long long n, cudaStream_t st) {
+    convert_w_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256 + 1), 256, 0, st>>>(w, o, n);
+    return cudaGetLastError();
+}
+
+// xhat[m] = bf16( LN(x[token(m)]) ) for window-ordered row m (or m itself): one warp per row, C <= 1024
+__global__ void __launch_bounds__(256) ln_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       long long rows, int C, int mapped, WinMap map) {
+    const int lane = threadIdx.x & 31;
+    const long long m = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= rows) return;
+    const long long tok = mapped ? map.token(m) : m;
+    const __nv_bfloat16* src = x + tok * C;
+    float f[4][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = (lane + i * 32) * 8;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (k < C) u = *reinterpret_cast<const uint4*>(src + k);
+        f[i][0] = __uint_as_float(u.x << 16); f[i][1] = __uint_as_float(u.x & 0xFFFF0000u);
+        f[i][2] = __uint_as_float(u.y << 16); f[i][3] = __uint_as_float(u.y & 0xFFFF0000u);
+        f[i][4] = __uint_as_float(u.z << 16); f[i][5] = __uint_as_float(u.z & 0xFFFF0000u);
+        f[i][6] = __uint_as_float(u.w << 16); f[i][7] = __uint_as_float(u.w & 0xFFFF0000u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+    const float mu = group_sum<32>(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = (lane + i * 32) * 8;
+        if (k < C) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { f[i][j] -= mu; q += f[i][j] * f[i][j]; }
+        }
+    }
+    const float rs = rsqrtf(group_sum<32>(q) / C + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = (lane + i * 32) * 8;
+        if (k < C) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + k), g1 = *reinterpret_cast<const float4*>(gamma + k + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + k), b1 = *reinterpret_cast<const float4*>(beta + k + 4);
+            *reinterpret_cast<uint4*>(out + m * C + k) = make_uint4(
+                tc::pack_bf16(f[i][0] * rs * g0.x + b0.x, f[i][1] * rs * g0.y + b0.y),
+                tc::pack_bf16(f[i][2] * rs * g0.z + b0.z, f[i][3] * rs * g0.w + b0.w),
+                tc::pack_bf16(f[i][4] * rs * g1.x + b1.x, f[i][5] * rs * g1.y + b1.y),
+                tc::pack_bf16(f[i][6] * rs * g1.z + b1.z, f[i][7] * rs * g1.w + b1.w));
+        }
+    }
+}
+inline cudaError_t launch_ln_apply(const __nv_bfloat16* x, __nv_bfloat16* out, const float* gamma, const float* beta,
+                                   long long rows, int C, int mapped, const WinMap& map, cudaStream_t st) {
+    ln_apply_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(x, out, gamma, beta, rows, C, mapped, map);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ void cp_async16_z(uint32_t smem_addr, const void* gmem, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gmem), "r"(sz));
+}
+
+template <int BN, int STAGES, int EPI>
+constexpr size_t tca_smem_bytes() {
+    return 1024 + STAGES * (TC_BM * 64 * 2 + BN * 64 * 2) + TC_BM * (2 * 8 + 4) + BN * 4 + 64 + 8 * STAGES +
+           (EPI == EPI_BIAS_GELU ? kGeluTabSize * 2 : 0);
+}
+
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(256, (STAGES <= 2 ? 2 : 1)) gemm_tca_kernel(const GemmArgs<__nv_bfloat16> g,
+                                                                             const __nv_bfloat16* __restrict__ Wb) {
+    using T = __nv_bfloat16;
+    constexpr int KC = 64, CPR = 8, THREADS = 256;
+    constexpr int A_STAGE = TC_BM * KC * 2, W_STAGE = BN * KC * 2;
+    constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* As = base;
+    unsigned char* Ws = As + STAGES * A_STAGE;
+    long long* offA = reinterpret_cast<long long*>(Ws + STAGES * W_STAGE);
+    long long* offY = offA + TC_BM;
+    float* s_rowscale = reinterpret_cast<float*>(offY + TC_BM);
+    float* s_bias = s_rowscale + TC_BM;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(s_bias + BN);          // [STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + STAGES);
+    uint16_t* gtab = reinterpret_cast<uint16_t*>(mbar + STAGES + 2);
+    if (EPI == EPI_BIAS_GELU) gelu_tab_to_smem(gtab, threadIdx.x, THREADS);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long m0 = static_cast<long long>(blockIdx.x) * TC_BM;
+    const int n0 = blockIdx.y * BN;
+
+    if (tid < TC_BM) {
+        const long long m = m0 + tid;
+        long long oa = -1, oy = -1;
+        float rsc = 1.f;
+        if (m < g.M) {
+            const long long tok = (g.mapA || g.mapY) ? g.map.token(m) : m;
+            const long long ra = g.mapA ? tok : m, ry = g.mapY ? tok : m;
+            oa = ra * g.lda; oy = ry * g.ldy;
+            if (g.a_row_scale) rsc = g.a_row_scale[ra / g.tokens_per_image];
+        }
+        offA[tid] = oa; offY[tid] = oy; s_rowscale[tid] = rsc;
+    }
+    for (int i = tid; i < BN; i += THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[n0 + i]) : 0.f;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) tc::mbar_init(&mbar[i], 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    const uint32_t As_u = tc::smem_u32(As), Ws_u = tc::smem_u32(Ws);
+    auto load_stage = [&](int kc, int st) {
+#pragma unroll
+        for (int i = 0; i < TC_BM * CPR / THREADS; ++i) {
+            const int c = tid + i * THREADS, r = c >> 3, ch = c & 7;
+            const long long o = offA[r];
+            cp_async16_z(As_u + st * A_STAGE + tc::swz_off<64>(r, ch), g.A + (o >= 0 ? o : 0) + kc * KC + ch * 8, o >= 0);
+        }
+#pragma unroll
+        for (int i = 0; i < BN * CPR / THREADS; ++i) {
+            const int c = tid + i * THREADS, r = c >> 3, ch = c & 7;
+            cp_async16_z(Ws_u + st * W_STAGE + tc::swz_off<64>(r, ch), Wb + static_cast<long long>(n0 + r) * g.K + kc * KC + ch * 8, true);
+        }
+    };
+    const int nk = g.K / KC;
+#pragma unroll
+    for (int p = 0; p < STAGES - 1; ++p) {
+        if (p < nk) load_stage(p, p);
+        cp_async_commit();
+    }
+    for (int kc = 0; kc < nk; ++kc) {
+        const int st = kc % STAGES;
+        const int pre = kc + STAGES - 1;                       // chunk to prefetch into the stage MMA(kc-1) is freeing
+        if (pre < nk) {
+            const int ps = pre % STAGES;
+            if (kc >= 1) tc::mbar_wait(&mbar[ps], ((kc - 1) / STAGES) & 1);
+            load_stage(pre, ps);
+        }
+        cp_async_commit();
+        cp_async_wait<STAGES - 1>();                           // chunk kc has landed (this thread's copies)
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            const uint64_t da = tc::make_desc<64>(As_u + st * A_STAGE);
+            const uint64_t db = tc::make_desc<64>(Ws_u + st * W_STAGE);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem_d, da + 2 * k16, db + 2 * k16, IDESC, (kc > 0 || k16 > 0) ? 1u : 0u);
+            tc::mma_commit(&mbar[st]);
+        }
+    }
+    tc::mbar_wait(&mbar[(nk - 1) % STAGES], ((nk - 1) / STAGES) & 1);
+    tc::tc_fence_after();
+    tc_epilogue<BN, EPI, 2>(g, tmem_d, offY, s_bias, gtab, n0, s_rowscale);
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
+}
+
+template <int BN, int EPI>
+cudaError_t launch_gemm_tca_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, cudaStream_t stream) {
+    constexpr int STAGES = 2;
+    constexpr size_t smem = tca_smem_bytes<BN, STAGES, EPI>();
+    auto k = gemm_tca_kernel<BN, STAGES, EPI>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    dim3 grid(static_cast<unsigned>((g.M + TC_BM - 1) / TC_BM), g.N / BN);
+    k<<<grid, 256, smem, stream>>>(g, Wb);
+    return cudaGetLastError();
+}
+
+// plain-bf16-operand GEMM (K % 64 == 0, no LayerNorm prologue): Wb = bf16 copy of g.Wt
+template <int EPI>
+cudaError_t launch_gemm_tca(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, cudaStream_t stream) {
+    if (g.N % 256 == 0) return launch_gemm_tca_bn<256, EPI>(g, Wb, stream);
+    if (g.N % 192 == 0) return launch_gemm_tca_bn<192, EPI>(g, Wb, stream);
+    if (g.N % 128 == 0) return launch_gemm_tca_bn<128, EPI>(g, Wb, stream);
+    return launch_gemm_tca_bn<64, EPI>(g, Wb, stream);
 }
 
 template <int BN, int KC, int EPI, int STAGES>

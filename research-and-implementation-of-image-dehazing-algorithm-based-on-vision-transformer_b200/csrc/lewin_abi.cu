@@ -73,7 +73,10 @@ int check_attn(const LewinAttnFwdArgs* a) {
 
 size_t attn_fwd_ws(const LewinAttnFwdArgs* a) {
     const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
-    return 2 * align_up(tokens * sizeof(float), 256) + align_up(kTok * kTok, 256) + align_up(kTok * kTok * 4, 256);
+    // + bf16 staging for the async tcgen05 GEMMs (C > 128): LN-applied window-ordered x, bf16 copies of W_qkv / W_out
+    const size_t C = a->C;
+    return 2 * align_up(tokens * sizeof(float), 256) + align_up(kTok * kTok, 256) + align_up(kTok * kTok * 4, 256) +
+           (C > 128 ? align_up(tokens * C * 2, 256) + align_up(4 * C * C * 2, 256) : 0);
 }
 
 template <typename T>
@@ -98,7 +101,8 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     const T* x = static_cast<const T*>(a->x);
 
     const KTimer kt{a->timing, stream};
-    if (!a->windowed) {
+    const bool skip_stats = Act<T>::kIsBf16 && C > 128 && C % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
+    if (!a->windowed && !skip_stats) {
         kt.begin(LEWIN_ATTN_K_LNSTATS);
         CK(launch_ln_stats<T>(x, tokens, C, mean, rstd, stream));
         kt.end(LEWIN_ATTN_K_LNSTATS);
@@ -109,6 +113,20 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     CK(cudaGetLastError());
     kt.end(LEWIN_ATTN_K_CNT);
 
+    bool async_gemm = false;
+    __nv_bfloat16* xhat = nullptr; __nv_bfloat16* wqkv_b = nullptr; __nv_bfloat16* wout_b = nullptr;
+    if constexpr (Act<T>::kIsBf16) {
+        static const bool on = [] { const char* e = getenv("LEWIN_NO_ASYNC_GEMM"); return !(e && e[0] == '1'); }();
+        async_gemm = on && C > 128 && C % 64 == 0;
+        if (async_gemm) {
+            unsigned char* q = reinterpret_cast<unsigned char*>(cw) + align_up(kTok * kTok * 4, 256);
+            xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
+            wqkv_b = reinterpret_cast<__nv_bfloat16*>(q);
+            wout_b = wqkv_b + static_cast<size_t>(3) * C * C;
+            CK(launch_convert_w(a->w_qkv, wqkv_b, static_cast<long long>(3) * C * C, stream));
+            CK(launch_convert_w(a->w_out, wout_b, static_cast<long long>(C) * C, stream));
+        }
+    }
     {   // q | k | v projections (attn.py:420-422) with LN1 + roll + window_partition as the A prologue
         GemmArgs<T> g{};
         g.A = x; g.lda = C;
@@ -119,7 +137,19 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.mapA = a->windowed ? 0 : 1; g.mapY = 0; g.map = map;
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_ATTN_K_QKV);
-        CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
+        if constexpr (Act<T>::kIsBf16) {
+            if (async_gemm) {
+                if (!a->windowed) {      // LN1 + roll + partition in one pre-pass; the GEMM then streams plain bf16 rows
+                    CK(launch_ln_apply(static_cast<const __nv_bfloat16*>(a->x), xhat, a->ln_w, a->ln_b, tokens, C, 1, map, stream));
+                    g.A = xhat; g.mapA = 0; g.mean = nullptr; g.rstd = nullptr;
+                }
+                CK((launch_gemm_tca<EPI_BIAS>(g, wqkv_b, stream)));
+            } else {
+                CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
+            }
+        } else {
+            CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
+        }
         kt.end(LEWIN_ATTN_K_QKV);
     }
     {   // ProbSparse core (attn.py:287-342)
@@ -156,11 +186,21 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.mapA = 0; g.mapY = a->windowed ? 0 : 1; g.map = map;
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_ATTN_K_OUT);
-        if (a->windowed) {
-            CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
-        } else {
-            g.R = x; g.drop_scale = a->drop_scale;
-            CK((launch_gemm_any<T, EPI_BIAS_RESID>(g, stream)));
+        bool done = false;
+        if constexpr (Act<T>::kIsBf16) {
+            if (async_gemm) {
+                if (a->windowed) { CK((launch_gemm_tca<EPI_BIAS>(g, wout_b, stream))); }
+                else { g.R = x; g.drop_scale = a->drop_scale; CK((launch_gemm_tca<EPI_BIAS_RESID>(g, wout_b, stream))); }
+                done = true;
+            }
+        }
+        if (!done) {
+            if (a->windowed) {
+                CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
+            } else {
+                g.R = x; g.drop_scale = a->drop_scale;
+                CK((launch_gemm_any<T, EPI_BIAS_RESID>(g, stream)));
+            }
         }
         kt.end(LEWIN_ATTN_K_OUT);
     }
@@ -223,7 +263,9 @@ int check_leff(const LewinLeffFwdArgs* a) {
 
 size_t leff_fwd_ws(const LewinLeffFwdArgs* a) {
     const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
-    return 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(a->C), 256);
+    const size_t C = a->C, Ch = a->hidden;
+    return 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(a->C), 256) +
+           (C > 128 ? align_up(tokens * C * 2, 256) + align_up(2 * C * Ch * 2, 256) : 0);
 }
 
 bool leff_use_fused(const LewinLeffFwdArgs* a, bool is_bf16) {
@@ -265,7 +307,21 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
             return 0;
         }
     }
-    if (a->fused) {
+    bool async_gemm = false;
+    __nv_bfloat16* xhat = nullptr; __nv_bfloat16* w1b = nullptr; __nv_bfloat16* w2b = nullptr;
+    if constexpr (Act<T>::kIsBf16) {
+        static const bool on = [] { const char* e = getenv("LEWIN_NO_ASYNC_GEMM"); return !(e && e[0] == '1'); }();
+        async_gemm = on && C > 128 && C % 64 == 0 && Ch % 64 == 0;
+        if (async_gemm) {
+            unsigned char* q = wsp + 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(C), 256);
+            xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
+            w1b = reinterpret_cast<__nv_bfloat16*>(q);
+            w2b = w1b + static_cast<size_t>(C) * Ch;
+            CK(launch_convert_w(a->w1, w1b, static_cast<long long>(C) * Ch, stream));
+            CK(launch_convert_w(a->w2, w2b, static_cast<long long>(C) * Ch, stream));
+        }
+    }
+    if (a->fused && !async_gemm) {
         kt.begin(LEWIN_LEFF_K_LNSTATS);
         CK(launch_ln_stats<T>(y, tokens, C, mean, rstd, stream));
         kt.end(LEWIN_LEFF_K_LNSTATS);
@@ -279,7 +335,19 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         if (a->fused) { g.mean = mean; g.rstd = rstd; g.ln_w = a->ln_w; g.ln_b = a->ln_b; }
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_LEFF_K_FC1);
-        CK((launch_gemm_any<T, EPI_BIAS_GELU>(g, stream)));
+        bool done1 = false;
+        if constexpr (Act<T>::kIsBf16) {
+            if (async_gemm) {
+                if (a->fused) {
+                    WinMap nomap{a->H, a->W, a->W / 8, (a->H / 8) * (a->W / 8), 0};
+                    CK(launch_ln_apply(static_cast<const __nv_bfloat16*>(a->y), xhat, a->ln_w, a->ln_b, tokens, C, 0, nomap, stream));
+                    g.A = xhat; g.mean = nullptr; g.rstd = nullptr;
+                }
+                CK((launch_gemm_tca<EPI_BIAS_GELU>(g, w1b, stream)));
+                done1 = true;
+            }
+        }
+        if (!done1) CK((launch_gemm_any<T, EPI_BIAS_GELU>(g, stream)));
         kt.end(LEWIN_LEFF_K_FC1);
     }
     kt.begin(LEWIN_LEFF_K_DWCONV);
@@ -294,11 +362,21 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.M = tokens; g.N = C; g.K = Ch;
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_LEFF_K_FC2);
-        if (a->fused) {
-            g.R = y; g.drop_scale = a->drop_scale;
-            CK((launch_gemm_any<T, EPI_BIAS_RESID>(g, stream)));
-        } else {
-            CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
+        bool done2 = false;
+        if constexpr (Act<T>::kIsBf16) {
+            if (async_gemm) {
+                if (a->fused) { g.R = y; g.drop_scale = a->drop_scale; CK((launch_gemm_tca<EPI_BIAS_RESID>(g, w2b, stream))); }
+                else { CK((launch_gemm_tca<EPI_BIAS>(g, w2b, stream))); }
+                done2 = true;
+            }
+        }
+        if (!done2) {
+            if (a->fused) {
+                g.R = y; g.drop_scale = a->drop_scale;
+                CK((launch_gemm_any<T, EPI_BIAS_RESID>(g, stream)));
+            } else {
+                CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
+            }
         }
         kt.end(LEWIN_LEFF_K_FC2);
     }

@@ -192,6 +192,9 @@ typedef struct {
 /* 1 if lewin_leff_fwd_<dtype> will run the single fused kernel for these arguments (timing slot
  * LEWIN_LEFF_K_FUSED), 0 if it runs the four-kernel pipeline (slots 0-3). */
 int lewin_leff_fwd_is_fused(const LewinLeffFwdArgs* a, int dtype);
+/* Bit k set <=> the forward call will record timing slot k (LEWIN_ATTN_K_* / LEWIN_LEFF_K_*) for these arguments. */
+int lewin_attn_fwd_kernel_mask(const LewinAttnFwdArgs* a, int dtype);
+int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype);
 
 int lewin_leff_fwd_f32 (const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 int lewin_leff_fwd_bf16(const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);

@@ -77,6 +77,7 @@ EXPORTS = (
     "lewin_leff_fwd_workspace_bytes", "lewin_leff_bwd_workspace_bytes",
     "lewin_probsparse_core_fwd_f32", "lewin_probsparse_core_fwd_bf16", "lewin_probsparse_core_fwd_workspace_bytes",
     "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count", "lewin_leff_fwd_is_fused",
+    "lewin_attn_fwd_kernel_mask", "lewin_leff_fwd_kernel_mask",
 )
 
 ABI_VERSION = 1
@@ -108,6 +109,10 @@ def load():
     lib.lewin_abi_version.restype = C.c_int
     lib.lewin_leff_fwd_is_fused.argtypes = [C.POINTER(LewinLeffFwdArgs), C.c_int]
     lib.lewin_leff_fwd_is_fused.restype = C.c_int
+    lib.lewin_attn_fwd_kernel_mask.argtypes = [C.POINTER(LewinAttnFwdArgs), C.c_int]
+    lib.lewin_attn_fwd_kernel_mask.restype = C.c_int
+    lib.lewin_leff_fwd_kernel_mask.argtypes = [C.POINTER(LewinLeffFwdArgs), C.c_int]
+    lib.lewin_leff_fwd_kernel_mask.restype = C.c_int
     lib.lewin_launch_count.restype = C.c_longlong
     lib.lewin_build_info.restype = C.c_char_p
     lib.lewin_error_string.argtypes = [C.c_int]

@@ -718,9 +718,8 @@ __global__ void __launch_bounds__(256, (STAGES <= 2 ? 2 : 1)) gemm_tca_kernel(co
     if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
 }
 
-template <int BN, int EPI>
-cudaError_t launch_gemm_tca_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, cudaStream_t stream) {
-    constexpr int STAGES = 2;
+template <int BN, int STAGES, int EPI>
+cudaError_t launch_gemm_tca_st(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, cudaStream_t stream) {
     constexpr size_t smem = tca_smem_bytes<BN, STAGES, EPI>();
     auto k = gemm_tca_kernel<BN, STAGES, EPI>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -728,6 +727,14 @@ cudaError_t launch_gemm_tca_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bflo
     dim3 grid(static_cast<unsigned>((g.M + TC_BM - 1) / TC_BM), g.N / BN);
     k<<<grid, 256, smem, stream>>>(g, Wb);
     return cudaGetLastError();
+}
+
+template <int BN, int EPI>
+cudaError_t launch_gemm_tca_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, cudaStream_t stream) {
+    static const int deep = [] { const char* e = getenv("LEWIN_TCA_STAGES"); return e ? atoi(e) : 2; }();
+    if (deep >= 4 && g.K >= 256) return launch_gemm_tca_st<BN, 4, EPI>(g, Wb, stream);
+    if (deep == 3 && g.K >= 192) return launch_gemm_tca_st<BN, 3, EPI>(g, Wb, stream);
+    return launch_gemm_tca_st<BN, 2, EPI>(g, Wb, stream);
 }
 
 // plain-bf16-operand GEMM (K % 64 == 0, no LayerNorm prologue): Wb = bf16 copy of g.Wt

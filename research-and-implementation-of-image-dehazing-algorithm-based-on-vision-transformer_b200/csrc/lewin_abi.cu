@@ -32,7 +32,12 @@ inline int device_info(DeviceInfo* d) {
     return d->cc_major == 10 ? 0 : LEWIN_E_ARCH;
 }
 
-std::atomic<long long> g_launches{0};   // diagnostic only (lewin_launch_count)
+std::atomic<long long> g_launches{0};
+
+inline int async_min_c() {   // channels above which the bf16 GEMMs take the async (cp.async ring) kernel
+    static const int v = [] { const char* e = getenv("LEWIN_ASYNC_MIN_C"); return e ? atoi(e) : 128; }();
+    return v;
+}   // diagnostic only (lewin_launch_count)
 
 // Optional per-kernel timing with caller-owned events (LewinAttnFwdArgs::timing).
 struct KTimer {
@@ -76,7 +81,7 @@ size_t attn_fwd_ws(const LewinAttnFwdArgs* a) {
     // + bf16 staging for the async tcgen05 GEMMs (C > 128): LN-applied window-ordered x, bf16 copies of W_qkv / W_out
     const size_t C = a->C;
     return 2 * align_up(tokens * sizeof(float), 256) + align_up(kTok * kTok, 256) + align_up(kTok * kTok * 4, 256) +
-           (C > 128 ? align_up(tokens * C * 2, 256) + align_up(4 * C * C * 2, 256) : 0);
+           (C >= 64 ? align_up(tokens * C * 2, 256) + align_up(4 * C * C * 2, 256) : 0);
 }
 
 template <typename T>
@@ -101,7 +106,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     const T* x = static_cast<const T*>(a->x);
 
     const KTimer kt{a->timing, stream};
-    const bool skip_stats = Act<T>::kIsBf16 && C > 128 && C % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
+    const bool skip_stats = Act<T>::kIsBf16 && C > async_min_c() && C % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
     if (!a->windowed && !skip_stats) {
         kt.begin(LEWIN_ATTN_K_LNSTATS);
         CK(launch_ln_stats<T>(x, tokens, C, mean, rstd, stream));
@@ -117,7 +122,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     __nv_bfloat16* xhat = nullptr; __nv_bfloat16* wqkv_b = nullptr; __nv_bfloat16* wout_b = nullptr;
     if constexpr (Act<T>::kIsBf16) {
         static const bool on = [] { const char* e = getenv("LEWIN_NO_ASYNC_GEMM"); return !(e && e[0] == '1'); }();
-        async_gemm = on && C > 128 && C % 64 == 0;
+        async_gemm = on && C > async_min_c() && C % 64 == 0;
         if (async_gemm) {
             unsigned char* q = reinterpret_cast<unsigned char*>(cw) + align_up(kTok * kTok * 4, 256);
             xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
@@ -265,7 +270,7 @@ size_t leff_fwd_ws(const LewinLeffFwdArgs* a) {
     const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
     const size_t C = a->C, Ch = a->hidden;
     return 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(a->C), 256) +
-           (C > 128 ? align_up(tokens * C * 2, 256) + align_up(2 * C * Ch * 2, 256) : 0);
+           (C >= 64 ? align_up(tokens * C * 2, 256) + align_up(2 * C * Ch * 2, 256) : 0);
 }
 
 bool leff_use_fused(const LewinLeffFwdArgs* a, bool is_bf16) {
@@ -311,7 +316,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     __nv_bfloat16* xhat = nullptr; __nv_bfloat16* w1b = nullptr; __nv_bfloat16* w2b = nullptr;
     if constexpr (Act<T>::kIsBf16) {
         static const bool on = [] { const char* e = getenv("LEWIN_NO_ASYNC_GEMM"); return !(e && e[0] == '1'); }();
-        async_gemm = on && C > 128 && C % 64 == 0 && Ch % 64 == 0;
+        async_gemm = on && C > async_min_c() && C % 64 == 0 && Ch % 64 == 0;
         if (async_gemm) {
             unsigned char* q = wsp + 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(C), 256);
             xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
@@ -402,6 +407,19 @@ int lewin_probsparse_core_fwd_bf16(const LewinCoreFwdArgs* a, void* ws, size_t n
 size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs*, int) { return kTok * kTok * 5; }
 int lewin_leff_fwd_is_fused(const LewinLeffFwdArgs* a, int dtype) {
     return (a && check_leff(a) == 0 && leff_use_fused(a, dtype == LEWIN_DTYPE_BF16)) ? 1 : 0;
+}
+int lewin_attn_fwd_kernel_mask(const LewinAttnFwdArgs* a, int dtype) {
+    if (!a) return 0;
+    const bool bf = dtype == LEWIN_DTYPE_BF16;
+    const bool skip_stats = bf && a->C > async_min_c() && a->C % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
+    return ((!a->windowed && !skip_stats) ? 1 : 0) | 0x1E;
+}
+int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype) {
+    if (!a) return 0;
+    const bool bf = dtype == LEWIN_DTYPE_BF16;
+    if (check_leff(a) == 0 && leff_use_fused(a, bf)) return 1 << LEWIN_LEFF_K_FUSED;
+    const bool async_gemm = bf && a->C > async_min_c() && a->C % 64 == 0 && a->hidden % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
+    return ((a->fused && !async_gemm) ? 1 : 0) | 0xE;
 }
 int lewin_leff_fwd_f32(const LewinLeffFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
     return leff_fwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));

@@ -126,8 +126,9 @@ class _AttnFn(torch.autograd.Function):
             index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
             qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
         if KernelTimer.active is not None:
+            mask = lib.lewin_attn_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
             tim = KernelTimer.active.events_for("attn", dict(tokens=tokens, C=C, nH=nH, dtype=dt),
-                                                (1, 2, 3, 4) if windowed else (0, 1, 2, 3, 4))
+                                                tuple(k for k in range(5) if mask >> k & 1))
             a.timing = ctypes_addr(tim)
         ws = _workspace(lib.lewin_attn_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_attn_fwd_{dt}")
@@ -204,8 +205,9 @@ class _LeffFn(torch.autograd.Function):
             w_dw=_ptr(wdw_), b_dw=_ptr(bdw_), w2=_ptr(w2_), b2=_ptr(b2_), drop_scale=_ptr(ds_),
             h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
         if KernelTimer.active is not None:
+            mask = lib.lewin_leff_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
             tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt),
-                                                (4,) if single else ((1, 2, 3) if not fused else (0, 1, 2, 3)))
+                                                tuple(k for k in range(5) if mask >> k & 1))
             a.timing = ctypes_addr(tim)
         ws = _workspace(lib.lewin_leff_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_leff_fwd_{dt}")

@@ -10,6 +10,7 @@
 #pragma once
 #include "../../include/lewin_b200.h"
 #include "common.cuh"
+#include "dwconv.cuh"
 #include "gemm_fused.cuh"
 #include "gemm_tc.cuh"
 #include "probsparse_core.cuh"
@@ -912,7 +913,7 @@ inline size_t leff_bwd_ws(const LewinLeffBwdArgs* a, int dtype) {
     const size_t tokens = static_cast<size_t>(f.B) * f.H * f.W;
     const size_t es = dtype == LEWIN_DTYPE_BF16 ? 2 : 4;
     const size_t C = f.C, Ch = f.hidden;
-    return 2 * bw_align(tokens * 4) + 2 * bw_align(tokens * Ch * es) + bw_align(tokens * C * es) + 2 * bw_align(C * Ch * 4);
+    return 2 * bw_align(tokens * 4) + 3 * bw_align(tokens * Ch * es) + bw_align(tokens * C * es) + 2 * bw_align(C * Ch * 4);
 }
 
 template <typename T>
@@ -935,6 +936,7 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     float* rstd = reinterpret_cast<float*>(p); p += bw_align(tokens * 4);
     T* dh2 = reinterpret_cast<T*>(p); p += bw_align(tokens * Ch * sizeof(T));
     T* da1 = reinterpret_cast<T*>(p); p += bw_align(tokens * Ch * sizeof(T));
+    T* da2 = reinterpret_cast<T*>(p); p += bw_align(tokens * Ch * sizeof(T));
     T* dz = reinterpret_cast<T*>(p); p += bw_align(tokens * C * sizeof(T));
     float* w2T = reinterpret_cast<float*>(p); p += bw_align(static_cast<size_t>(C) * Ch * 4);
     float* w1T = reinterpret_cast<float*>(p);
@@ -962,8 +964,17 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
     }
     // depthwise conv backward: da1 = conv^T(dh2 * gelu'(a2)) * gelu'(a1); dWdw, dbdw
-    BCK(launch_dwconv_bwd<T>(dh2, static_cast<const T*>(f.a2), static_cast<const T*>(f.h1), static_cast<const T*>(f.a1),
-                             da1, f.w_dw, a->d_w_dw, a->d_b_dw, f.B, f.H, f.W, Ch, sms, st));
+    {
+        if (Act<T>::kIsBf16) BCK(launch_gelu_tab_init(st));
+        cudaError_t derr = cudaSuccess;
+        if (launch_dwconv_bwd_tiled<T>(dh2, static_cast<const T*>(f.a2), static_cast<const T*>(f.h1), static_cast<const T*>(f.a1),
+                                       da1, da2, f.w_dw, a->d_w_dw, a->d_b_dw, f.B, f.H, f.W, Ch, sms, st, &derr)) {
+            BCK(derr);
+        } else {
+            BCK(launch_dwconv_bwd<T>(dh2, static_cast<const T*>(f.a2), static_cast<const T*>(f.h1), static_cast<const T*>(f.a1),
+                                     da1, f.w_dw, a->d_w_dw, a->d_b_dw, f.B, f.H, f.W, Ch, sms, st));
+        }
+    }
     {   // dW1 += da1^T LN2(y) ; db1 += colsum(da1)
         WgradArgs<T> w{};
         w.dY = da1; w.lddy = Ch; w.X = y; w.ldx = C;

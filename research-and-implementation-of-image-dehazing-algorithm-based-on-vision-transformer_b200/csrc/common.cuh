@@ -139,6 +139,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // instruction bottleneck of LeFF on B200.
 constexpr int kGeluTabSize = 4096;
 __device__ uint16_t g_gelu_tab[kGeluTabSize];
+__device__ uint16_t g_gelu_grad_tab[kGeluTabSize];     // bf16(gelu'(x)) on the same index space (backward, bf16 path)
 
 __global__ void gelu_tab_init_kernel() {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,6 +147,7 @@ __global__ void gelu_tab_init_kernel() {
     const uint32_t sign = (i >> 11) & 1, e = 115 + ((i >> 7) & 15), m = i & 127;
     const float x = __uint_as_float((sign << 31) | (e << 23) | (m << 16));
     g_gelu_tab[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf(x)));
+    g_gelu_grad_tab[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf_grad(x)));
 }
 inline cudaError_t launch_gelu_tab_init(cudaStream_t st) {       // idempotent; a few microseconds
     gelu_tab_init_kernel<<<kGeluTabSize / 256, 256, 0, st>>>();
@@ -164,6 +166,14 @@ __device__ __forceinline__ uint32_t gelu_bits(const uint16_t* __restrict__ tab, 
         return ((u & 0x7F80u) > 0x0080u) ? (u - 0x80u) : (u & 0x8000u);
     return (u & 0x8000u) ? 0x8000u : u;                            // huge: x, or -0 for negative x
 }
+// gelu'(x) for x given as bf16 bits (table value is bf16-rounded; outside the table: 0.5, 1 or 0)
+__device__ __forceinline__ float gelu_grad_bits(const uint16_t* __restrict__ tab, uint32_t u) {
+    const uint32_t r = (u & 0x7FFFu) - 0x3980u;
+    if (__builtin_expect(r < 2048u, 1)) return __uint_as_float(static_cast<uint32_t>(tab[r + ((u >> 15) << 11)]) << 16);
+    if (static_cast<int32_t>(r) < 0) return 0.5f;
+    return (u & 0x8000u) ? 0.0f : 1.0f;
+}
+
 // GELU of a float that is rounded to bf16 first; returns the bf16-valued result as float
 __device__ __forceinline__ float gelu_tab(const uint16_t* __restrict__ tab, float x) {
     const uint32_t u = __bfloat16_as_ushort(__float2bfloat16_rn(x));

@@ -227,4 +227,255 @@ cudaError_t launch_dwconv_gelu_auto(const T* x, T* out, T* preact, const float* 
     return launch_dwconv_gelu<T>(x, out, preact, w, bias, B, H, W, Ch, stream);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of dwconv3x3 + GELU, shared-memory tiled, split in two kernels:
+//   dwconv_bwd_data_kernel : da2 = g2 * gelu'(a2) computed ONCE per element into the halo tile (and written to a
+//                            global scratch for the weight kernel), dh1 = conv^T(da2, w), da1 = dh1 * gelu'(a1)
+//   dwconv_bwd_wgrad_kernel: dW[c,t] += sum_p da2[p,c] * h1[p+t,c], db[c] += sum_p da2[p,c]; persistent per channel
+//                            slab, register accumulators, one shuffle + shared-memory reduction per CTA.
+template <typename T>
+__device__ __forceinline__ void dw_unpack(const unsigned char* src, float (&f)[16 / sizeof(T)]) {
+    if (sizeof(T) == 2) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src);
+        f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xFFFF0000u);
+        f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xFFFF0000u);
+        constexpr int E = 16 / sizeof(T);
+        f[E - 4] = __uint_as_float(u.z << 16); f[E - 3] = __uint_as_float(u.z & 0xFFFF0000u);
+        f[E - 2] = __uint_as_float(u.w << 16); f[E - 1] = __uint_as_float(u.w & 0xFFFF0000u);
+    } else {
+        const float4 u = *reinterpret_cast<const float4*>(src);
+        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void dw_pack_store(void* dst, const float (&f)[16 / sizeof(T)]) {
+    if (sizeof(T) == 2) {
+        constexpr int E = 16 / sizeof(T);
+        __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(f[E - 4], f[E - 3]), e = __floats2bfloat162_rn(f[E - 2], f[E - 1]);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                                                    *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&e));
+    } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+}
+// gelu'(x) for the EPC values of a 16-byte chunk of pre-activations
+template <typename T>
+__device__ __forceinline__ void dw_gelu_grad(const unsigned char* src, const uint16_t* gtab, float (&g)[16 / sizeof(T)]) {
+    constexpr int E = 16 / sizeof(T);
+    if (sizeof(T) == 2) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            g[(2 * j) % E] = gelu_grad_bits(gtab, w[j] & 0xFFFFu);
+            g[(2 * j + 1) % E] = gelu_grad_bits(gtab, w[j] >> 16);
+        }
+    } else {
+        const float4 u = *reinterpret_cast<const float4*>(src);
+        g[0] = gelu_erf_grad(u.x); g[1] = gelu_erf_grad(u.y); g[2] = gelu_erf_grad(u.z); g[3] = gelu_erf_grad(u.w);
+    }
+}
+
+template <typename T, int TX>
+__global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const T* __restrict__ g2, const T* __restrict__ a2,
+                                                              const T* __restrict__ a1, T* __restrict__ da1,
+                                                              T* __restrict__ da2_out, const float* __restrict__ w,
+                                                              int B, int H, int W, int Ch) {
+    constexpr int EPC = 16 / sizeof(T), SLAB = 8 * EPC, TY = 8, HX = TX + 2, HY = TY + 2, PPT = TY * TX / 32;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    unsigned char* gt = dyn_smem;                                      // g2 halo tile, then da2
+    unsigned char* at = gt + HY * HX * 8 * 16;                         // a2 halo tile
+    float* ws = reinterpret_cast<float*>(at + HY * HX * 8 * 16);       // [9][SLAB]
+    uint16_t* gtab = reinterpret_cast<uint16_t*>(ws + 9 * SLAB);       // gelu' table (bf16 path)
+    if (Act<T>::kIsBf16)
+        for (int i = threadIdx.x; i < kGeluTabSize / 8; i += 256)
+            reinterpret_cast<uint4*>(gtab)[i] = reinterpret_cast<const uint4*>(g_gelu_grad_tab)[i];
+    const int tid = threadIdx.x;
+    const int slabs = Ch / SLAB, tiles_x = W / TX, tiles_y = H / TY;
+    int t = blockIdx.x;
+    const int slab = t % slabs; t /= slabs;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int c0 = slab * SLAB, y0 = ty * TY - 1, x0 = tx * TX - 1;
+    for (int i = tid; i < HY * HX * 8; i += 256) {
+        const int ch = i & 7, p = i >> 3, hy = p / HX, hx = p - hy * HX;
+        const int yy = y0 + hy, xx = x0 + hx;
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const long long o = ((static_cast<long long>(b) * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * Ch + c0 + ch * EPC;
+        cp_async16_zfill(gt + i * 16, g2 + o, ok);
+        cp_async16_zfill(at + i * 16, a2 + o, ok);
+    }
+    cp_async_commit();
+    for (int i = tid; i < 9 * SLAB; i += 256) {
+        const int tap = i / SLAB, c = i - tap * SLAB;
+        ws[i] = Act<T>::round(w[static_cast<long long>(c0 + c) * 9 + tap]);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // da2 = g2 * gelu'(a2), once per halo element
+    for (int i = tid; i < HY * HX * 8; i += 256) {
+        float gv[EPC], gg[EPC];
+        dw_unpack<T>(gt + i * 16, gv);
+        dw_gelu_grad<T>(at + i * 16, gtab, gg);
+#pragma unroll
+        for (int j = 0; j < EPC; ++j) gv[j] *= gg[j];
+        dw_pack_store<T>(gt + i * 16, gv);
+        const int ch = i & 7, p = i >> 3, hy = p / HX, hx = p - hy * HX;
+        if (hy >= 1 && hy <= TY && hx >= 1 && hx <= TX) {
+            const long long o = ((static_cast<long long>(b) * H + (y0 + hy)) * W + (x0 + hx)) * Ch + c0 + ch * EPC;
+            *reinterpret_cast<uint4*>(da2_out + o) = *reinterpret_cast<const uint4*>(gt + i * 16);
+        }
+    }
+    __syncthreads();
+    const int ch = tid & 7, lane = tid >> 3;
+    const int px = lane % TX, py0 = (lane / TX) * PPT;
+    float acc[PPT][EPC];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p)
+#pragma unroll
+        for (int j = 0; j < EPC; ++j) acc[p][j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            float wv[EPC];
+#pragma unroll
+            for (int j = 0; j < EPC; j += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * SLAB + ch * EPC + j);
+                wv[j] = t4.x; wv[j + 1] = t4.y; wv[j + 2] = t4.z; wv[j + 3] = t4.w;
+            }
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {       // dh1[y,x] = sum da2[y - ky + 1, x - kx + 1] * w[ky,kx]
+                float f[EPC];
+                dw_unpack<T>(gt + (((py0 + p + 2 - ky) * HX + px + 2 - kx) * 8 + ch) * 16, f);
+#pragma unroll
+                for (int j = 0; j < EPC; ++j) acc[p][j] = fmaf(f[j], wv[j], acc[p][j]);
+            }
+        }
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        const int yy = ty * TY + py0 + p, xx = tx * TX + px;
+        const long long o = ((static_cast<long long>(b) * H + yy) * W + xx) * Ch + c0 + ch * EPC;
+        float gg[EPC];
+        dw_gelu_grad<T>(reinterpret_cast<const unsigned char*>(a1 + o), gtab, gg);
+#pragma unroll
+        for (int j = 0; j < EPC; ++j) acc[p][j] *= gg[j];
+        dw_pack_store<T>(da1 + o, acc[p]);
+    }
+}
+
+template <typename T, int TX>
+__global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __restrict__ da2, const T* __restrict__ h1,
+                                                                  float* __restrict__ dw, float* __restrict__ dbias,
+                                                                  int B, int H, int W, int Ch) {
+    constexpr int EPC = 16 / sizeof(T), SLAB = 8 * EPC, TY = 8, HX = TX + 2, HY = TY + 2, PPT = TY * TX / 32;
+    __shared__ __align__(16) unsigned char ht[HY * HX * 8 * 16];      // h1 halo tile
+    __shared__ __align__(16) unsigned char dt[TY * TX * 8 * 16];      // da2 interior tile
+    const int tid = threadIdx.x, ch = tid & 7, lane = tid >> 3;
+    const int px = lane % TX, py0 = (lane / TX) * PPT;
+    const int slab = blockIdx.y, c0 = slab * SLAB;
+    const int tiles_x = W / TX, tiles_y = H / TY;
+    const int ntiles = B * tiles_y * tiles_x;
+    float wacc[9][EPC], bacc[EPC];
+#pragma unroll
+    for (int j = 0; j < EPC; ++j) {
+        bacc[j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wacc[t][j] = 0.f;
+    }
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % tiles_x; t /= tiles_x;
+        const int ty = t % tiles_y;
+        const int b = t / tiles_y;
+        const int y0 = ty * TY - 1, x0 = tx * TX - 1;
+        __syncthreads();
+        for (int i = tid; i < HY * HX * 8; i += 256) {
+            const int c = i & 7, p = i >> 3, hy = p / HX, hx = p - hy * HX;
+            const int yy = y0 + hy, xx = x0 + hx;
+            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const long long o = ((static_cast<long long>(b) * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * Ch + c0 + c * EPC;
+            cp_async16_zfill(ht + i * 16, h1 + o, ok);
+        }
+        for (int i = tid; i < TY * TX * 8; i += 256) {
+            const int c = i & 7, p = i >> 3, iy = p / TX, ix = p - iy * TX;
+            const long long o = ((static_cast<long long>(b) * H + ty * TY + iy) * W + tx * TX + ix) * Ch + c0 + c * EPC;
+            cp_async16(dt + i * 16, da2 + o);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            float dv[EPC];
+            dw_unpack<T>(dt + (((py0 + p) * TX + px) * 8 + ch) * 16, dv);
+#pragma unroll
+            for (int j = 0; j < EPC; ++j) bacc[j] += dv[j];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {   // dw[ky,kx] += da2[y,x] * h1[y + ky - 1, x + kx - 1]
+                    float hv[EPC];
+                    dw_unpack<T>(ht + (((py0 + p + ky) * HX + px + kx) * 8 + ch) * 16, hv);
+#pragma unroll
+                    for (int j = 0; j < EPC; ++j) wacc[ky * 3 + kx][j] = fmaf(dv[j], hv[j], wacc[ky * 3 + kx][j]);
+                }
+        }
+    }
+    // lanes tid, tid^8, tid^16, tid^24 of a warp share the channel chunk: shuffle-reduce, then across the 8 warps
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(ht);           // [8 warps][8 chunks][10 * EPC]
+#pragma unroll
+    for (int t = 0; t < 10; ++t)
+#pragma unroll
+        for (int j = 0; j < EPC; ++j) {
+            float v = t < 9 ? wacc[t][j] : bacc[j];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if ((tid & 31) < 8) red[(((tid >> 5) * 8 + ch) * 10 + t) * EPC + j] = v;
+        }
+    __syncthreads();
+    for (int e = tid; e < 8 * 10 * EPC; e += 256) {
+        const int c = e / (10 * EPC), rem = e - c * 10 * EPC, t = rem / EPC, j = rem - t * EPC;
+        float sum = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) sum += red[((wv * 8 + c) * 10 + t) * EPC + j];
+        const int cc = c0 + c * EPC + j;
+        if (t < 9) atomicAdd(dw + static_cast<long long>(cc) * 9 + t, sum);
+        else atomicAdd(dbias + cc, sum);
+    }
+}
+
+// returns false if the shape is not covered (caller falls back to the register-window kernel)
+template <typename T>
+bool launch_dwconv_bwd_tiled(const T* g2, const T* a2, const T* h1, const T* a1, T* da1, T* da2_scratch, const float* w,
+                             float* dw, float* dbias, int B, int H, int W, int Ch, int num_sms, cudaStream_t st,
+                             cudaError_t* err) {
+    constexpr int SLAB = 8 * (16 / sizeof(T));
+    if (H % 8 || W % 8 || Ch % SLAB) return false;
+    const int slabs = Ch / SLAB;
+    if (W % 16 == 0) {
+        const unsigned grid = static_cast<unsigned>(B) * (H / 8) * (W / 16) * slabs;
+        constexpr int smem16 = 2 * 10 * 18 * 128 + 9 * SLAB * 4 + kGeluTabSize * 2;
+        cudaFuncSetAttribute(dwconv_bwd_data_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16);
+        dwconv_bwd_data_kernel<T, 16><<<grid, 256, smem16, st>>>(g2, a2, a1, da1, da2_scratch, w, B, H, W, Ch);
+        const int ntiles = B * (H / 8) * (W / 16);
+        int gx = (2 * num_sms + slabs - 1) / slabs; if (gx > ntiles) gx = ntiles;
+        dwconv_bwd_wgrad_kernel<T, 16><<<dim3(gx, slabs), 256, 0, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);
+    } else {
+        const unsigned grid = static_cast<unsigned>(B) * (H / 8) * (W / 8) * slabs;
+        constexpr int smem8 = 2 * 10 * 10 * 128 + 9 * SLAB * 4 + kGeluTabSize * 2;
+        cudaFuncSetAttribute(dwconv_bwd_data_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
+        dwconv_bwd_data_kernel<T, 8><<<grid, 256, smem8, st>>>(g2, a2, a1, da1, da2_scratch, w, B, H, W, Ch);
+        const int ntiles = B * (H / 8) * (W / 8);
+        int gx = (2 * num_sms + slabs - 1) / slabs; if (gx > ntiles) gx = ntiles;
+        dwconv_bwd_wgrad_kernel<T, 8><<<dim3(gx, slabs), 256, 0, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);
+    }
+    *err = cudaGetLastError();
+    return true;
+}
+
 }  // namespace lewin

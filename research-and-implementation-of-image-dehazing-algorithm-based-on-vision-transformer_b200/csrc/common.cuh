@@ -211,6 +211,21 @@ struct WinMap {
         if (x >= W) x -= W;
         return (static_cast<long long>(b) * H + y) * W + x;
     }
+    // 32-bit variant (token counts are far below 2^31): two 32-bit divisions instead of two 64-bit ones
+    __device__ __forceinline__ uint32_t token32(uint32_t m) const {
+        const uint32_t n = m & 63u, wg = m >> 6;
+        const uint32_t b = wg / static_cast<uint32_t>(nWin), w = wg - b * static_cast<uint32_t>(nWin);
+        const uint32_t wy = w / static_cast<uint32_t>(nWw), wx = w - wy * static_cast<uint32_t>(nWw);
+        return pixel(b, wy, wx, n);
+    }
+    // token of window (b, wy, wx), in-window index n
+    __device__ __forceinline__ uint32_t pixel(uint32_t b, uint32_t wy, uint32_t wx, uint32_t n) const {
+        int y = static_cast<int>(wy * 8 + (n >> 3)) + shift;
+        int x = static_cast<int>(wx * 8 + (n & 7u)) + shift;
+        if (y >= H) y -= H;
+        if (x >= W) x -= W;
+        return (b * static_cast<uint32_t>(H) + static_cast<uint32_t>(y)) * static_cast<uint32_t>(W) + static_cast<uint32_t>(x);
+    }
 };
 
 }  // namespace lewin

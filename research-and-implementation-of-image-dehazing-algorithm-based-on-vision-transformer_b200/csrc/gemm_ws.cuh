@@ -1,0 +1,420 @@
+// Warp-specialised persistent tcgen05 token GEMM for the HBM-bound LeWin levels (C <= 128, bf16):
+//
+//   Y = epi( LN?(A)[M,K] * W[N,K]^T + bias )
+//
+// Same contract as gemm_fused_kernel / gemm_tc_kernel (q|k|v projections attn.py:420-422, out projection :456,
+// LeFF linear1 My_model_1.py:508, linear2 :529, with LN / roll / window_partition / window_reverse / DropPath /
+// residual folded in), restructured so that the three things that bound it run concurrently inside ONE resident
+// CTA per SM instead of taking turns:
+//
+//   * 8 producer warps  : global -> registers (a register ring keeps >= 8 x 16 B per thread in flight across stage
+//                         boundaries) -> LayerNorm computed on the fly from the row itself (no ln_stats pre-pass,
+//                         no second read of x) -> bf16 -> swizzled UMMA tile in an S-stage shared-memory ring;
+//   * 1 MMA thread      : tcgen05.mma kind::f16 M=128 x N=BN, accumulating into one of TWO TMEM accumulator stages;
+//                         tcgen05.commit releases the smem stage to the producers and hands the accumulator over;
+//   * 8 epilogue warps  : tcgen05.ld (thread == row) -> bias / exact table GELU / DropPath * residual -> per-warp
+//                         staging tile -> row-cooperative, fully coalesced 16-byte global stores (window_reverse +
+//                         un-shift as the row address); residual rows are prefetched into the staging tile with
+//                         cp.async before the accumulator is awaited.
+//
+// The weight tile W[BN x K] (bf16-rounded, autocast semantics) stays resident in shared memory for the whole kernel;
+// every hand-over is an mbarrier, there is no __syncthreads in the steady state.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace lewin {
+namespace ws {
+
+constexpr int NEW = 8;                        // epilogue warps (warp % 4 == TMEM lane group, warp / 4 == column half)
+constexpr int NPW = 8;                        // producer warps
+constexpr int MMA_WARP = NEW;
+constexpr int THREADS = (NEW + 1 + NPW) * 32;
+constexpr int STG_ROW = 80;                   // staging row: 32 bf16 columns (64 B) + 16 B pad (conflict-free 16 B accesses)
+constexpr int STG_BUF = 32 * STG_ROW;
+constexpr int SMEM_MAX = 227 * 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xFFFF0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xFFFF0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xFFFF0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xFFFF0000u);
+}
+
+
+// fixed shared memory besides the weight tile and the A ring
+template <int BN, int EPI>
+constexpr size_t fixed_smem() {
+    return 1024 /*align*/ + NEW * 2 * STG_BUF + BN * 4 + (2 * 8 + 4) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGeluTabSize * 2 : 0);
+}
+
+// BN: tile columns; KC: k-chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); CPS: k-chunks per ring stage (LN needs the
+// whole row in one stage: CPS * KC == K); LN: LayerNorm prologue over the K channels of the A row.
+template <int BN, int KC, int CPS, int EPI, bool LN>
+__global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv_bfloat16> g, int row_tiles, int nkc, int S) {
+    using T = __nv_bfloat16;
+    constexpr int CPR = KC / 8;                        // 16-byte chunks per tile row per k-chunk
+    constexpr int A_CHUNK = TC_BM * KC * 2;
+    constexpr int W_CHUNK = BN * KC * 2;
+    constexpr int STAGE = CPS * A_CHUNK;
+    constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM columns per accumulator stage
+    constexpr int TMEM_COLS = 2 * ACC;
+    constexpr int NCH = BN / 32;                       // 32-column epilogue chunks
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
+    static_assert(BN % 32 == 0 && BN <= 256, "tile width");
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // align inside the shared window with pointer arithmetic only (an integer round-trip would turn every later
+    // access into a generic LD/ST instead of LDS/STS)
+    unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Ws = base;                                       // [nkc][W_CHUNK] resident
+    unsigned char* As = Ws + static_cast<size_t>(nkc) * W_CHUNK;    // [S][STAGE]
+    unsigned char* stg = As + static_cast<size_t>(S) * STAGE;       // [NEW][2][STG_BUF]
+    float* s_bias = reinterpret_cast<float*>(stg + NEW * 2 * STG_BUF);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + BN);      // [8]
+    uint64_t* empty = full + 8;                                     // [8]
+    uint64_t* tfull = empty + 8;                                    // [2]
+    uint64_t* tempty = tfull + 2;                                   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint16_t* gtab = reinterpret_cast<uint16_t*>(tmem_slot + 4);    // EPI_BIAS_GELU only
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.y * BN;
+    const int SPT = nkc / CPS;                                      // ring stages per row tile
+    const int my_tiles = (row_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+    // ---------------------------------------------------------------- one-time setup (all threads)
+    for (int c = tid; c < nkc * BN * CPR; c += THREADS) {
+        const int kc = c / (BN * CPR), rem = c - kc * (BN * CPR);
+        const int r = rem / CPR, ch = rem % CPR;
+        const float* src = g.Wt + static_cast<long long>(n0 + r) * g.K + kc * KC + ch * 8;
+        const float4 a4 = *reinterpret_cast<const float4*>(src);
+        const float4 b4 = *reinterpret_cast<const float4*>(src + 4);
+        *reinterpret_cast<uint4*>(Ws + static_cast<size_t>(kc) * W_CHUNK + tc::swz_off<KC>(r, ch)) =
+            make_uint4(tc::pack_bf16(a4.x, a4.y), tc::pack_bf16(a4.z, a4.w), tc::pack_bf16(b4.x, b4.y), tc::pack_bf16(b4.z, b4.w));
+    }
+    for (int i = tid; i < BN; i += THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[n0 + i]) : 0.f;
+    if (EPI == EPI_BIAS_GELU) gelu_tab_to_smem(gtab, tid, THREADS);
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], NPW * 32); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], NEW * 32); }
+        tc::fence_barrier_init();
+    }
+    if (warp == MMA_WARP) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc::fence_proxy_async();                         // resident W tile: generic-proxy writes -> async proxy (tensor core)
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp > MMA_WARP) {
+        // ============================================================ producers
+        constexpr int G = CPS * CPR;                   // lanes per row (one 16-byte chunk each)
+        constexpr int RPW = 32 / G;                    // rows per warp pass
+        constexpr int RPP = NPW * RPW;                 // rows per pass over all producer warps
+        constexpr int U = TC_BM / RPP;                 // rows (== 16-byte loads) per thread per stage
+        constexpr int UB = U > 4 ? 4 : U;              // rows per register batch
+        constexpr int NB = U / UB;                     // batches per stage
+        constexpr int D = (UB * 2 >= 8) ? (NB > 1 ? 3 : 2) : 8 / UB;   // ring depth in batches: >= 8 loads in flight per thread
+        const int pw = warp - (MMA_WARP + 1);
+        const int gl = lane % G, sub = lane / G;
+        const int kcl = gl / CPR, ch = gl % CPR;
+        float gam[8], bet[8];
+        if (LN) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { gam[j] = g.ln_w[gl * 8 + j]; bet[j] = g.ln_b[gl * 8 + j]; }
+        }
+        const int total = my_tiles * SPT * NB;         // register batches this CTA produces
+        uint4 buf[D][UB];
+        // running positions (no divisions in the steady state): loader and writer each walk batch -> stage -> tile
+        int l_b = 0, l_st = 0;
+        uint32_t l_tile = blockIdx.x;
+        uint32_t wb[2] = {0u, 0u}, wy[2] = {0u, 0u}, wx[2] = {0u, 0u};
+        auto load = [&](uint4 (&dst)[UB], int jb) {
+            if (jb >= total) return;
+            if (g.mapA && l_b == 0 && l_st == 0) {     // a 128-row tile is two consecutive windows: decode the first, step once
+                const uint32_t wg = l_tile * 2u;
+                wb[0] = wg / static_cast<uint32_t>(g.map.nWin);
+                const uint32_t w = wg - wb[0] * static_cast<uint32_t>(g.map.nWin);
+                wy[0] = w / static_cast<uint32_t>(g.map.nWw);
+                wx[0] = w - wy[0] * static_cast<uint32_t>(g.map.nWw);
+                wb[1] = wb[0]; wy[1] = wy[0]; wx[1] = wx[0] + 1u;
+                if (wx[1] == static_cast<uint32_t>(g.map.nWw)) {
+                    wx[1] = 0u; wy[1] += 1u;
+                    if (wy[1] * static_cast<uint32_t>(g.map.nWw) == static_cast<uint32_t>(g.map.nWin)) { wy[1] = 0u; wb[1] += 1u; }
+                }
+            }
+            const uint32_t m0 = l_tile * TC_BM;
+            const int kcol = (l_st * CPS + kcl) * KC + ch * 8;
+#pragma unroll
+            for (int p = 0; p < UB; ++p) {
+                const uint32_t r = (l_b * UB + p) * RPP + pw * RPW + sub;
+                const uint32_t m = m0 + r;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (m < g.M) {
+                    const uint32_t hi = r >> 6;
+                    const uint32_t ra = g.mapA ? g.map.pixel(hi ? wb[1] : wb[0], hi ? wy[1] : wy[0], hi ? wx[1] : wx[0], r & 63u) : m;
+                    v = *reinterpret_cast<const uint4*>(g.A + static_cast<long long>(ra) * g.lda + kcol);
+                }
+                dst[p] = v;
+            }
+            if (++l_b == NB) { l_b = 0; if (++l_st == SPT) { l_st = 0; l_tile += gridDim.x; } }
+        };
+        int p_b = 0, p_s = 0;
+        uint32_t p_ph = 0;
+        auto process = [&](const uint4 (&src)[UB]) {
+            if (p_b == 0) tc::mbar_wait(&empty[p_s], p_ph ^ 1u);     // the MMAs that read this stage last time have retired
+            unsigned char* dstA = As + static_cast<size_t>(p_s) * STAGE + kcl * A_CHUNK;
+#pragma unroll
+            for (int p = 0; p < UB; ++p) {
+                const int r = (p_b * UB + p) * RPP + pw * RPW + sub;
+                uint4 v = src[p];
+                if (LN) {
+                    float f[8];
+                    unpack8(v, f);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) sum += f[q];
+                    const float mu = group_sum<G>(sum) * (1.0f / (G * 8));
+                    float sq = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { f[q] -= mu; sq += f[q] * f[q]; }
+                    const float rs = rsqrtf(group_sum<G>(sq) * (1.0f / (G * 8)) + 1e-5f);
+                    v.x = tc::pack_bf16(f[0] * rs * gam[0] + bet[0], f[1] * rs * gam[1] + bet[1]);
+                    v.y = tc::pack_bf16(f[2] * rs * gam[2] + bet[2], f[3] * rs * gam[3] + bet[3]);
+                    v.z = tc::pack_bf16(f[4] * rs * gam[4] + bet[4], f[5] * rs * gam[5] + bet[5]);
+                    v.w = tc::pack_bf16(f[6] * rs * gam[6] + bet[6], f[7] * rs * gam[7] + bet[7]);
+                }
+                *reinterpret_cast<uint4*>(dstA + tc::swz_off<KC>(r, ch)) = v;
+            }
+            if (++p_b == NB) {
+                tc::fence_proxy_async();               // my generic-proxy smem writes -> visible to the tensor core
+                mbar_arrive(&full[p_s]);
+                p_b = 0;
+                if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
+            }
+        };
+#pragma unroll
+        for (int d = 0; d < D - 1; ++d) load(buf[d], d);
+        for (int j0 = 0; j0 < total; j0 += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const int jb = j0 + d;
+                if (jb < total) {
+                    load(buf[(d + D - 1) % D], jb + D - 1);
+                    process(buf[d]);
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ============================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t As_u = tc::smem_u32(As), Ws_u = tc::smem_u32(Ws);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int acc = it & 1;
+                const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+                tc::mbar_wait(&tempty[acc], aph ^ 1u);             // epilogue drained this accumulator
+                tc::tc_fence_after();
+                const uint32_t d_addr = tmem_d + static_cast<uint32_t>(acc * ACC);
+                for (int st = 0; st < SPT; ++st) {
+                    tc::mbar_wait(&full[s], ph);
+                    tc::tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < CPS; ++c) {
+                        const uint64_t da = tc::make_desc<KC>(As_u + s * STAGE + c * A_CHUNK);
+                        const uint64_t db = tc::make_desc<KC>(Ws_u + (st * CPS + c) * W_CHUNK);
+#pragma unroll
+                        for (int k16 = 0; k16 < KC / 16; ++k16)
+                            tc::mma_bf16(d_addr, da + 2 * k16, db + 2 * k16, IDESC, (st > 0 || c > 0 || k16 > 0) ? 1u : 0u);
+                    }
+                    tc::mma_commit(&empty[s]);                     // stage free once these MMAs have read it
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                tc::mma_commit(&tfull[acc]);                       // accumulator complete
+            }
+        }
+    } else {
+        // ============================================================ epilogue: thread == TMEM lane == tile row
+        const int lg = warp & 3, half = warp >> 2;
+        unsigned char* my_stg = stg + warp * 2 * STG_BUF;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+            const uint32_t tile = blockIdx.x + static_cast<uint32_t>(it) * gridDim.x;
+            const uint32_t m = tile * TC_BM + lg * 32 + lane;
+            long long oy = -1;
+            float sc = 1.f;
+            if (m < g.M) {
+                const uint32_t ry = g.mapY ? g.map.token32(m) : m;
+                oy = static_cast<long long>(ry) * g.ldy;
+                if (EPI == EPI_BIAS_RESID && g.drop_scale) sc = g.drop_scale[ry / static_cast<uint32_t>(g.tokens_per_image)];
+            }
+            if (EPI == EPI_BIAS_RESID) {            // residual rows of my first two chunks -> staging (async, coalesced)
+                int q = 0;
+                for (int c = half; c < NCH && q < 2; c += 2, ++q) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+                        const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                        if (o >= 0) cp_async16(my_stg + q * STG_BUF + rl * STG_ROW + cc * 16, g.R + o + n0 + c * 32 + cc * 8);
+                    }
+                }
+                cp_async_commit();
+            }
+            tc::mbar_wait(&tfull[acc], aph);
+            tc::tc_fence_after();
+            if (EPI == EPI_BIAS_RESID) { cp_async_wait<0>(); __syncwarp(); }
+            const uint32_t t_addr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(acc * ACC);
+            int q = 0;
+            for (int c = half; c < NCH; c += 2, ++q) {
+                float v[32];
+                tc::tmem_ld32(t_addr + c * 32, v);
+                if (c + 2 >= NCH) {                 // last chunk of this warp is in registers: hand the accumulator back
+                    tc::tc_fence_before();
+                    mbar_arrive(&tempty[acc]);
+                }
+                unsigned char* sb = my_stg + (q & 1) * STG_BUF;
+                unsigned char* srow = sb + lane * STG_ROW;
+                const float* bs = s_bias + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += bs[j];
+                if (EPI == EPI_BIAS_RESID) {
+                    if (q >= 2) {                   // (not reached for BN <= 128) late residual chunk: synchronous, coalesced
+                        __syncwarp();
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+                            const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                            if (o >= 0)
+                                *reinterpret_cast<uint4*>(sb + rl * STG_ROW + cc * 16) =
+                                    *reinterpret_cast<const uint4*>(g.R + o + n0 + c * 32 + cc * 8);
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 rv = *reinterpret_cast<const uint4*>(srow + j * 2);
+                        float rf[8];
+                        unpack8(rv, rf);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[j + e] = rf[e] + sc * Act<T>::round(v[j + e]);
+                    }
+                }
+                if (EPI == EPI_BIAS_GELU && g.Y2) {          // training: pre-activation copy first
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8)
+                        *reinterpret_cast<uint4*>(srow + j * 2) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
+                                                                              tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
+                    __syncwarp();
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+                        const uint4 val = *reinterpret_cast<const uint4*>(sb + rl * STG_ROW + cc * 16);
+                        const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                        if (o >= 0) *reinterpret_cast<uint4*>(g.Y2 + o + n0 + c * 32 + cc * 8) = val;
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        pk[h] = tc::pack_bf16(v[j + 2 * h], v[j + 2 * h + 1]);
+                        if (EPI == EPI_BIAS_GELU) pk[h] = gelu_bits(gtab, pk[h] & 0xFFFFu) | (gelu_bits(gtab, pk[h] >> 16) << 16);
+                    }
+                    *reinterpret_cast<uint4*>(srow + j * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {             // 8 rows x 64 contiguous bytes per warp instruction
+                    const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+                    const uint4 val = *reinterpret_cast<const uint4*>(sb + rl * STG_ROW + cc * 16);
+                    const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                    if (o >= 0) *reinterpret_cast<uint4*>(g.Y + o + n0 + c * 32 + cc * 8) = val;
+                }
+                __syncwarp();                                // staging buffer reusable
+            }
+            if (half >= NCH) {                               // this warp owns no chunk (BN == 32): still hand back
+                tc::tc_fence_before();
+                mbar_arrive(&tempty[acc]);
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- teardown
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
+}
+
+template <int BN, int KC, int CPS, int EPI, bool LN>
+cudaError_t launch_inst(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaStream_t stream) {
+    constexpr int A_CHUNK = TC_BM * KC * 2, W_CHUNK = BN * KC * 2, STAGE = CPS * A_CHUNK;
+    const int nkc = g.K / KC;
+    const size_t fixed = fixed_smem<BN, EPI>() + static_cast<size_t>(nkc) * W_CHUNK;
+    if (fixed + 2 * STAGE > SMEM_MAX) return cudaErrorInvalidConfiguration;
+    int S = static_cast<int>((SMEM_MAX - fixed) / STAGE);
+    if (S > 8) S = 8;
+    const size_t smem = fixed + static_cast<size_t>(S) * STAGE;
+    auto k = gemm_ws_kernel<BN, KC, CPS, EPI, LN>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const int row_tiles = static_cast<int>((g.M + TC_BM - 1) / TC_BM);
+    const int col_tiles = g.N / BN;
+    int gx = num_sms / col_tiles;
+    if (gx < 1) gx = 1;
+    if (gx > row_tiles) gx = row_tiles;
+    k<<<dim3(gx, col_tiles), THREADS, smem, stream>>>(g, row_tiles, nkc, S);
+    return cudaGetLastError();
+}
+
+inline bool enabled() {
+    static const bool on = [] { const char* e = getenv("LEWIN_NO_WS_GEMM"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+// Shapes served (everything the C <= 128 levels of the fused block path need); anything else -> caller's fallback.
+//   LN + EPI_BIAS       (q|k|v)   : K = C in {32, 64, 128}, N = 3C
+//   LN + EPI_BIAS_GELU  (linear1) : K = C in {32, 64, 128}, N = 4C
+//   EPI_BIAS_RESID      (out, linear2): N = C in {32, 64, 128}, K in {C, 4C}
+template <int EPI>
+inline bool supported(const GemmArgs<__nv_bfloat16>& g, bool ln) {
+    if (!enabled() || g.a_row_scale || g.aux) return false;
+    if (g.M < 4 * TC_BM) return false;
+    if (ln) {
+        if (!(g.K == 32 || g.K == 64 || g.K == 128)) return false;
+        if (EPI == EPI_BIAS) return g.N == 3 * g.K && !g.Y2;
+        if (EPI == EPI_BIAS_GELU) return g.N == 4 * g.K;
+        return false;
+    }
+    if (EPI != EPI_BIAS_RESID || !g.R) return false;
+    if (!(g.N == 32 || g.N == 64 || g.N == 128)) return false;
+    return g.K == g.N || g.K == 4 * g.N;
+}
+
+template <int EPI>
+cudaError_t launch(const GemmArgs<__nv_bfloat16>& g, bool ln, int num_sms, cudaStream_t stream) {
+    if constexpr (EPI == EPI_BIAS) {
+        if (g.K == 32) return launch_inst<96, 32, 1, EPI_BIAS, true>(g, num_sms, stream);
+        if (g.K == 64) return launch_inst<192, 64, 1, EPI_BIAS, true>(g, num_sms, stream);
+        return launch_inst<192, 64, 2, EPI_BIAS, true>(g, num_sms, stream);
+    } else if constexpr (EPI == EPI_BIAS_GELU) {
+        if (g.K == 32) return launch_inst<128, 32, 1, EPI_BIAS_GELU, true>(g, num_sms, stream);
+        if (g.K == 64) return launch_inst<256, 64, 1, EPI_BIAS_GELU, true>(g, num_sms, stream);
+        return launch_inst<256, 64, 2, EPI_BIAS_GELU, true>(g, num_sms, stream);
+    } else {
+        if (g.N == 32 && g.K == 32) return launch_inst<32, 32, 1, EPI_BIAS_RESID, false>(g, num_sms, stream);
+        if (g.N == 32) return launch_inst<32, 64, 1, EPI_BIAS_RESID, false>(g, num_sms, stream);
+        if (g.N == 64) return launch_inst<64, 64, 1, EPI_BIAS_RESID, false>(g, num_sms, stream);
+        return launch_inst<128, 64, 1, EPI_BIAS_RESID, false>(g, num_sms, stream);
+    }
+}
+
+}  // namespace ws
+}  // namespace lewin

@@ -5,6 +5,7 @@
 #include "dwconv.cuh"
 #include "gemm_fused.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_ws.cuh"
 #include "leff_fused.cuh"
 #include "probsparse_core.cuh"
 #include "probsparse_core_bf16.cuh"
@@ -38,6 +39,20 @@ inline int async_min_c() {   // channels above which the bf16 GEMMs take the asy
     static const int v = [] { const char* e = getenv("LEWIN_ASYNC_MIN_C"); return e ? atoi(e) : 128; }();
     return v;
 }   // diagnostic only (lewin_launch_count)
+
+// Which kernels a forward call will run (shared by the launch code and the kernel-mask queries).
+inline bool ws_level(int C, long long tokens) {     // warp-specialised persistent GEMM (gemm_ws.cuh) serves this level
+    return ws::enabled() && (C == 32 || C == 64 || C == 128) && tokens >= 4 * TC_BM;
+}
+struct AttnPlan { bool async_gemm, ws_gemm, ln_stats; };
+inline AttnPlan plan_attn(const LewinAttnFwdArgs* a, bool bf) {
+    AttnPlan p{};
+    const long long tokens = static_cast<long long>(a->B) * a->H * a->W;
+    p.ws_gemm = bf && !a->windowed && ws_level(a->C, tokens);
+    p.async_gemm = bf && !p.ws_gemm && a->C > async_min_c() && a->C % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
+    p.ln_stats = !a->windowed && !p.async_gemm && !p.ws_gemm;
+    return p;
+}
 
 // Optional per-kernel timing with caller-owned events (LewinAttnFwdArgs::timing).
 struct KTimer {
@@ -106,8 +121,8 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     const T* x = static_cast<const T*>(a->x);
 
     const KTimer kt{a->timing, stream};
-    const bool skip_stats = Act<T>::kIsBf16 && C > async_min_c() && C % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
-    if (!a->windowed && !skip_stats) {
+    const AttnPlan plan = plan_attn(a, Act<T>::kIsBf16);
+    if (plan.ln_stats) {
         kt.begin(LEWIN_ATTN_K_LNSTATS);
         CK(launch_ln_stats<T>(x, tokens, C, mean, rstd, stream));
         kt.end(LEWIN_ATTN_K_LNSTATS);
@@ -121,8 +136,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     bool async_gemm = false;
     __nv_bfloat16* xhat = nullptr; __nv_bfloat16* wqkv_b = nullptr; __nv_bfloat16* wout_b = nullptr;
     if constexpr (Act<T>::kIsBf16) {
-        static const bool on = [] { const char* e = getenv("LEWIN_NO_ASYNC_GEMM"); return !(e && e[0] == '1'); }();
-        async_gemm = on && C > async_min_c() && C % 64 == 0;
+        async_gemm = plan.async_gemm;
         if (async_gemm) {
             unsigned char* q = reinterpret_cast<unsigned char*>(cw) + align_up(kTok * kTok * 4, 256);
             xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
@@ -143,7 +157,10 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_ATTN_K_QKV);
         if constexpr (Act<T>::kIsBf16) {
-            if (async_gemm) {
+            if (plan.ws_gemm) {          // LN1 statistics computed inside the GEMM's producer warps
+                g.mean = nullptr; g.rstd = nullptr;
+                CK((ws::launch<EPI_BIAS>(g, true, di.sms, stream)));
+            } else if (async_gemm) {
                 if (!a->windowed) {      // LN1 + roll + partition in one pre-pass; the GEMM then streams plain bf16 rows
                     CK(launch_ln_apply(static_cast<const __nv_bfloat16*>(a->x), xhat, a->ln_w, a->ln_b, tokens, C, 1, map, stream));
                     g.A = xhat; g.mapA = 0; g.mean = nullptr; g.rstd = nullptr;
@@ -193,7 +210,11 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         kt.begin(LEWIN_ATTN_K_OUT);
         bool done = false;
         if constexpr (Act<T>::kIsBf16) {
-            if (async_gemm) {
+            if (plan.ws_gemm) {
+                g.R = x; g.drop_scale = a->drop_scale;
+                CK((ws::launch<EPI_BIAS_RESID>(g, false, di.sms, stream)));
+                done = true;
+            } else if (async_gemm) {
                 if (a->windowed) { CK((launch_gemm_tca<EPI_BIAS>(g, wout_b, stream))); }
                 else { g.R = x; g.drop_scale = a->drop_scale; CK((launch_gemm_tca<EPI_BIAS_RESID>(g, wout_b, stream))); }
                 done = true;
@@ -273,11 +294,25 @@ size_t leff_fwd_ws(const LewinLeffFwdArgs* a) {
            (C >= 64 ? align_up(tokens * C * 2, 256) + align_up(2 * C * Ch * 2, 256) : 0);
 }
 
-bool leff_use_fused(const LewinLeffFwdArgs* a, bool is_bf16) {
-    static const bool fused_on = [] { const char* e = getenv("LEWIN_NO_FUSED_LEFF"); return !(e && e[0] == '1'); }();
-    return is_bf16 && fused_on && a->fused && !a->save_for_backward && leff_fused_supported(a->C, a->hidden) &&
-           a->H % 8 == 0 && a->W % 8 == 0;
+// bf16 LeFF at C <= 128: LEWIN_LEFF=fused selects the single on-chip kernel (leff_fused.cuh); the default is the
+// three-kernel pipeline on the warp-specialised GEMM (h1 / h2 round-trip HBM once each, every kernel HBM-bound).
+struct LeffPlan { bool fused_kernel, ws_gemm, async_gemm, ln_stats; };
+inline LeffPlan plan_leff(const LewinLeffFwdArgs* a, bool bf) {
+    static const bool want_fused = [] { const char* e = getenv("LEWIN_LEFF"); return e && e[0] == 'f'; }();
+    static const bool fused_off = [] { const char* e = getenv("LEWIN_NO_FUSED_LEFF"); return e && e[0] == '1'; }();
+    LeffPlan p{};
+    const long long tokens = static_cast<long long>(a->B) * a->H * a->W;
+    const bool fused_ok = bf && !fused_off && a->fused && !a->save_for_backward && leff_fused_supported(a->C, a->hidden) &&
+                          a->H % 8 == 0 && a->W % 8 == 0;
+    const bool ws_ok = bf && a->fused && a->hidden == 4 * a->C && ws_level(a->C, tokens);
+    p.fused_kernel = fused_ok && (want_fused || !ws_ok);
+    p.ws_gemm = !p.fused_kernel && ws_ok;
+    p.async_gemm = bf && !p.fused_kernel && !p.ws_gemm && a->C > async_min_c() && a->C % 64 == 0 && a->hidden % 64 == 0 &&
+                   !getenv("LEWIN_NO_ASYNC_GEMM");
+    p.ln_stats = !p.fused_kernel && a->fused && !p.async_gemm && !p.ws_gemm;
+    return p;
 }
+bool leff_use_fused(const LewinLeffFwdArgs* a, bool is_bf16) { return plan_leff(a, is_bf16).fused_kernel; }
 
 template <typename T>
 int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -295,10 +330,11 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     const bool save = a->save_for_backward != 0;
 
     const KTimer kt{a->timing, stream};
+    const LeffPlan plan = plan_leff(a, Act<T>::kIsBf16);
     if constexpr (Act<T>::kIsBf16) CK(launch_gelu_tab_init(stream));     // idempotent 8 KB table (common.cuh)
     if constexpr (Act<T>::kIsBf16) {
-        // HBM-bound levels: one kernel, hidden activations stay on chip (leff_fused.cuh)
-        if (leff_use_fused(a, true)) {
+        // one kernel, hidden activations stay on chip (leff_fused.cuh)
+        if (plan.fused_kernel) {
             LeffFusedArgs fa{};
             fa.y = static_cast<const __nv_bfloat16*>(a->y);
             fa.out = static_cast<__nv_bfloat16*>(a->out);
@@ -315,8 +351,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     bool async_gemm = false;
     __nv_bfloat16* xhat = nullptr; __nv_bfloat16* w1b = nullptr; __nv_bfloat16* w2b = nullptr;
     if constexpr (Act<T>::kIsBf16) {
-        static const bool on = [] { const char* e = getenv("LEWIN_NO_ASYNC_GEMM"); return !(e && e[0] == '1'); }();
-        async_gemm = on && C > async_min_c() && C % 64 == 0 && Ch % 64 == 0;
+        async_gemm = plan.async_gemm;
         if (async_gemm) {
             unsigned char* q = wsp + 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(C), 256);
             xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
@@ -326,7 +361,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
             CK(launch_convert_w(a->w2, w2b, static_cast<long long>(C) * Ch, stream));
         }
     }
-    if (a->fused && !async_gemm) {
+    if (plan.ln_stats) {
         kt.begin(LEWIN_LEFF_K_LNSTATS);
         CK(launch_ln_stats<T>(y, tokens, C, mean, rstd, stream));
         kt.end(LEWIN_LEFF_K_LNSTATS);
@@ -342,7 +377,11 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         kt.begin(LEWIN_LEFF_K_FC1);
         bool done1 = false;
         if constexpr (Act<T>::kIsBf16) {
-            if (async_gemm) {
+            if (plan.ws_gemm) {          // LN2 statistics computed inside the GEMM's producer warps
+                g.mean = nullptr; g.rstd = nullptr;
+                CK((ws::launch<EPI_BIAS_GELU>(g, true, di.sms, stream)));
+                done1 = true;
+            } else if (async_gemm) {
                 if (a->fused) {
                     WinMap nomap{a->H, a->W, a->W / 8, (a->H / 8) * (a->W / 8), 0};
                     CK(launch_ln_apply(static_cast<const __nv_bfloat16*>(a->y), xhat, a->ln_w, a->ln_b, tokens, C, 0, nomap, stream));
@@ -369,7 +408,11 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         kt.begin(LEWIN_LEFF_K_FC2);
         bool done2 = false;
         if constexpr (Act<T>::kIsBf16) {
-            if (async_gemm) {
+            if (plan.ws_gemm) {
+                g.R = y; g.drop_scale = a->drop_scale;
+                CK((ws::launch<EPI_BIAS_RESID>(g, false, di.sms, stream)));
+                done2 = true;
+            } else if (async_gemm) {
                 if (a->fused) { g.R = y; g.drop_scale = a->drop_scale; CK((launch_gemm_tca<EPI_BIAS_RESID>(g, w2b, stream))); }
                 else { CK((launch_gemm_tca<EPI_BIAS>(g, w2b, stream))); }
                 done2 = true;
@@ -410,16 +453,14 @@ int lewin_leff_fwd_is_fused(const LewinLeffFwdArgs* a, int dtype) {
 }
 int lewin_attn_fwd_kernel_mask(const LewinAttnFwdArgs* a, int dtype) {
     if (!a) return 0;
-    const bool bf = dtype == LEWIN_DTYPE_BF16;
-    const bool skip_stats = bf && a->C > async_min_c() && a->C % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
-    return ((!a->windowed && !skip_stats) ? 1 : 0) | 0x1E;
+    return (plan_attn(a, dtype == LEWIN_DTYPE_BF16).ln_stats ? 1 : 0) | 0x1E;
 }
 int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype) {
     if (!a) return 0;
-    const bool bf = dtype == LEWIN_DTYPE_BF16;
-    if (check_leff(a) == 0 && leff_use_fused(a, bf)) return 1 << LEWIN_LEFF_K_FUSED;
-    const bool async_gemm = bf && a->C > async_min_c() && a->C % 64 == 0 && a->hidden % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
-    return ((a->fused && !async_gemm) ? 1 : 0) | 0xE;
+    if (check_leff(a) != 0) return 0;
+    const LeffPlan p = plan_leff(a, dtype == LEWIN_DTYPE_BF16);
+    if (p.fused_kernel) return 1 << LEWIN_LEFF_K_FUSED;
+    return (p.ln_stats ? 1 : 0) | 0xE;
 }
 int lewin_leff_fwd_f32(const LewinLeffFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
     return leff_fwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));

@@ -141,8 +141,21 @@ constexpr int kGeluTabSize = 4096;
 __device__ uint16_t g_gelu_tab[kGeluTabSize];
 __device__ uint16_t g_gelu_grad_tab[kGeluTabSize];     // bf16(gelu'(x)) on the same index space (backward, bf16 path)
 
+// Wide table for the branch-free pair lookup below: 32 binades (2^-28 <= |x| < 16) x 128 mantissas x 2 signs =
+// 8192 entries (16 KB), index = (|x| bits - 0x3180) | sign << 12.  With 2^-28 as the lower edge an out-of-table
+// element is a once-per-billions event for activations, so the range check is deferred to one test per thread and
+// chunk (OR of the biased magnitudes) and the exact slow path (gelu_bits) is practically never taken.
+constexpr int kGelu2TabSize = 8192;
+constexpr uint32_t kGelu2Base = 99u << 7;              // bf16 bits of 2^-28
+__device__ uint16_t g_gelu_tab2[kGelu2TabSize];
+
 __global__ void gelu_tab_init_kernel() {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kGelu2TabSize) {
+        const uint32_t sign2 = (i >> 12) & 1, em = kGelu2Base + (i & 4095);
+        const float x2 = __uint_as_float((sign2 << 31) | (em << 16));
+        g_gelu_tab2[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf(x2)));
+    }
     if (i >= kGeluTabSize) return;
     const uint32_t sign = (i >> 11) & 1, e = 115 + ((i >> 7) & 15), m = i & 127;
     const float x = __uint_as_float((sign << 31) | (e << 23) | (m << 16));
@@ -150,7 +163,7 @@ __global__ void gelu_tab_init_kernel() {
     g_gelu_grad_tab[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf_grad(x)));
 }
 inline cudaError_t launch_gelu_tab_init(cudaStream_t st) {       // idempotent; a few microseconds
-    gelu_tab_init_kernel<<<kGeluTabSize / 256, 256, 0, st>>>();
+    gelu_tab_init_kernel<<<kGelu2TabSize / 256, 256, 0, st>>>();
     return cudaGetLastError();
 }
 __device__ __forceinline__ void gelu_tab_to_smem(uint16_t* dst, int tid, int nthreads) {
@@ -166,6 +179,38 @@ __device__ __forceinline__ uint32_t gelu_bits(const uint16_t* __restrict__ tab, 
         return ((u & 0x7F80u) > 0x0080u) ? (u - 0x80u) : (u & 0x8000u);
     return (u & 0x8000u) ? 0x8000u : u;                            // huge: x, or -0 for negative x
 }
+__device__ __forceinline__ void gelu_tab2_to_smem(uint16_t* dst, int tid, int nthreads) {
+    for (int i = tid; i < kGelu2TabSize / 8; i += nthreads)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(g_gelu_tab2)[i];
+}
+// Packed pair: bf16x2 bits in -> bf16x2 bits of GELU out, ~7 ALU instructions + one 16-bit shared load per element and
+// no branch.  `oor` accumulates the biased magnitudes: (oor >> 12) != 0 afterwards means some element handled by this
+// thread was outside the table and the caller must redo its elements with gelu_pair_exact.
+__device__ __forceinline__ uint32_t gelu_pair_fast(const uint16_t* __restrict__ tab2, uint32_t in2, uint32_t& oor) {
+    const uint32_t sh3 = in2 >> 3;
+    const uint32_t r0 = (in2 & 0x7FFFu) - kGelu2Base;
+    const uint32_t r1 = ((in2 >> 16) & 0x7FFFu) - kGelu2Base;
+    oor |= r0 | r1;
+    const uint32_t i0 = min(r0, 4095u) | (sh3 & 0x1000u);
+    const uint32_t i1 = min(r1, 4095u) | ((sh3 >> 16) & 0x1000u);
+    return static_cast<uint32_t>(tab2[i0]) | (static_cast<uint32_t>(tab2[i1]) << 16);
+}
+// exact for every bf16 input (table inside 2^-28 <= |x| < 16, closed forms outside: 0.5 x, x or -0)
+__device__ __noinline__ uint32_t gelu_pair_exact(const uint16_t* __restrict__ tab2, uint32_t in2) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t u = (in2 >> (16 * h)) & 0xFFFFu;
+        const uint32_t r = (u & 0x7FFFu) - kGelu2Base;
+        uint32_t v;
+        if (r < 4096u) v = tab2[r | ((u >> 3) & 0x1000u)];
+        else if (static_cast<int32_t>(r) < 0) v = ((u & 0x7F80u) > 0x0080u) ? (u - 0x80u) : (u & 0x8000u);
+        else v = (u & 0x8000u) ? 0x8000u : u;
+        out |= v << (16 * h);
+    }
+    return out;
+}
+
 // gelu'(x) for x given as bf16 bits (table value is bf16-rounded; outside the table: 0.5, 1 or 0)
 __device__ __forceinline__ float gelu_grad_bits(const uint16_t* __restrict__ tab, uint32_t u) {
     const uint32_t r = (u & 0x7FFFu) - 0x3980u;

@@ -1,0 +1,169 @@
+// Persistent, double-buffered depthwise 3x3 + bias + exact GELU for bf16 channel-last maps (My_model_1.py:489-491, :517).
+//
+// The element-wise work, not HBM, bounded the earlier kernels (dwconv.cuh): ~0.66 SM-cycles per hidden element.  This
+// variant is built around the instruction count per element:
+//   * persistent CTAs (2 per SM) walk 16x16-pixel x 64-channel tiles, slab-major so the 36 weights + 4 biases a thread
+//     needs stay in registers until the channel slab changes; the 16 KB GELU table is staged once per CTA;
+//   * the (16+2)x(16+2) halo tile of the NEXT tile is fetched with 16-byte cp.async (zero-filled outside the map ==
+//     the conv's zero padding) while the current one is computed (two shared-memory buffers);
+//   * thread = (4-channel group, pixel column): it walks the 16 rows with a rolling 3x3 register window, so every input
+//     value is loaded from shared memory and unpacked once per thread-row (3 LDS.64 + 12 unpacks per 4 outputs) and the
+//     36 MACs are 18 packed FFMA2;
+//   * GELU is the branch-free pair lookup (common.cuh) with one deferred range test per 4 outputs;
+//   * a warp stores 2 pixels x 128 contiguous bytes per instruction.
+// Algorithmic HBM traffic: read Ch + write Ch per pixel (the halo re-reads hit L2).
+#pragma once
+#include "common.cuh"
+
+namespace lewin {
+namespace dws {
+
+constexpr int TY = 16, TX = 16, SLAB = 64;
+constexpr int HY = TY + 2, HX = TX + 2;
+constexpr int TILE_BYTES = HY * HX * SLAB * 2;            // 41472
+constexpr int THREADS = 256;
+constexpr size_t SMEM = 2 * TILE_BYTES + kGelu2TabSize * 2;
+
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+__device__ __forceinline__ void cp16z(uint32_t smem_addr, const void* gmem, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gmem), "r"(sz));
+}
+
+struct Args {
+    const __nv_bfloat16* x;      // [B, H, W, Ch]
+    __nv_bfloat16* out;          // [B, H, W, Ch]
+    __nv_bfloat16* preact;       // optional pre-GELU copy (training), may be null
+    const float* w;              // [Ch, 9]
+    const float* bias;           // [Ch]
+    int B, H, W, Ch;
+    int tiles_x, tiles_y, spatial_tiles, total_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t* gtab = reinterpret_cast<uint16_t*>(smem + 2 * TILE_BYTES);
+    const uint32_t smem_u = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const int tid = threadIdx.x;
+    const int cq = tid & 15, px = tid >> 4;                // 4-channel group, pixel column
+
+    auto decode = [&](int t, int& slab, int& b, int& ty, int& tx) {
+        slab = t / a.spatial_tiles;
+        int r = t - slab * a.spatial_tiles;
+        tx = r % a.tiles_x; r /= a.tiles_x;
+        ty = r % a.tiles_y;
+        b = r / a.tiles_y;
+    };
+    auto fetch = [&](int t, int bufi) {
+        int slab, b, ty, tx;
+        decode(t, slab, b, ty, tx);
+        const int y0 = ty * TY - 1, x0 = tx * TX - 1;
+        const __nv_bfloat16* src0 = a.x + static_cast<long long>(b) * a.H * a.W * a.Ch + slab * SLAB;
+        const uint32_t dst0 = smem_u + bufi * TILE_BYTES;
+        for (int i = tid; i < HY * HX * 8; i += THREADS) {
+            const int ch = i & 7, p = i >> 3;
+            const int hy = p / HX, hx = p - hy * HX;
+            const int yy = y0 + hy, xx = x0 + hx;
+            const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+            cp16z(dst0 + i * 16, src0 + (static_cast<long long>(ok ? yy : 0) * a.W + (ok ? xx : 0)) * a.Ch + ch * 8, ok);
+        }
+    };
+
+    int t = blockIdx.x;
+    if (t < a.total_tiles) fetch(t, 0);
+    cp_async_commit();
+    gelu_tab2_to_smem(gtab, tid, THREADS);
+
+    float2 wk[9][2];                                       // taps x channel pairs (autocast: bf16-rounded weights)
+    float2 bz[2];
+    int cur_slab = -1;
+    int bufi = 0;
+    for (; t < a.total_tiles; t += gridDim.x, bufi ^= 1) {
+        const int tn = t + gridDim.x;
+        if (tn < a.total_tiles) fetch(tn, bufi ^ 1);
+        cp_async_commit();
+        int slab, b, ty, tx;
+        decode(t, slab, b, ty, tx);
+        if (slab != cur_slab) {
+            cur_slab = slab;
+            const int c = slab * SLAB + cq * 4;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                wk[k][0] = make_float2(Act<__nv_bfloat16>::round(__ldg(a.w + (c + 0) * 9 + k)), Act<__nv_bfloat16>::round(__ldg(a.w + (c + 1) * 9 + k)));
+                wk[k][1] = make_float2(Act<__nv_bfloat16>::round(__ldg(a.w + (c + 2) * 9 + k)), Act<__nv_bfloat16>::round(__ldg(a.w + (c + 3) * 9 + k)));
+            }
+            const float4 b4 = *reinterpret_cast<const float4*>(a.bias + c);
+            bz[0] = make_float2(Act<__nv_bfloat16>::round(b4.x), Act<__nv_bfloat16>::round(b4.y));
+            bz[1] = make_float2(Act<__nv_bfloat16>::round(b4.z), Act<__nv_bfloat16>::round(b4.w));
+        }
+        cp_async_wait<1>();                                // this tile's halo has landed (the next one may still fly)
+        __syncthreads();
+
+        const unsigned char* tile = smem + bufi * TILE_BYTES + cq * 8;
+        auto ldrow = [&](float2 (&dst)[3][2], int hy) {    // 3 columns x 4 channels of halo row hy
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const uint2 u = *reinterpret_cast<const uint2*>(tile + ((hy * HX + px + j) * SLAB) * 2);
+                dst[j][0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u));
+                dst[j][1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+            }
+        };
+        float2 win[3][3][2];                               // [row][col][channel pair]
+        ldrow(win[0], 0);
+        ldrow(win[1], 1);
+        const long long obase = ((static_cast<long long>(b) * a.H + ty * TY) * a.W + tx * TX + px) * a.Ch + slab * SLAB + cq * 4;
+        const long long rstride = static_cast<long long>(a.W) * a.Ch;
+        __nv_bfloat16* op = a.out + obase;
+        __nv_bfloat16* pp = a.preact ? a.preact + obase : nullptr;
+#pragma unroll
+        for (int y = 0; y < TY; ++y) {
+            ldrow(win[(y + 2) % 3], y + 2);
+            float2 acc0 = bz[0], acc1 = bz[1];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    ffma2(acc0, win[(y + ky) % 3][kx][0], wk[ky * 3 + kx][0]);
+                    ffma2(acc1, win[(y + ky) % 3][kx][1], wk[ky * 3 + kx][1]);
+                }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc0.x, acc0.y), h1 = __floats2bfloat162_rn(acc1.x, acc1.y);
+            const uint32_t in0 = *reinterpret_cast<uint32_t*>(&h0), in1 = *reinterpret_cast<uint32_t*>(&h1);
+            uint32_t oor = 0;
+            uint32_t q0 = gelu_pair_fast(gtab, in0, oor), q1 = gelu_pair_fast(gtab, in1, oor);
+            if (__builtin_expect((oor >> 12) != 0u, 0)) { q0 = gelu_pair_exact(gtab, in0); q1 = gelu_pair_exact(gtab, in1); }
+            if (pp) { *reinterpret_cast<uint2*>(pp) = make_uint2(in0, in1); pp += rstride; }
+            *reinterpret_cast<uint2*>(op) = make_uint2(q0, q1);
+            op += rstride;
+        }
+        __syncthreads();                                   // every thread is done with this buffer before it is refilled
+    }
+}
+
+inline bool supported(int H, int W, int Ch) {
+    static const bool on = [] { const char* e = getenv("LEWIN_NO_STREAM_DWCONV"); return !(e && e[0] == '1'); }();
+    return on && H % TY == 0 && W % TX == 0 && Ch % SLAB == 0;
+}
+
+inline cudaError_t launch(const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloat16* preact, const float* w, const float* bias,
+                          int B, int H, int W, int Ch, int num_sms, cudaStream_t stream) {
+    Args a{};
+    a.x = x; a.out = out; a.preact = preact; a.w = w; a.bias = bias;
+    a.B = B; a.H = H; a.W = W; a.Ch = Ch;
+    a.tiles_x = W / TX; a.tiles_y = H / TY;
+    a.spatial_tiles = B * a.tiles_x * a.tiles_y;
+    a.total_tiles = a.spatial_tiles * (Ch / SLAB);
+    cudaError_t e = cudaFuncSetAttribute(dwconv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM));
+    if (e != cudaSuccess) return e;
+    int grid = 2 * num_sms;
+    if (grid > a.total_tiles) grid = a.total_tiles;
+    dwconv_stream_kernel<<<grid, THREADS, SMEM, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace dws
+}  // namespace lewin

@@ -47,7 +47,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // fixed shared memory besides the weight tile and the A ring
 template <int BN, int EPI>
 constexpr size_t fixed_smem() {
-    return 1024 /*align*/ + NEW * 2 * STG_BUF + BN * 4 + (2 * 8 + 4) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGeluTabSize * 2 : 0);
+    return 1024 /*align*/ + NEW * 2 * STG_BUF + BN * 4 + (2 * 8 + 4) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGelu2TabSize * 2 : 0);
 }
 
 // BN: tile columns; KC: k-chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); CPS: k-chunks per ring stage (LN needs the
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
             make_uint4(tc::pack_bf16(a4.x, a4.y), tc::pack_bf16(a4.z, a4.w), tc::pack_bf16(b4.x, b4.y), tc::pack_bf16(b4.z, b4.w));
     }
     for (int i = tid; i < BN; i += THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[n0 + i]) : 0.f;
-    if (EPI == EPI_BIAS_GELU) gelu_tab_to_smem(gtab, tid, THREADS);
+    if (EPI == EPI_BIAS_GELU) gelu_tab2_to_smem(gtab, tid, THREADS);
     if (tid == 0) {
         for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], NPW * 32); tc::mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], NEW * 32); }
@@ -320,15 +320,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
                     }
                     __syncwarp();
                 }
+                {
+                    uint32_t pk[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    uint32_t pk[4];
+                    for (int h = 0; h < 16; ++h) pk[h] = tc::pack_bf16(v[2 * h], v[2 * h + 1]);
+                    if (EPI == EPI_BIAS_GELU) {        // branch-free table GELU, one deferred range test per thread and chunk
+                        uint32_t oor = 0, ge[16];
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        pk[h] = tc::pack_bf16(v[j + 2 * h], v[j + 2 * h + 1]);
-                        if (EPI == EPI_BIAS_GELU) pk[h] = gelu_bits(gtab, pk[h] & 0xFFFFu) | (gelu_bits(gtab, pk[h] >> 16) << 16);
+                        for (int h = 0; h < 16; ++h) ge[h] = gelu_pair_fast(gtab, pk[h], oor);
+                        if (__builtin_expect((oor >> 12) != 0u, 0)) {
+#pragma unroll
+                            for (int h = 0; h < 16; ++h) ge[h] = gelu_pair_exact(gtab, pk[h]);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 16; ++h) pk[h] = ge[h];
                     }
-                    *reinterpret_cast<uint4*>(srow + j * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(srow + j * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 }
                 __syncwarp();
 #pragma unroll

@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "dwconv.cuh"
+#include "dwconv_stream.cuh"
 #include "gemm_fused.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
@@ -395,8 +396,17 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         kt.end(LEWIN_LEFF_K_FC1);
     }
     kt.begin(LEWIN_LEFF_K_DWCONV);
-    CK(launch_dwconv_gelu_auto<T>(static_cast<const T*>(a->h1), static_cast<T*>(a->h2), save ? static_cast<T*>(a->a2) : nullptr,
-                             a->w_dw, a->b_dw, a->B, a->H, a->W, Ch, stream));
+    bool dw_done = false;
+    if constexpr (Act<T>::kIsBf16) {
+        if (dws::supported(a->H, a->W, Ch)) {     // persistent double-buffered kernel (dwconv_stream.cuh)
+            CK(dws::launch(static_cast<const __nv_bfloat16*>(a->h1), static_cast<__nv_bfloat16*>(a->h2),
+                           save ? static_cast<__nv_bfloat16*>(a->a2) : nullptr, a->w_dw, a->b_dw, a->B, a->H, a->W, Ch, di.sms, stream));
+            dw_done = true;
+        }
+    }
+    if (!dw_done)
+        CK(launch_dwconv_gelu_auto<T>(static_cast<const T*>(a->h1), static_cast<T*>(a->h2), save ? static_cast<T*>(a->a2) : nullptr,
+                                      a->w_dw, a->b_dw, a->B, a->H, a->W, Ch, stream));
     kt.end(LEWIN_LEFF_K_DWCONV);
     {   // linear2 (My_model_1.py:529) + DropPath scale + residual (My_model_1.py:873)
         GemmArgs<T> g{};

@@ -44,6 +44,27 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 
+// packed fp32x2 arithmetic (one issue slot for two lanes of work; same IEEE rounding as the scalar instructions)
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 // fixed shared memory besides the weight tile and the A ring
 template <int BN, int EPI>
 constexpr size_t fixed_smem() {
@@ -118,24 +139,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
         constexpr int U = TC_BM / RPP;                 // rows (== 16-byte loads) per thread per stage
         constexpr int UB = U > 4 ? 4 : U;              // rows per register batch
         constexpr int NB = U / UB;                     // batches per stage
-        constexpr int D = (UB * 2 >= 8) ? (NB > 1 ? 3 : 2) : 8 / UB;   // ring depth in batches: >= 8 loads in flight per thread
         const int pw = warp - (MMA_WARP + 1);
         const int gl = lane % G, sub = lane / G;
         const int kcl = gl / CPR, ch = gl % CPR;
-        float gam[8], bet[8];
-        if (LN) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { gam[j] = g.ln_w[gl * 8 + j]; bet[j] = g.ln_b[gl * 8 + j]; }
-        }
-        const int total = my_tiles * SPT * NB;         // register batches this CTA produces
-        uint4 buf[D][UB];
         // running positions (no divisions in the steady state): loader and writer each walk batch -> stage -> tile
         int l_b = 0, l_st = 0;
         uint32_t l_tile = blockIdx.x;
         uint32_t wb[2] = {0u, 0u}, wy[2] = {0u, 0u}, wx[2] = {0u, 0u};
-        auto load = [&](uint4 (&dst)[UB], int jb) {
-            if (jb >= total) return;
-            if (g.mapA && l_b == 0 && l_st == 0) {     // a 128-row tile is two consecutive windows: decode the first, step once
+        // global address of this thread's 16-byte chunk of batch row p (nullptr: row beyond M); advance() steps to the next batch
+        auto src_of = [&](int p) -> const __nv_bfloat16* {
+            const uint32_t r = (l_b * UB + p) * RPP + pw * RPW + sub;
+            const uint32_t m = l_tile * TC_BM + r;
+            if (m >= g.M) return nullptr;
+            const uint32_t hi = r >> 6;
+            const uint32_t ra = g.mapA ? g.map.pixel(hi ? wb[1] : wb[0], hi ? wy[1] : wy[0], hi ? wx[1] : wx[0], r & 63u) : m;
+            return g.A + static_cast<long long>(ra) * g.lda + (l_st * CPS + kcl) * KC + ch * 8;
+        };
+        auto decode_tile = [&]() {                     // a 128-row tile is two consecutive windows: decode the first, step once
+            if (g.mapA && l_b == 0 && l_st == 0) {
                 const uint32_t wg = l_tile * 2u;
                 wb[0] = wg / static_cast<uint32_t>(g.map.nWin);
                 const uint32_t w = wg - wb[0] * static_cast<uint32_t>(g.map.nWin);
@@ -147,66 +168,138 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
                     if (wy[1] * static_cast<uint32_t>(g.map.nWw) == static_cast<uint32_t>(g.map.nWin)) { wy[1] = 0u; wb[1] += 1u; }
                 }
             }
-            const uint32_t m0 = l_tile * TC_BM;
-            const int kcol = (l_st * CPS + kcl) * KC + ch * 8;
-#pragma unroll
-            for (int p = 0; p < UB; ++p) {
-                const uint32_t r = (l_b * UB + p) * RPP + pw * RPW + sub;
-                const uint32_t m = m0 + r;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (m < g.M) {
-                    const uint32_t hi = r >> 6;
-                    const uint32_t ra = g.mapA ? g.map.pixel(hi ? wb[1] : wb[0], hi ? wy[1] : wy[0], hi ? wx[1] : wx[0], r & 63u) : m;
-                    v = *reinterpret_cast<const uint4*>(g.A + static_cast<long long>(ra) * g.lda + kcol);
-                }
-                dst[p] = v;
-            }
-            if (++l_b == NB) { l_b = 0; if (++l_st == SPT) { l_st = 0; l_tile += gridDim.x; } }
         };
-        int p_b = 0, p_s = 0;
-        uint32_t p_ph = 0;
-        auto process = [&](const uint4 (&src)[UB]) {
-            if (p_b == 0) tc::mbar_wait(&empty[p_s], p_ph ^ 1u);     // the MMAs that read this stage last time have retired
-            unsigned char* dstA = As + static_cast<size_t>(p_s) * STAGE + kcl * A_CHUNK;
+        auto advance = [&]() { if (++l_b == NB) { l_b = 0; if (++l_st == SPT) { l_st = 0; l_tile += gridDim.x; } } };
+        const int total = my_tiles * SPT * NB;         // batches this CTA produces
+
+        if constexpr (LN) {
+            // ---- LayerNorm prologue: global -> register ring -> LN (row statistics by shuffles over the G lanes of the row)
+            //      -> bf16 -> swizzled stage.  The UB rows of a batch are processed side by side (independent dependency
+            //      chains interleave); element-wise steps are packed fp32x2.  Summation order == ln_stats_kernel's.
+            constexpr int D = (UB * 2 >= 8) ? 2 : 8 / UB;   // ring depth in batches: >= 8 loads in flight per thread
+            float2 gam[4], bet[4];
 #pragma unroll
-            for (int p = 0; p < UB; ++p) {
-                const int r = (p_b * UB + p) * RPP + pw * RPW + sub;
-                uint4 v = src[p];
-                if (LN) {
-                    float f[8];
-                    unpack8(v, f);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) sum += f[q];
-                    const float mu = group_sum<G>(sum) * (1.0f / (G * 8));
-                    float sq = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) { f[q] -= mu; sq += f[q] * f[q]; }
-                    const float rs = rsqrtf(group_sum<G>(sq) * (1.0f / (G * 8)) + 1e-5f);
-                    v.x = tc::pack_bf16(f[0] * rs * gam[0] + bet[0], f[1] * rs * gam[1] + bet[1]);
-                    v.y = tc::pack_bf16(f[2] * rs * gam[2] + bet[2], f[3] * rs * gam[3] + bet[3]);
-                    v.z = tc::pack_bf16(f[4] * rs * gam[4] + bet[4], f[5] * rs * gam[5] + bet[5]);
-                    v.w = tc::pack_bf16(f[6] * rs * gam[6] + bet[6], f[7] * rs * gam[7] + bet[7]);
-                }
-                *reinterpret_cast<uint4*>(dstA + tc::swz_off<KC>(r, ch)) = v;
+            for (int j = 0; j < 4; ++j) {
+                gam[j] = make_float2(g.ln_w[gl * 8 + 2 * j], g.ln_w[gl * 8 + 2 * j + 1]);
+                bet[j] = make_float2(g.ln_b[gl * 8 + 2 * j], g.ln_b[gl * 8 + 2 * j + 1]);
             }
-            if (++p_b == NB) {
-                tc::fence_proxy_async();               // my generic-proxy smem writes -> visible to the tensor core
-                mbar_arrive(&full[p_s]);
-                p_b = 0;
-                if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
-            }
-        };
+            uint4 buf[D][UB];
+            auto load = [&](uint4 (&dst)[UB], int jb) {
+                if (jb >= total) return;
+                decode_tile();
 #pragma unroll
-        for (int d = 0; d < D - 1; ++d) load(buf[d], d);
-        for (int j0 = 0; j0 < total; j0 += D) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const int jb = j0 + d;
-                if (jb < total) {
-                    load(buf[(d + D - 1) % D], jb + D - 1);
-                    process(buf[d]);
+                for (int p = 0; p < UB; ++p) {
+                    const __nv_bfloat16* src = src_of(p);
+                    dst[p] = src ? *reinterpret_cast<const uint4*>(src) : make_uint4(0u, 0u, 0u, 0u);
                 }
+                advance();
+            };
+            int p_b = 0, p_s = 0;
+            uint32_t p_ph = 0;
+            auto process = [&](const uint4 (&src)[UB]) {
+                if (p_b == 0) tc::mbar_wait(&empty[p_s], p_ph ^ 1u);     // the MMAs that read this stage last time have retired
+                unsigned char* dstA = As + static_cast<size_t>(p_s) * STAGE + kcl * A_CHUNK;
+                constexpr int PB = UB < 2 ? UB : 2;    // rows processed side by side (register budget: 96 per thread)
+#pragma unroll
+                for (int p0 = 0; p0 < UB; p0 += PB) {
+                    float2 f[PB][4];
+                    float sum[PB], sq[PB];
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const uint32_t w4[4] = {src[p0 + p].x, src[p0 + p].y, src[p0 + p].z, src[p0 + p].w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) f[p][q] = make_float2(__uint_as_float(w4[q] << 16), __uint_as_float(w4[q] & 0xFFFF0000u));
+                        sum[p] = 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int p = 0; p < PB; ++p) { sum[p] += f[p][q].x; sum[p] += f[p][q].y; }
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+                        for (int p = 0; p < PB; ++p) sum[p] += __shfl_xor_sync(0xffffffffu, sum[p], o);
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const float nmu = -(sum[p] * (1.0f / (G * 8)));
+                        const float2 nm2 = make_float2(nmu, nmu);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) f[p][q] = add2(f[p][q], nm2);
+                        sq[p] = 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int p = 0; p < PB; ++p) { sq[p] = fmaf(f[p][q].x, f[p][q].x, sq[p]); sq[p] = fmaf(f[p][q].y, f[p][q].y, sq[p]); }
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+                        for (int p = 0; p < PB; ++p) sq[p] += __shfl_xor_sync(0xffffffffu, sq[p], o);
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const int r = (p_b * UB + p0 + p) * RPP + pw * RPW + sub;
+                        const float rs = rsqrtf(sq[p] * (1.0f / (G * 8)) + 1e-5f);
+                        const float2 rs2 = make_float2(rs, rs);
+                        uint32_t o4[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 y2 = fma2(mul2(f[p][q], rs2), gam[q], bet[q]);
+                            o4[q] = tc::pack_bf16(y2.x, y2.y);
+                        }
+                        *reinterpret_cast<uint4*>(dstA + tc::swz_off<KC>(r, ch)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                    }
+                }
+                if (++p_b == NB) {
+                    tc::fence_proxy_async();           // my generic-proxy smem writes -> visible to the tensor core
+                    mbar_arrive(&full[p_s]);
+                    p_b = 0;
+                    if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
+                }
+            };
+#pragma unroll
+            for (int d = 0; d < D - 1; ++d) load(buf[d], d);
+            for (int j0 = 0; j0 < total; j0 += D) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const int jb = j0 + d;
+                    if (jb < total) {
+                        load(buf[(d + D - 1) % D], jb + D - 1);
+                        process(buf[d]);
+                    }
+                }
+            }
+        } else {
+            // ---- plain bf16 operand: 16-byte cp.async straight into the swizzled stage, DD stages in flight per thread
+            //      (no register staging: the in-flight depth is bounded by shared memory, not registers)
+            static_assert(NB == 1, "plain operands: one batch per stage");
+            const int DD = S - 1 < 4 ? S - 1 : 4;      // stages issued ahead (S >= 2)
+            const uint32_t As_u = tc::smem_u32(As);
+            int i_s = 0;                               // issue-side ring position
+            uint32_t i_ph = 0;
+            auto issue = [&](int j) {
+                if (j < total) {
+                    tc::mbar_wait(&empty[i_s], i_ph ^ 1u);
+                    decode_tile();
+#pragma unroll
+                    for (int p = 0; p < UB; ++p) {
+                        const int r = p * RPP + pw * RPW + sub;
+                        const __nv_bfloat16* src = src_of(p);
+                        cp_async16_z(As_u + i_s * STAGE + kcl * A_CHUNK + tc::swz_off<KC>(r, ch), src ? src : g.A, src != nullptr);
+                    }
+                    advance();
+                    if (++i_s == S) { i_s = 0; i_ph ^= 1u; }
+                }
+                cp_async_commit();
+            };
+            for (int d = 0; d < DD; ++d) issue(d);
+            int c_s = 0;
+            for (int j = 0; j < total; ++j) {
+                issue(j + DD);
+                // groups complete in order: allow DD newer groups to stay in flight
+                if (DD == 4) cp_async_wait<4>(); else if (DD == 3) cp_async_wait<3>(); else if (DD == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                tc::fence_proxy_async();
+                mbar_arrive(&full[c_s]);
+                if (++c_s == S) c_s = 0;
             }
         }
     } else if (warp == MMA_WARP) {
@@ -280,9 +373,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
                 }
                 unsigned char* sb = my_stg + (q & 1) * STG_BUF;
                 unsigned char* srow = sb + lane * STG_ROW;
-                const float* bs = s_bias + c * 32;
+                const float2* bs2 = reinterpret_cast<const float2*>(s_bias + c * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += bs[j];
+                for (int j = 0; j < 16; ++j) {
+                    const float2 t2 = add2(make_float2(v[2 * j], v[2 * j + 1]), bs2[j]);
+                    v[2 * j] = t2.x; v[2 * j + 1] = t2.y;
+                }
                 if (EPI == EPI_BIAS_RESID) {
                     if (q >= 2) {                   // (not reached for BN <= 128) late residual chunk: synchronous, coalesced
                         __syncwarp();

@@ -10,6 +10,7 @@
 #include "leff_fused.cuh"
 #include "probsparse_core.cuh"
 #include "probsparse_core_bf16.cuh"
+#include "probsparse_core_v3.cuh"
 #include "backward.cuh"
 
 #include <atomic>
@@ -194,7 +195,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
             b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense; b.cw = cw;
             b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
             b.shift = c.shift; b.H = c.H; b.W = c.W; b.nWw = c.nWw; b.nWin = c.nWin;
-            CK(launch_core_bf16(b, di.sms, stream));
+            CK(pc3::enabled() ? pc3::launch(b, di.sms, stream) : launch_core_bf16(b, di.sms, stream));
         } else {
             CK(launch_core_fwd<T>(c, di.sms, stream));
         }
@@ -266,7 +267,7 @@ int core_only_fwd(const LewinCoreFwdArgs* a, void* ws, size_t ws_bytes, cudaStre
         b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense; b.cw = cw;
         b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
         b.shift = 0; b.H = 8; b.W = 8; b.nWw = 1; b.nWin = 1;
-        CK(launch_core_bf16(b, di.sms, stream));
+        CK(pc3::enabled() ? pc3::launch(b, di.sms, stream) : launch_core_bf16(b, di.sms, stream));
     } else
     CK(launch_core_fwd<T>(c, di.sms, stream));
     g_launches.fetch_add(2, std::memory_order_relaxed);

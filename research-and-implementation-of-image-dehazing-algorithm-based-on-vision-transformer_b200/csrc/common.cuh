@@ -187,14 +187,16 @@ __device__ __forceinline__ void gelu_tab2_to_smem(uint16_t* dst, int tid, int nt
 // no branch.  `oor` accumulates the biased magnitudes: (oor >> 12) != 0 afterwards means some element handled by this
 // thread was outside the table and the caller must redo its elements with gelu_pair_exact.
 __device__ __forceinline__ uint32_t gelu_pair_fast(const uint16_t* __restrict__ tab2, uint32_t in2, uint32_t& oor) {
-    const uint32_t sh3 = in2 >> 3;
-    const uint32_t r0 = (in2 & 0x7FFFu) - kGelu2Base;
-    const uint32_t r1 = ((in2 >> 16) & 0x7FFFu) - kGelu2Base;
-    oor |= r0 | r1;
-    const uint32_t i0 = min(r0, 4095u) | (sh3 & 0x1000u);
-    const uint32_t i1 = min(r1, 4095u) | ((sh3 >> 16) & 0x1000u);
-    return static_cast<uint32_t>(tab2[i0]) | (static_cast<uint32_t>(tab2[i1]) << 16);
+    // both halves at once: biased magnitudes (a borrow out of the low half only happens when that half is out of range,
+    // and then the whole pair is redone exactly), sign bits moved to bit 12 of each half
+    const uint32_t t = (in2 & 0x7FFF7FFFu) - (kGelu2Base | (kGelu2Base << 16));
+    oor |= t;
+    const uint32_t idx2 = (t & 0x0FFF0FFFu) | ((in2 >> 3) & 0x10001000u);
+    const uint32_t lo = tab2[idx2 & 0xFFFFu], hi = tab2[idx2 >> 16];
+    return lo | (hi << 16);
 }
+// true if any element accumulated into `oor` by gelu_pair_fast was outside the table
+__device__ __forceinline__ bool gelu_pair_oor(uint32_t oor) { return (oor & 0xF000F000u) != 0u; }
 // exact for every bf16 input (table inside 2^-28 <= |x| < 16, closed forms outside: 0.5 x, x or -0)
 __device__ __noinline__ uint32_t gelu_pair_exact(const uint16_t* __restrict__ tab2, uint32_t in2) {
     uint32_t out = 0;

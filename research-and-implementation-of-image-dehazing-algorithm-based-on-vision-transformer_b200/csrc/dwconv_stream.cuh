@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a)
             const uint32_t in0 = *reinterpret_cast<uint32_t*>(&h0), in1 = *reinterpret_cast<uint32_t*>(&h1);
             uint32_t oor = 0;
             uint32_t q0 = gelu_pair_fast(gtab, in0, oor), q1 = gelu_pair_fast(gtab, in1, oor);
-            if (__builtin_expect((oor >> 12) != 0u, 0)) { q0 = gelu_pair_exact(gtab, in0); q1 = gelu_pair_exact(gtab, in1); }
+            if (__builtin_expect(gelu_pair_oor(oor), 0)) { q0 = gelu_pair_exact(gtab, in0); q1 = gelu_pair_exact(gtab, in1); }
             if (pp) { *reinterpret_cast<uint2*>(pp) = make_uint2(in0, in1); pp += rstride; }
             *reinterpret_cast<uint2*>(op) = make_uint2(q0, q1);
             op += rstride;

@@ -25,10 +25,11 @@
 namespace lewin {
 namespace ws {
 
-constexpr int NEW = 8;                        // epilogue warps (warp % 4 == TMEM lane group, warp / 4 == column half)
-constexpr int NPW = 8;                        // producer warps
-constexpr int MMA_WARP = NEW;
-constexpr int THREADS = (NEW + 1 + NPW) * 32;
+// warp roles: [0, NEW) epilogue (warp % 4 == TMEM lane group, warp / 4 == column group), NEW: MMA issuer,
+// (NEW, NEW + NPW]: producers.  NEW + NPW == 16 (17 warps); the split is a template parameter because the balance differs:
+// 8 + 8 for the plain epilogues, 12 + 4 where the epilogue carries the GELU.
+constexpr int WARPS = 17;
+constexpr int THREADS = WARPS * 32;
 constexpr int STG_ROW = 80;                   // staging row: 32 bf16 columns (64 B) + 16 B pad (conflict-free 16 B accesses)
 constexpr int STG_BUF = 32 * STG_ROW;
 constexpr int SMEM_MAX = 227 * 1024;
@@ -66,16 +67,20 @@ __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const flo
 }
 
 // fixed shared memory besides the weight tile and the A ring
-template <int BN, int EPI>
+template <int BN, int EPI, int NEW>
 constexpr size_t fixed_smem() {
     return 1024 /*align*/ + NEW * 2 * STG_BUF + BN * 4 + (2 * 8 + 4) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGelu2TabSize * 2 : 0);
 }
 
 // BN: tile columns; KC: k-chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); CPS: k-chunks per ring stage (LN needs the
 // whole row in one stage: CPS * KC == K); LN: LayerNorm prologue over the K channels of the A row.
-template <int BN, int KC, int CPS, int EPI, bool LN>
+template <int BN, int KC, int CPS, int EPI, bool LN, int NEW>
 __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv_bfloat16> g, int row_tiles, int nkc, int S) {
     using T = __nv_bfloat16;
+    constexpr int NPW = WARPS - 1 - NEW;               // producer warps
+    constexpr int MMA_WARP = NEW;
+    constexpr int NCG = NEW / 4;                       // epilogue column groups
+    static_assert(NEW % 4 == 0 && (NPW == 4 || NPW == 8), "warp split");
     constexpr int CPR = KC / 8;                        // 16-byte chunks per tile row per k-chunk
     constexpr int A_CHUNK = TC_BM * KC * 2;
     constexpr int W_CHUNK = BN * KC * 2;
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
         }
     } else {
         // ============================================================ epilogue: thread == TMEM lane == tile row
-        const int lg = warp & 3, half = warp >> 2;
+        const int lg = warp & 3, half = warp >> 2;     // TMEM lane group, column group
         unsigned char* my_stg = stg + warp * 2 * STG_BUF;
         for (int it = 0; it < my_tiles; ++it) {
             const int acc = it & 1;
@@ -349,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
             }
             if (EPI == EPI_BIAS_RESID) {            // residual rows of my first two chunks -> staging (async, coalesced)
                 int q = 0;
-                for (int c = half; c < NCH && q < 2; c += 2, ++q) {
+                for (int c = half; c < NCH && q < 2; c += NCG, ++q) {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
@@ -364,10 +369,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
             if (EPI == EPI_BIAS_RESID) { cp_async_wait<0>(); __syncwarp(); }
             const uint32_t t_addr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(acc * ACC);
             int q = 0;
-            for (int c = half; c < NCH; c += 2, ++q) {
+            for (int c = half; c < NCH; c += NCG, ++q) {
                 float v[32];
                 tc::tmem_ld32(t_addr + c * 32, v);
-                if (c + 2 >= NCH) {                 // last chunk of this warp is in registers: hand the accumulator back
+                if (c + NCG >= NCH) {               // last chunk of this warp is in registers: hand the accumulator back
                     tc::tc_fence_before();
                     mbar_arrive(&tempty[acc]);
                 }
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
                         uint32_t oor = 0, ge[16];
 #pragma unroll
                         for (int h = 0; h < 16; ++h) ge[h] = gelu_pair_fast(gtab, pk[h], oor);
-                        if (__builtin_expect((oor >> 12) != 0u, 0)) {
+                        if (__builtin_expect(gelu_pair_oor(oor), 0)) {
 #pragma unroll
                             for (int h = 0; h < 16; ++h) ge[h] = gelu_pair_exact(gtab, pk[h]);
                         }
@@ -462,12 +467,13 @@ template <int BN, int KC, int CPS, int EPI, bool LN>
 cudaError_t launch_inst(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaStream_t stream) {
     constexpr int A_CHUNK = TC_BM * KC * 2, W_CHUNK = BN * KC * 2, STAGE = CPS * A_CHUNK;
     const int nkc = g.K / KC;
-    const size_t fixed = fixed_smem<BN, EPI>() + static_cast<size_t>(nkc) * W_CHUNK;
+    constexpr int NEW = 8;   // (12 + 4 measured slower for the GELU epilogue: the 4 producer warps become the bottleneck)
+    const size_t fixed = fixed_smem<BN, EPI, NEW>() + static_cast<size_t>(nkc) * W_CHUNK;
     if (fixed + 2 * STAGE > SMEM_MAX) return cudaErrorInvalidConfiguration;
     int S = static_cast<int>((SMEM_MAX - fixed) / STAGE);
     if (S > 8) S = 8;
     const size_t smem = fixed + static_cast<size_t>(S) * STAGE;
-    auto k = gemm_ws_kernel<BN, KC, CPS, EPI, LN>;
+    auto k = gemm_ws_kernel<BN, KC, CPS, EPI, LN, NEW>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const int row_tiles = static_cast<int>((g.M + TC_BM - 1) / TC_BM);

@@ -60,8 +60,11 @@ __global__ void __launch_bounds__(THREADS, 5) probsparse_core_v3_kernel(const Co
             if (__half2float(c1) > 0.f) sampled |= 1u << (half * 16 + j * 2 + 1);
         }
     if (tid < 32) s.tok_of[tid] = -1;                   // slots 25..31 stay -1 for the whole kernel
-    if (a.use_rpb && a.rpb_table && a.nH == 1)
-        for (int i = tid; i < 225; i += THREADS) s.tbl[i] = a.rpb_table[i];
+    // the grid is a multiple of nH whenever it is smaller than the item count, so a CTA keeps one head: its bias table
+    // is staged once
+    const bool fixed_head = (gridDim.x % a.nH) == 0;
+    if (a.use_rpb && a.rpb_table && fixed_head)
+        for (int i = tid; i < 225; i += THREADS) s.tbl[i] = a.rpb_table[i * a.nH + static_cast<int>(blockIdx.x) % a.nH];
 
     auto prefetch = [&](int item, int buf) {
         const int wg = item / a.nH, h = item - wg * a.nH;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(THREADS, 5) probsparse_core_v3_kernel(const Co
         const __nv_bfloat16* sk = sq + TILE;
         const __nv_bfloat16* sv = sk + TILE;
         // per-item tables (visible to their readers after B2 / B3)
-        if (a.use_rpb && a.rpb_table && a.nH > 1)
+        if (a.use_rpb && a.rpb_table && !fixed_head)
             for (int i = tid; i < 225; i += THREADS) s.tbl[i] = a.rpb_table[i * a.nH + h];
         if (a.shift > 0) {
             if (tid < kTok) {
@@ -327,7 +330,9 @@ inline cudaError_t launch(const CoreBf16Args& a, int num_sms, cudaStream_t strea
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const long long items = static_cast<long long>(a.B_) * a.nH;
-    const long long cap = static_cast<long long>(num_sms) * 5;
+    long long cap = static_cast<long long>(num_sms) * 5;
+    cap -= cap % a.nH;                                   // one head per CTA (see fixed_head)
+    if (cap < a.nH) cap = a.nH;
     k<<<static_cast<unsigned>(items < cap ? items : cap), THREADS, smem, stream>>>(a);
     return cudaGetLastError();
 }

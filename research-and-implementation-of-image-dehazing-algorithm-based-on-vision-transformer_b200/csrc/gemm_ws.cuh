@@ -45,6 +45,11 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 
+inline bool enabled() {
+    static const bool on = [] { const char* e = getenv("LEWIN_NO_WS_GEMM"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 // packed fp32x2 arithmetic (one issue slot for two lanes of work; same IEEE rounding as the scalar instructions)
 __device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
     unsigned long long d;
@@ -70,6 +75,127 @@ __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const flo
 template <int BN, int EPI, int NEW>
 constexpr size_t fixed_smem() {
     return 1024 /*align*/ + NEW * 2 * STG_BUF + BN * 4 + (2 * 8 + 4) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGelu2TabSize * 2 : 0);
+}
+
+// One warp's share of one output tile: wait for the accumulator, tcgen05.ld 32-column chunks (thread == TMEM lane == tile
+// row), bias / GELU / residual, stage, row-cooperative coalesced stores.  Shared by the resident-W and streamed-W kernels.
+template <int BN, int EPI, int NCG>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, uint32_t tmem_d, int acc, uint32_t aph, uint32_t tile,
+                                              int n0, const float* s_bias, const uint16_t* gtab, unsigned char* my_stg,
+                                              uint64_t* tfull, uint64_t* tempty, int lg, int half, int lane) {
+    using T = __nv_bfloat16;
+    constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr int NCH = BN / 32;
+        const uint32_t m = tile * TC_BM + lg * 32 + lane;
+        long long oy = -1;
+        float sc = 1.f;
+        if (m < g.M) {
+            const uint32_t ry = g.mapY ? g.map.token32(m) : m;
+            oy = static_cast<long long>(ry) * g.ldy;
+            if (EPI == EPI_BIAS_RESID && g.drop_scale) sc = g.drop_scale[ry / static_cast<uint32_t>(g.tokens_per_image)];
+        }
+        if (EPI == EPI_BIAS_RESID) {            // residual rows of my first two chunks -> staging (async, coalesced)
+            int q = 0;
+            for (int c = half; c < NCH && q < 2; c += NCG, ++q) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+                    const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                    if (o >= 0) cp_async16(my_stg + q * STG_BUF + rl * STG_ROW + cc * 16, g.R + o + n0 + c * 32 + cc * 8);
+                }
+            }
+            cp_async_commit();
+        }
+        tc::mbar_wait(&tfull[acc], aph);
+        tc::tc_fence_after();
+        if (EPI == EPI_BIAS_RESID) { cp_async_wait<0>(); __syncwarp(); }
+        const uint32_t t_addr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(acc * ACC);
+        int q = 0;
+        for (int c = half; c < NCH; c += NCG, ++q) {
+            float v[32];
+            tc::tmem_ld32(t_addr + c * 32, v);
+            if (c + NCG >= NCH) {               // last chunk of this warp is in registers: hand the accumulator back
+                tc::tc_fence_before();
+                mbar_arrive(&tempty[acc]);
+            }
+            unsigned char* sb = my_stg + (q & 1) * STG_BUF;
+            unsigned char* srow = sb + lane * STG_ROW;
+            const float2* bs2 = reinterpret_cast<const float2*>(s_bias + c * 32);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 t2 = add2(make_float2(v[2 * j], v[2 * j + 1]), bs2[j]);
+                v[2 * j] = t2.x; v[2 * j + 1] = t2.y;
+            }
+            if (EPI == EPI_BIAS_RESID) {
+                if (q >= 2) {                   // (not reached for BN <= 128) late residual chunk: synchronous, coalesced
+                    __syncwarp();
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+                        const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                        if (o >= 0)
+                            *reinterpret_cast<uint4*>(sb + rl * STG_ROW + cc * 16) =
+                                *reinterpret_cast<const uint4*>(g.R + o + n0 + c * 32 + cc * 8);
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 rv = *reinterpret_cast<const uint4*>(srow + j * 2);
+                    float rf[8];
+                    unpack8(rv, rf);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[j + e] = rf[e] + sc * Act<T>::round(v[j + e]);
+                }
+            }
+            if (EPI == EPI_BIAS_GELU && g.Y2) {          // training: pre-activation copy first
+#pragma unroll
+                for (int j = 0; j < 32; j += 8)
+                    *reinterpret_cast<uint4*>(srow + j * 2) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
+                                                                          tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
+                __syncwarp();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+                    const uint4 val = *reinterpret_cast<const uint4*>(sb + rl * STG_ROW + cc * 16);
+                    const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                    if (o >= 0) *reinterpret_cast<uint4*>(g.Y2 + o + n0 + c * 32 + cc * 8) = val;
+                }
+                __syncwarp();
+            }
+            {
+                uint32_t pk[16];
+#pragma unroll
+                for (int h = 0; h < 16; ++h) pk[h] = tc::pack_bf16(v[2 * h], v[2 * h + 1]);
+                if (EPI == EPI_BIAS_GELU) {        // branch-free table GELU, one deferred range test per thread and chunk
+                    uint32_t oor = 0, ge[16];
+#pragma unroll
+                    for (int h = 0; h < 16; ++h) ge[h] = gelu_pair_fast(gtab, pk[h], oor);
+                    if (__builtin_expect(gelu_pair_oor(oor), 0)) {
+#pragma unroll
+                        for (int h = 0; h < 16; ++h) ge[h] = gelu_pair_exact(gtab, pk[h]);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 16; ++h) pk[h] = ge[h];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(srow + j * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {             // 8 rows x 64 contiguous bytes per warp instruction
+                const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+                const uint4 val = *reinterpret_cast<const uint4*>(sb + rl * STG_ROW + cc * 16);
+                const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                if (o >= 0) *reinterpret_cast<uint4*>(g.Y + o + n0 + c * 32 + cc * 8) = val;
+            }
+            __syncwarp();                                // staging buffer reusable
+        }
+        if (half >= NCH) {                               // this warp owns no chunk (BN == 32): still hand back
+            tc::tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+        }
 }
 
 // BN: tile columns; KC: k-chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); CPS: k-chunks per ring stage (LN needs the
@@ -341,119 +467,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
         const int lg = warp & 3, half = warp >> 2;     // TMEM lane group, column group
         unsigned char* my_stg = stg + warp * 2 * STG_BUF;
         for (int it = 0; it < my_tiles; ++it) {
-            const int acc = it & 1;
-            const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
-            const uint32_t tile = blockIdx.x + static_cast<uint32_t>(it) * gridDim.x;
-            const uint32_t m = tile * TC_BM + lg * 32 + lane;
-            long long oy = -1;
-            float sc = 1.f;
-            if (m < g.M) {
-                const uint32_t ry = g.mapY ? g.map.token32(m) : m;
-                oy = static_cast<long long>(ry) * g.ldy;
-                if (EPI == EPI_BIAS_RESID && g.drop_scale) sc = g.drop_scale[ry / static_cast<uint32_t>(g.tokens_per_image)];
-            }
-            if (EPI == EPI_BIAS_RESID) {            // residual rows of my first two chunks -> staging (async, coalesced)
-                int q = 0;
-                for (int c = half; c < NCH && q < 2; c += NCG, ++q) {
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
-                        const long long o = __shfl_sync(0xffffffffu, oy, rl);
-                        if (o >= 0) cp_async16(my_stg + q * STG_BUF + rl * STG_ROW + cc * 16, g.R + o + n0 + c * 32 + cc * 8);
-                    }
-                }
-                cp_async_commit();
-            }
-            tc::mbar_wait(&tfull[acc], aph);
-            tc::tc_fence_after();
-            if (EPI == EPI_BIAS_RESID) { cp_async_wait<0>(); __syncwarp(); }
-            const uint32_t t_addr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(acc * ACC);
-            int q = 0;
-            for (int c = half; c < NCH; c += NCG, ++q) {
-                float v[32];
-                tc::tmem_ld32(t_addr + c * 32, v);
-                if (c + NCG >= NCH) {               // last chunk of this warp is in registers: hand the accumulator back
-                    tc::tc_fence_before();
-                    mbar_arrive(&tempty[acc]);
-                }
-                unsigned char* sb = my_stg + (q & 1) * STG_BUF;
-                unsigned char* srow = sb + lane * STG_ROW;
-                const float2* bs2 = reinterpret_cast<const float2*>(s_bias + c * 32);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float2 t2 = add2(make_float2(v[2 * j], v[2 * j + 1]), bs2[j]);
-                    v[2 * j] = t2.x; v[2 * j + 1] = t2.y;
-                }
-                if (EPI == EPI_BIAS_RESID) {
-                    if (q >= 2) {                   // (not reached for BN <= 128) late residual chunk: synchronous, coalesced
-                        __syncwarp();
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
-                            const long long o = __shfl_sync(0xffffffffu, oy, rl);
-                            if (o >= 0)
-                                *reinterpret_cast<uint4*>(sb + rl * STG_ROW + cc * 16) =
-                                    *reinterpret_cast<const uint4*>(g.R + o + n0 + c * 32 + cc * 8);
-                        }
-                        __syncwarp();
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const uint4 rv = *reinterpret_cast<const uint4*>(srow + j * 2);
-                        float rf[8];
-                        unpack8(rv, rf);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[j + e] = rf[e] + sc * Act<T>::round(v[j + e]);
-                    }
-                }
-                if (EPI == EPI_BIAS_GELU && g.Y2) {          // training: pre-activation copy first
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8)
-                        *reinterpret_cast<uint4*>(srow + j * 2) = make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
-                                                                              tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
-                    __syncwarp();
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
-                        const uint4 val = *reinterpret_cast<const uint4*>(sb + rl * STG_ROW + cc * 16);
-                        const long long o = __shfl_sync(0xffffffffu, oy, rl);
-                        if (o >= 0) *reinterpret_cast<uint4*>(g.Y2 + o + n0 + c * 32 + cc * 8) = val;
-                    }
-                    __syncwarp();
-                }
-                {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int h = 0; h < 16; ++h) pk[h] = tc::pack_bf16(v[2 * h], v[2 * h + 1]);
-                    if (EPI == EPI_BIAS_GELU) {        // branch-free table GELU, one deferred range test per thread and chunk
-                        uint32_t oor = 0, ge[16];
-#pragma unroll
-                        for (int h = 0; h < 16; ++h) ge[h] = gelu_pair_fast(gtab, pk[h], oor);
-                        if (__builtin_expect(gelu_pair_oor(oor), 0)) {
-#pragma unroll
-                            for (int h = 0; h < 16; ++h) ge[h] = gelu_pair_exact(gtab, pk[h]);
-                        }
-#pragma unroll
-                        for (int h = 0; h < 16; ++h) pk[h] = ge[h];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4*>(srow + j * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {             // 8 rows x 64 contiguous bytes per warp instruction
-                    const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
-                    const uint4 val = *reinterpret_cast<const uint4*>(sb + rl * STG_ROW + cc * 16);
-                    const long long o = __shfl_sync(0xffffffffu, oy, rl);
-                    if (o >= 0) *reinterpret_cast<uint4*>(g.Y + o + n0 + c * 32 + cc * 8) = val;
-                }
-                __syncwarp();                                // staging buffer reusable
-            }
-            if (half >= NCH) {                               // this warp owns no chunk (BN == 32): still hand back
-                tc::tc_fence_before();
-                mbar_arrive(&tempty[acc]);
-            }
+            epilogue_tile<BN, EPI, NCG>(g, tmem_d, it & 1, static_cast<uint32_t>(it >> 1) & 1u, blockIdx.x + static_cast<uint32_t>(it) * gridDim.x,
+                                        n0, s_bias, gtab, my_stg, tfull, tempty, lg, half, lane);
         }
     }
 
@@ -485,10 +500,167 @@ cudaError_t launch_inst(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaStrea
     return cudaGetLastError();
 }
 
-inline bool enabled() {
-    static const bool on = [] { const char* e = getenv("LEWIN_NO_WS_GEMM"); return !(e && e[0] == '1'); }();
-    return on;
+// ------------------------------------------------------------------------------------------------------------------
+// Streamed-W variant for the tensor-bound levels (C >= 256): the weight matrix no longer fits next to the A ring, so a
+// ring stage carries one k-chunk of BOTH operands (A[128 x 64] + W[BN x 64], plain bf16 in global memory: weights
+// pre-converted by convert_w_kernel, LayerNorm pre-applied by ln_apply_kernel).  Same three roles and the same
+// epilogue as above; tiles are walked column-fastest so that the CTAs working on one row band share its A rows in L2.
+template <int BN, int EPI>
+constexpr size_t wss_fixed_smem(int N) {
+    return 1024 + 8 * 2 * STG_BUF + static_cast<size_t>(N) * 4 + (2 * 8 + 4) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGelu2TabSize * 2 : 0);
 }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(THREADS, 1) gemm_wss_kernel(const GemmArgs<__nv_bfloat16> g, const __nv_bfloat16* __restrict__ Wb,
+                                                              int row_tiles, int col_tiles, int nkc, int S) {
+    using T = __nv_bfloat16;
+    constexpr int NEW = 8, NPW = 8, MMA_WARP = NEW, NCG = NEW / 4;
+    constexpr int KC = 64, CPR = 8;
+    constexpr int A_CHUNK = TC_BM * KC * 2, W_CHUNK = BN * KC * 2, STAGE = A_CHUNK + W_CHUNK;
+    constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr int TMEM_COLS = 2 * ACC;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(TC_BM >> 4) << 24);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* ring = base;                                     // [S][A_CHUNK | W_CHUNK]
+    unsigned char* stg = ring + static_cast<size_t>(S) * STAGE;     // [NEW][2][STG_BUF]
+    float* s_bias = reinterpret_cast<float*>(stg + NEW * 2 * STG_BUF);          // [N] (all column tiles)
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + g.N);
+    uint64_t* empty = full + 8;
+    uint64_t* tfull = empty + 8;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint16_t* gtab = reinterpret_cast<uint16_t*>(tmem_slot + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int total_tiles = row_tiles * col_tiles;
+    const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+    for (int i = tid; i < g.N; i += THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[i]) : 0.f;
+    if (EPI == EPI_BIAS_GELU) gelu_tab2_to_smem(gtab, tid, THREADS);
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], NPW * 32); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], NEW * 32); }
+        tc::fence_barrier_init();
+    }
+    if (warp == MMA_WARP) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp > MMA_WARP) {
+        // ============================================================ producers: cp.async both operands, DD stages ahead
+        const int pt = tid - (MMA_WARP + 1) * 32;                  // 0..255
+        const int DD = S - 1 < 4 ? S - 1 : 4;
+        const uint32_t ring_u = tc::smem_u32(ring);
+        const int total = my_tiles * nkc;
+        int l_kc = 0;
+        int l_tile = blockIdx.x;
+        int i_s = 0;
+        uint32_t i_ph = 0;
+        auto issue = [&](int j) {
+            if (j < total) {
+                tc::mbar_wait(&empty[i_s], i_ph ^ 1u);
+                const int rt = l_tile / col_tiles, ct = l_tile - rt * col_tiles;
+                const uint32_t dst = ring_u + i_s * STAGE;
+#pragma unroll
+                for (int i = 0; i < TC_BM * CPR / 256; ++i) {
+                    const int c = pt + i * 256, r = c >> 3, ch = c & 7;
+                    const long long m = static_cast<long long>(rt) * TC_BM + r;
+                    const bool ok = m < g.M;
+                    cp_async16_z(dst + tc::swz_off<64>(r, ch), g.A + (ok ? m : 0) * g.lda + l_kc * KC + ch * 8, ok);
+                }
+#pragma unroll
+                for (int i = 0; i < BN * CPR / 256; ++i) {
+                    const int c = pt + i * 256, r = c >> 3, ch = c & 7;
+                    cp_async16_z(dst + A_CHUNK + tc::swz_off<64>(r, ch), Wb + static_cast<long long>(ct * BN + r) * g.K + l_kc * KC + ch * 8, true);
+                }
+                if (++l_kc == nkc) { l_kc = 0; l_tile += gridDim.x; }
+                if (++i_s == S) { i_s = 0; i_ph ^= 1u; }
+            }
+            cp_async_commit();
+        };
+        for (int d = 0; d < DD; ++d) issue(d);
+        int c_s = 0;
+        for (int j = 0; j < total; ++j) {
+            issue(j + DD);
+            if (DD == 4) cp_async_wait<4>(); else if (DD == 3) cp_async_wait<3>(); else if (DD == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+            tc::fence_proxy_async();
+            mbar_arrive(&full[c_s]);
+            if (++c_s == S) c_s = 0;
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t ring_u = tc::smem_u32(ring);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int acc = it & 1;
+                const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+                tc::mbar_wait(&tempty[acc], aph ^ 1u);
+                tc::tc_fence_after();
+                const uint32_t d_addr = tmem_d + static_cast<uint32_t>(acc * ACC);
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait(&full[s], ph);
+                    tc::tc_fence_after();
+                    const uint64_t da = tc::make_desc<64>(ring_u + s * STAGE);
+                    const uint64_t db = tc::make_desc<64>(ring_u + s * STAGE + A_CHUNK);
+#pragma unroll
+                    for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(d_addr, da + 2 * k16, db + 2 * k16, IDESC, (kc > 0 || k16 > 0) ? 1u : 0u);
+                    tc::mma_commit(&empty[s]);
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                tc::mma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        const int lg = warp & 3, half = warp >> 2;
+        unsigned char* my_stg = stg + warp * 2 * STG_BUF;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
+            const int rt = t / col_tiles, ct = t - rt * col_tiles;
+            epilogue_tile<BN, EPI, NCG>(g, tmem_d, it & 1, static_cast<uint32_t>(it >> 1) & 1u, static_cast<uint32_t>(rt), ct * BN,
+                                        s_bias + ct * BN, gtab, my_stg, tfull, tempty, lg, half, lane);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
+}
+
+template <int BN, int EPI>
+cudaError_t wss_launch_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, int num_sms, cudaStream_t stream) {
+    constexpr int STAGE = TC_BM * 64 * 2 + BN * 64 * 2;
+    const size_t fixed = wss_fixed_smem<BN, EPI>(g.N);
+    if (fixed + 2 * STAGE > SMEM_MAX) return cudaErrorInvalidConfiguration;
+    int S = static_cast<int>((SMEM_MAX - fixed) / STAGE);
+    if (S > 8) S = 8;
+    const size_t smem = fixed + static_cast<size_t>(S) * STAGE;
+    auto k = gemm_wss_kernel<BN, EPI>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const int row_tiles = static_cast<int>((g.M + TC_BM - 1) / TC_BM);
+    const int col_tiles = g.N / BN;
+    int grid = num_sms;
+    if (grid > row_tiles * col_tiles) grid = row_tiles * col_tiles;
+    k<<<grid, THREADS, smem, stream>>>(g, Wb, row_tiles, col_tiles, g.K / 64, S);
+    return cudaGetLastError();
+}
+
+// plain bf16 operands, K % 64 == 0, N % 128 == 0, no A-row gather / scale (callers fall back to gemm_tca otherwise)
+inline bool wss_supported(const GemmArgs<__nv_bfloat16>& g) {
+    static const bool on = [] { const char* e = getenv("LEWIN_NO_WSS_GEMM"); return !(e && e[0] == '1'); }();
+    return on && enabled() && !g.mapA && !g.a_row_scale && !g.aux && !g.mean && g.K % 64 == 0 && g.N % 128 == 0 && g.N <= 4096 &&
+           g.M >= 4 * TC_BM;
+}
+template <int EPI>
+cudaError_t wss_launch(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, int num_sms, cudaStream_t stream) {
+    if (g.N % 256 == 0) return wss_launch_bn<256, EPI>(g, Wb, num_sms, stream);
+    return wss_launch_bn<128, EPI>(g, Wb, num_sms, stream);
+}
+
 
 // Shapes served (everything the C <= 128 levels of the fused block path need); anything else -> caller's fallback.
 //   LN + EPI_BIAS       (q|k|v)   : K = C in {32, 64, 128}, N = 3C

@@ -167,7 +167,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
                     CK(launch_ln_apply(static_cast<const __nv_bfloat16*>(a->x), xhat, a->ln_w, a->ln_b, tokens, C, 1, map, stream));
                     g.A = xhat; g.mapA = 0; g.mean = nullptr; g.rstd = nullptr;
                 }
-                CK((launch_gemm_tca<EPI_BIAS>(g, wqkv_b, stream)));
+                CK(((ws::wss_supported(g) ? ws::wss_launch<EPI_BIAS>(g, wqkv_b, di.sms, stream) : launch_gemm_tca<EPI_BIAS>(g, wqkv_b, stream))));
             } else {
                 CK((launch_gemm_any<T, EPI_BIAS>(g, stream)));
             }
@@ -217,8 +217,8 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
                 CK((ws::launch<EPI_BIAS_RESID>(g, false, di.sms, stream)));
                 done = true;
             } else if (async_gemm) {
-                if (a->windowed) { CK((launch_gemm_tca<EPI_BIAS>(g, wout_b, stream))); }
-                else { g.R = x; g.drop_scale = a->drop_scale; CK((launch_gemm_tca<EPI_BIAS_RESID>(g, wout_b, stream))); }
+                if (a->windowed) { CK(((ws::wss_supported(g) ? ws::wss_launch<EPI_BIAS>(g, wout_b, di.sms, stream) : launch_gemm_tca<EPI_BIAS>(g, wout_b, stream)))); }
+                else { g.R = x; g.drop_scale = a->drop_scale; CK(((ws::wss_supported(g) ? ws::wss_launch<EPI_BIAS_RESID>(g, wout_b, di.sms, stream) : launch_gemm_tca<EPI_BIAS_RESID>(g, wout_b, stream)))); }
                 done = true;
             }
         }
@@ -389,7 +389,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
                     CK(launch_ln_apply(static_cast<const __nv_bfloat16*>(a->y), xhat, a->ln_w, a->ln_b, tokens, C, 0, nomap, stream));
                     g.A = xhat; g.mean = nullptr; g.rstd = nullptr;
                 }
-                CK((launch_gemm_tca<EPI_BIAS_GELU>(g, w1b, stream)));
+                CK(((ws::wss_supported(g) ? ws::wss_launch<EPI_BIAS_GELU>(g, w1b, di.sms, stream) : launch_gemm_tca<EPI_BIAS_GELU>(g, w1b, stream))));
                 done1 = true;
             }
         }
@@ -424,8 +424,8 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
                 CK((ws::launch<EPI_BIAS_RESID>(g, false, di.sms, stream)));
                 done2 = true;
             } else if (async_gemm) {
-                if (a->fused) { g.R = y; g.drop_scale = a->drop_scale; CK((launch_gemm_tca<EPI_BIAS_RESID>(g, w2b, stream))); }
-                else { CK((launch_gemm_tca<EPI_BIAS>(g, w2b, stream))); }
+                if (a->fused) { g.R = y; g.drop_scale = a->drop_scale; CK(((ws::wss_supported(g) ? ws::wss_launch<EPI_BIAS_RESID>(g, w2b, di.sms, stream) : launch_gemm_tca<EPI_BIAS_RESID>(g, w2b, stream)))); }
+                else { CK(((ws::wss_supported(g) ? ws::wss_launch<EPI_BIAS>(g, w2b, di.sms, stream) : launch_gemm_tca<EPI_BIAS>(g, w2b, stream)))); }
                 done2 = true;
             }
         }

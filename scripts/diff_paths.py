@@ -15,10 +15,10 @@ sys.path.insert(0, ROOT)
 
 CASES = [  # (C, nH, B, H, W, shift)
     (32, 1, 1, 24, 24, 0), (32, 1, 3, 64, 64, 4), (64, 2, 2, 40, 24, 4), (64, 2, 1, 64, 64, 0),
-    (128, 4, 2, 32, 32, 4), (128, 4, 1, 24, 40, 0),
+    (128, 4, 2, 32, 32, 4), (128, 4, 1, 24, 40, 0), (256, 8, 2, 32, 32, 4), (512, 16, 3, 16, 16, 4), (256, 8, 1, 24, 24, 0),
 ]
 TIMED = [(32, 1, 16, 128, 128, 4), (64, 2, 16, 128, 128, 4), (64, 2, 16, 64, 64, 4), (128, 4, 16, 64, 64, 4),
-         (128, 4, 16, 32, 32, 4)]
+         (128, 4, 16, 32, 32, 4), (256, 8, 169, 16, 16, 4), (512, 16, 169, 16, 16, 4)]
 
 
 def child(tag, out_dir, timed):

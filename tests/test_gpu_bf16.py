@@ -22,7 +22,8 @@ def _mk(C, nH, shift, p, dev):
 
 
 @pytest.mark.parametrize("C,nH,hw,B,shift", [(32, 1, 16, 2, 0), (32, 1, 16, 2, 4), (64, 2, 32, 1, 4),
-                                             (128, 4, 16, 2, 4), (512, 16, 8, 2, 0)])
+                                             (128, 4, 16, 2, 4), (512, 16, 8, 2, 0),
+                                             (256, 8, 16, 2, 4), (512, 16, 16, 2, 4), (64, 2, 48, 1, 4)])
 def test_block_forward_bf16_matches_bf16_oracle(C, nH, hw, B, shift):
     import lewin_b200 as L
     rng = np.random.default_rng(77 + C + shift)
@@ -87,3 +88,31 @@ def test_autocast_routes_to_bf16_kernels_and_trains():
         a, b = g32[k].flatten(), dict(blk.named_parameters())[k].grad.flatten()
         cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
         assert cos > 0.9, (k, cos)
+
+
+def test_gelu_table_edges_through_leff():
+    """The branch-free GELU pair lookup defers its range test; inputs outside the 2^-28 <= |x| < 16 table (exact zeros,
+    huge and tiny values) must take the exact slow path.  A LeFF whose depthwise kernel is zero makes the dwconv output
+    equal its per-channel bias, so GELU sees exactly the values planted in b_dw."""
+    import lewin_b200 as L
+    dev = torch.device("cuda:0")
+    C, B, hw = 32, 2, 16
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(B, hw * hw, C, generator=g).to(dev).to(torch.bfloat16)
+    planted = torch.tensor([0.0, -0.0, 20.0, -20.0, 1e-10, -1e-10, 3e-5, -3e-5, 15.9, -15.9, 16.0, 1e30, -1e30, 0.5, -0.5, 2.0 ** -28])
+    b_dw = planted.repeat(8)                                   # 128 hidden channels
+    w1 = torch.randn(4 * C, C, generator=g) * 0.2
+    w2 = torch.randn(C, 4 * C, generator=g) * 0.1
+    args = dict(ln_w=torch.ones(C), ln_b=torch.zeros(C), w1=w1, b1=torch.zeros(4 * C), w_dw=torch.zeros(4 * C, 1, 3, 3),
+                b_dw=b_dw, w2=w2, b2=torch.zeros(C))
+    args = {k: v.to(dev) for k, v in args.items()}
+    with torch.no_grad():
+        out = L.ops.lewin_leff(y, B=B, H=hw, W=hw, **args)
+    bb = b_dw.to(dev).to(torch.bfloat16)
+    h2 = torch.nn.functional.gelu(bb.float()).to(torch.bfloat16)          # exact (erf) GELU of the bf16-rounded bias
+    lin = (h2.float() @ w2.to(dev).to(torch.bfloat16).float().t()).to(torch.bfloat16)
+    ref = (y.float() + lin.float()).to(torch.bfloat16)
+    err = (out.float() - ref.float()).abs()
+    tol = 2.0 ** -7 * ref.float().abs().clamp(min=1.0)
+    assert torch.isfinite(out.float()).all()
+    assert (err <= tol).all(), float((err / tol).max())

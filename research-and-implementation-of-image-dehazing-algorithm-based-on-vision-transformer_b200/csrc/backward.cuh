@@ -14,6 +14,8 @@
 #include "gemm_fused.cuh"
 #include "gemm_tc.cuh"
 #include "probsparse_core.cuh"
+#include "wgrad_args.cuh"
+#include "wgrad_bf16.cuh"
 
 namespace lewin {
 
@@ -39,24 +41,7 @@ inline cudaError_t launch_transpose(const float* src, float* dst, int R, int Cc,
     return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------ weight gradient
-template <typename T>
-struct WgradArgs {
-    const T* dY; long long lddy;      // [rows, lddy]; columns [0, N) used
-    const T* X;  long long ldx;       // [rows, ldx];  columns [0, K) used
-    float* dW;                        // [N, K] fp32, accumulated with atomics
-    float* db;                        // [N] or null
-    long long M;
-    int N, K;
-    int mapDY, mapX;                  // operand rows are tokens addressed through `map` (row m is window-ordered)
-    WinMap map;
-    const float* dy_row_scale;        // [B] or null (DropPath factor on dY rows)
-    int tokens_per_image;
-    const float* mean; const float* rstd; const float* ln_w; const float* ln_b;   // LN prologue on X (null mean => none)
-    const T* dy_aux;                  // null, or pre-activation: dY is multiplied by gelu'(aux) (same indexing as dY)
-    long long rows_per_split;         // multiple of 32
-};
-
+// ------------------------------------------------------------------------------ weight gradient (WgradArgs: wgrad_args.cuh)
 constexpr int WG_BM = 32;             // tokens per stage
 constexpr int WG_THREADS = 256;
 
@@ -185,6 +170,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradArgs<T> g)
 
 template <typename T>
 cudaError_t launch_wgrad(WgradArgs<T> g, int num_sms, cudaStream_t st) {
+    if constexpr (Act<T>::kIsBf16) {
+        if (wg2::supported(g)) return wg2::launch(g, num_sms, st);      // pipelined bf16 path (wgrad_bf16.cuh)
+    }
     const int tile = (g.N % 64 == 0 && g.K % 64 == 0) ? 64 : 32;
     const long long tiles = static_cast<long long>(g.N / tile) * (g.K / tile);
     long long want = (static_cast<long long>(num_sms) * 4 + tiles - 1) / tiles;

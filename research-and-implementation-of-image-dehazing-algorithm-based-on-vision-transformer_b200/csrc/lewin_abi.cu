@@ -130,7 +130,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         kt.end(LEWIN_ATTN_K_LNSTATS);
     }
     kt.begin(LEWIN_ATTN_K_CNT);
-    if constexpr (Act<T>::kIsBf16) build_cw_kernel<<<1, 64, 0, stream>>>(a->index_sample, cw);
+    if constexpr (Act<T>::kIsBf16) build_cw_kernel<<<1, 256, 0, stream>>>(a->index_sample, cw);
     else build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
     CK(cudaGetLastError());
     kt.end(LEWIN_ATTN_K_CNT);
@@ -248,7 +248,7 @@ int core_only_fwd(const LewinCoreFwdArgs* a, void* ws, size_t ws_bytes, cudaStre
     if (!aligned16(ws)) return LEWIN_E_ALIGN;
     uint8_t* cnt = static_cast<uint8_t*>(ws);
     __half2* cw = reinterpret_cast<__half2*>(cnt + kTok * kTok);
-    if constexpr (Act<T>::kIsBf16) build_cw_kernel<<<1, 64, 0, stream>>>(a->index_sample, cw);
+    if constexpr (Act<T>::kIsBf16) build_cw_kernel<<<1, 256, 0, stream>>>(a->index_sample, cw);
     else build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
     CK(cudaGetLastError());
     CoreFwdArgs<T> c{};

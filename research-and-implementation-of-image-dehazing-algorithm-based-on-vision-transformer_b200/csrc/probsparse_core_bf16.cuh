@@ -37,15 +37,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }  // namespace pc
 
 // {multiplicity, 0 or -inf} per (query n, key m) as half2, built from index_sample (attn.py:91) next to `cnt`
-__global__ void build_cw_kernel(const int32_t* __restrict__ idx, __half2* __restrict__ cw) {
-    const int n = threadIdx.x;
-    if (n >= kTok) return;
-    uint8_t row[kTok];
-#pragma unroll
-    for (int m = 0; m < kTok; ++m) row[m] = 0;
-    for (int t = 0; t < kSampleK; ++t) row[idx[n * kSampleK + t] & 63]++;
-    for (int m = 0; m < kTok; ++m)
-        cw[n * kTok + m] = __halves2half2(__int2half_rn(row[m]), row[m] ? __float2half(0.f) : __ushort_as_half(0xFC00));
+__global__ void __launch_bounds__(256) build_cw_kernel(const int32_t* __restrict__ idx, __half2* __restrict__ cw) {
+    __shared__ int cnt[kTok * kTok];
+    for (int i = threadIdx.x; i < kTok * kTok; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTok * kSampleK; i += blockDim.x) atomicAdd(&cnt[(i / kSampleK) * kTok + (idx[i] & 63)], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTok * kTok; i += blockDim.x) {
+        const int c = cnt[i];
+        cw[i] = __halves2half2(__int2half_rn(c), c ? __float2half(0.f) : __ushort_as_half(0xFC00));
+    }
 }
 
 constexpr int PC_LD = 40;      // bf16 row stride of q/k/v tiles (80 B: conflict-free ldmatrix)

@@ -14,6 +14,7 @@
 // Algorithmic HBM traffic: read Ch + write Ch per pixel (the halo re-reads hit L2).
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace lewin {
 namespace dws {
@@ -22,7 +23,7 @@ constexpr int TY = 16, TX = 16, SLAB = 64;
 constexpr int HY = TY + 2, HX = TX + 2;
 constexpr int TILE_BYTES = HY * HX * SLAB * 2;            // 41472
 constexpr int THREADS = 256;
-constexpr size_t SMEM = 2 * TILE_BYTES + kGelu2TabSize * 2;
+constexpr size_t SMEM = 128 /*align*/ + 2 * TILE_BYTES + kGelu2TabSize * 2 + 64 /*mbarriers*/;
 
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
     unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
@@ -45,9 +46,14 @@ struct Args {
     int tiles_x, tiles_y, spatial_tiles, total_tiles;
 };
 
-__global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+// USE_TMA: the halo tile is ONE cp.async.bulk.tensor box per tile (issued by thread 0, zero-filled outside the map by
+// the TMA unit, completion on an mbarrier) instead of 2592 per-thread 16-byte cp.async with their index arithmetic.
+template <bool USE_TMA>
+__global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a, const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
     uint16_t* gtab = reinterpret_cast<uint16_t*>(smem + 2 * TILE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TILE_BYTES + kGelu2TabSize * 2);
     const uint32_t smem_u = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
     const int tid = threadIdx.x;
     const int cq = tid & 15, px = tid >> 4;                // 4-channel group, pixel column
@@ -62,6 +68,13 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a)
     auto fetch = [&](int t, int bufi) {
         int slab, b, ty, tx;
         decode(t, slab, b, ty, tx);
+        if constexpr (USE_TMA) {
+            if (tid == 0) {
+                tma::mbar_expect_tx(&bars[bufi], TILE_BYTES);
+                tma::load_4d(smem + bufi * TILE_BYTES, &xmap, &bars[bufi], slab * SLAB, tx * TX - 1, ty * TY - 1, b);
+            }
+            return;
+        }
         const int y0 = ty * TY - 1, x0 = tx * TX - 1;
         const __nv_bfloat16* src0 = a.x + static_cast<long long>(b) * a.H * a.W * a.Ch + slab * SLAB;
         const uint32_t dst0 = smem_u + bufi * TILE_BYTES;
@@ -74,14 +87,25 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a)
         }
     };
 
+    if constexpr (USE_TMA) {
+        if (tid == 0) {
+            tma::prefetch_map(&xmap);
+            tma::mbar_init(&bars[0], 1);
+            tma::mbar_init(&bars[1], 1);
+            tma::fence_barrier_init();
+        }
+        __syncthreads();
+    }
     int t = blockIdx.x;
     if (t < a.total_tiles) fetch(t, 0);
     cp_async_commit();
     gelu_tab2_to_smem(gtab, tid, THREADS);
+    uint32_t bphase[2] = {0u, 0u};
 
     float2 wk[9][2];                                       // taps x channel pairs (autocast: bf16-rounded weights)
     float2 bz[2];
     int cur_slab = -1;
+    bool cur_slab_first = true;
     int bufi = 0;
     for (; t < a.total_tiles; t += gridDim.x, bufi ^= 1) {
         const int tn = t + gridDim.x;
@@ -101,8 +125,14 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a)
             bz[0] = make_float2(Act<__nv_bfloat16>::round(b4.x), Act<__nv_bfloat16>::round(b4.y));
             bz[1] = make_float2(Act<__nv_bfloat16>::round(b4.z), Act<__nv_bfloat16>::round(b4.w));
         }
-        cp_async_wait<1>();                                // this tile's halo has landed (the next one may still fly)
-        __syncthreads();
+        if constexpr (USE_TMA) {
+            tma::mbar_wait(&bars[bufi], bphase[bufi]);         // this tile's box has landed (async proxy -> visible after the wait)
+            bphase[bufi] ^= 1u;
+            if (cur_slab_first) { __syncthreads(); cur_slab_first = false; }   // GELU table staged by all threads
+        } else {
+            cp_async_wait<1>();                            // this tile's halo has landed (the next one may still fly)
+            __syncthreads();
+        }
 
         const unsigned char* tile = smem + bufi * TILE_BYTES + cq * 8;
         auto ldrow = [&](float2 (&dst)[3][2], int hy) {    // 3 columns x 4 channels of halo row hy
@@ -157,11 +187,19 @@ inline cudaError_t launch(const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloa
     a.tiles_x = W / TX; a.tiles_y = H / TY;
     a.spatial_tiles = B * a.tiles_x * a.tiles_y;
     a.total_tiles = a.spatial_tiles * (Ch / SLAB);
-    cudaError_t e = cudaFuncSetAttribute(dwconv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM));
-    if (e != cudaSuccess) return e;
     int grid = 2 * num_sms;
     if (grid > a.total_tiles) grid = a.total_tiles;
-    dwconv_stream_kernel<<<grid, THREADS, SMEM, stream>>>(a);
+    static const bool tma_on = [] { const char* e = getenv("LEWIN_NO_TMA"); return !(e && e[0] == '1'); }();
+    CUtensorMap map{};
+    if (tma_on && tma::make_nhwc_bf16(&map, x, B, H, W, Ch, HY, HX, SLAB)) {
+        cudaError_t e = cudaFuncSetAttribute(dwconv_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM));
+        if (e != cudaSuccess) return e;
+        dwconv_stream_kernel<true><<<grid, THREADS, SMEM, stream>>>(a, map);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(dwconv_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM));
+        if (e != cudaSuccess) return e;
+        dwconv_stream_kernel<false><<<grid, THREADS, SMEM, stream>>>(a, map);
+    }
     return cudaGetLastError();
 }
 

@@ -21,6 +21,7 @@
 // every hand-over is an mbarrier, there is no __syncthreads in the steady state.
 #pragma once
 #include "gemm_tc.cuh"
+#include "tma.cuh"
 
 namespace lewin {
 namespace ws {
@@ -79,13 +80,14 @@ constexpr size_t fixed_smem() {
 
 // One warp's share of one output tile: wait for the accumulator, tcgen05.ld 32-column chunks (thread == TMEM lane == tile
 // row), bias / GELU / residual, stage, row-cooperative coalesced stores.  Shared by the resident-W and streamed-W kernels.
-template <int BN, int EPI, int NCG>
+template <int BN, int EPI, int NCG, int NBUF = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, uint32_t tmem_d, int acc, uint32_t aph, uint32_t tile,
                                               int n0, const float* s_bias, const uint16_t* gtab, unsigned char* my_stg,
                                               uint64_t* tfull, uint64_t* tempty, int lg, int half, int lane) {
     using T = __nv_bfloat16;
     constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     constexpr int NCH = BN / 32;
+    static_assert(NBUF == 2 || EPI != EPI_BIAS_RESID, "the residual prefetch uses two staging buffers");
         const uint32_t m = tile * TC_BM + lg * 32 + lane;
         long long oy = -1;
         float sc = 1.f;
@@ -118,7 +120,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
                 tc::tc_fence_before();
                 mbar_arrive(&tempty[acc]);
             }
-            unsigned char* sb = my_stg + (q & 1) * STG_BUF;
+            unsigned char* sb = my_stg + (NBUF == 2 ? (q & 1) : 0) * STG_BUF;
             unsigned char* srow = sb + lane * STG_ROW;
             const float2* bs2 = reinterpret_cast<const float2*>(s_bias + c * 32);
 #pragma unroll
@@ -505,17 +507,28 @@ cudaError_t launch_inst(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaStrea
 // ring stage carries one k-chunk of BOTH operands (A[128 x 64] + W[BN x 64], plain bf16 in global memory: weights
 // pre-converted by convert_w_kernel, LayerNorm pre-applied by ln_apply_kernel).  Same three roles and the same
 // epilogue as above; tiles are walked column-fastest so that the CTAs working on one row band share its A rows in L2.
-template <int BN, int EPI>
-constexpr size_t wss_fixed_smem(int N) {
-    return 1024 + 8 * 2 * STG_BUF + static_cast<size_t>(N) * 4 + (2 * 8 + 4) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGelu2TabSize * 2 : 0);
-}
+template <int EPI> struct WssCfg {
+    static constexpr int NEW = (EPI == EPI_BIAS_RESID) ? 8 : 16;     // epilogue warps (the residual prefetch needs 2 staging buffers)
+    static constexpr int NBUF = (EPI == EPI_BIAS_RESID) ? 2 : 1;
+    static constexpr int THREADS = (NEW + 2) * 32;                   // + MMA warp + TMA warp
+};
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(THREADS, 1) gemm_wss_kernel(const GemmArgs<__nv_bfloat16> g, const __nv_bfloat16* __restrict__ Wb,
-                                                              int row_tiles, int col_tiles, int nkc, int S) {
+constexpr size_t wss_fixed_smem(int N) {
+    return 1024 + WssCfg<EPI>::NEW * WssCfg<EPI>::NBUF * STG_BUF + static_cast<size_t>(N) * 4 + (2 * 8 + 4) * 8 + 16 +
+           (EPI == EPI_BIAS_GELU ? kGelu2TabSize * 2 : 0);
+}
+
+// Both operands arrive by TMA (one elected thread, 2 boxes per stage, SWIZZLE_128B = the UMMA layout, zero fill for the
+// M tail), so no warp spends issue slots on loads: 16 epilogue warps (4 column groups) for the bias / GELU epilogues.
+template <int BN, int EPI>
+__global__ void __launch_bounds__(WssCfg<EPI>::THREADS, 1) gemm_wss_kernel(const GemmArgs<__nv_bfloat16> g, const __grid_constant__ CUtensorMap amap,
+                                                                         const __grid_constant__ CUtensorMap wmap,
+                                                                         int row_tiles, int col_tiles, int nkc, int S) {
     using T = __nv_bfloat16;
-    constexpr int NEW = 8, NPW = 8, MMA_WARP = NEW, NCG = NEW / 4;
-    constexpr int KC = 64, CPR = 8;
+    constexpr int NEW = WssCfg<EPI>::NEW, NBUF = WssCfg<EPI>::NBUF, THREADS_ = WssCfg<EPI>::THREADS;
+    constexpr int MMA_WARP = NEW, TMA_WARP = NEW + 1, NCG = NEW / 4;
+    constexpr int KC = 64;
     constexpr int A_CHUNK = TC_BM * KC * 2, W_CHUNK = BN * KC * 2, STAGE = A_CHUNK + W_CHUNK;
     constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     constexpr int TMEM_COLS = 2 * ACC;
@@ -524,8 +537,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wss_kernel(const GemmArgs<__n
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* ring = base;                                     // [S][A_CHUNK | W_CHUNK]
-    unsigned char* stg = ring + static_cast<size_t>(S) * STAGE;     // [NEW][2][STG_BUF]
-    float* s_bias = reinterpret_cast<float*>(stg + NEW * 2 * STG_BUF);          // [N] (all column tiles)
+    unsigned char* stg = ring + static_cast<size_t>(S) * STAGE;     // [NEW][NBUF][STG_BUF]
+    float* s_bias = reinterpret_cast<float*>(stg + NEW * NBUF * STG_BUF);       // [N] (all column tiles)
     uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + g.N);
     uint64_t* empty = full + 8;
     uint64_t* tfull = empty + 8;
@@ -537,12 +550,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wss_kernel(const GemmArgs<__n
     const int total_tiles = row_tiles * col_tiles;
     const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
-    for (int i = tid; i < g.N; i += THREADS) s_bias[i] = g.bias ? Act<T>::round(g.bias[i]) : 0.f;
-    if (EPI == EPI_BIAS_GELU) gelu_tab2_to_smem(gtab, tid, THREADS);
+    for (int i = tid; i < g.N; i += THREADS_) s_bias[i] = g.bias ? Act<T>::round(g.bias[i]) : 0.f;
+    if (EPI == EPI_BIAS_GELU) gelu_tab2_to_smem(gtab, tid, THREADS_);
     if (tid == 0) {
-        for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], NPW * 32); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], NEW * 32); }
         tc::fence_barrier_init();
+        tma::prefetch_map(&amap);
+        tma::prefetch_map(&wmap);
     }
     if (warp == MMA_WARP) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
     tc::tc_fence_before();
@@ -550,46 +565,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wss_kernel(const GemmArgs<__n
     tc::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp > MMA_WARP) {
-        // ============================================================ producers: cp.async both operands, DD stages ahead
-        const int pt = tid - (MMA_WARP + 1) * 32;                  // 0..255
-        const int DD = S - 1 < 4 ? S - 1 : 4;
-        const uint32_t ring_u = tc::smem_u32(ring);
-        const int total = my_tiles * nkc;
-        int l_kc = 0;
-        int l_tile = blockIdx.x;
-        int i_s = 0;
-        uint32_t i_ph = 0;
-        auto issue = [&](int j) {
-            if (j < total) {
-                tc::mbar_wait(&empty[i_s], i_ph ^ 1u);
-                const int rt = l_tile / col_tiles, ct = l_tile - rt * col_tiles;
-                const uint32_t dst = ring_u + i_s * STAGE;
-#pragma unroll
-                for (int i = 0; i < TC_BM * CPR / 256; ++i) {
-                    const int c = pt + i * 256, r = c >> 3, ch = c & 7;
-                    const long long m = static_cast<long long>(rt) * TC_BM + r;
-                    const bool ok = m < g.M;
-                    cp_async16_z(dst + tc::swz_off<64>(r, ch), g.A + (ok ? m : 0) * g.lda + l_kc * KC + ch * 8, ok);
+    if (warp == TMA_WARP) {
+        // ============================================================ producer: one thread, two TMA boxes per stage
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
+                const int rt = t / col_tiles, ct = t - rt * col_tiles;
+                for (int kc = 0; kc < nkc; ++kc) {
+                    tc::mbar_wait(&empty[s], ph ^ 1u);
+                    tma::mbar_expect_tx(&full[s], STAGE);
+                    tma::load_2d(ring + s * STAGE, &amap, &full[s], kc * KC, rt * TC_BM);
+                    tma::load_2d(ring + s * STAGE + A_CHUNK, &wmap, &full[s], kc * KC, ct * BN);
+                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
-#pragma unroll
-                for (int i = 0; i < BN * CPR / 256; ++i) {
-                    const int c = pt + i * 256, r = c >> 3, ch = c & 7;
-                    cp_async16_z(dst + A_CHUNK + tc::swz_off<64>(r, ch), Wb + static_cast<long long>(ct * BN + r) * g.K + l_kc * KC + ch * 8, true);
-                }
-                if (++l_kc == nkc) { l_kc = 0; l_tile += gridDim.x; }
-                if (++i_s == S) { i_s = 0; i_ph ^= 1u; }
             }
-            cp_async_commit();
-        };
-        for (int d = 0; d < DD; ++d) issue(d);
-        int c_s = 0;
-        for (int j = 0; j < total; ++j) {
-            issue(j + DD);
-            if (DD == 4) cp_async_wait<4>(); else if (DD == 3) cp_async_wait<3>(); else if (DD == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-            tc::fence_proxy_async();
-            mbar_arrive(&full[c_s]);
-            if (++c_s == S) c_s = 0;
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
@@ -617,12 +608,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_wss_kernel(const GemmArgs<__n
         }
     } else {
         const int lg = warp & 3, half = warp >> 2;
-        unsigned char* my_stg = stg + warp * 2 * STG_BUF;
+        unsigned char* my_stg = stg + warp * NBUF * STG_BUF;
         for (int it = 0; it < my_tiles; ++it) {
             const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
             const int rt = t / col_tiles, ct = t - rt * col_tiles;
-            epilogue_tile<BN, EPI, NCG>(g, tmem_d, it & 1, static_cast<uint32_t>(it >> 1) & 1u, static_cast<uint32_t>(rt), ct * BN,
-                                        s_bias + ct * BN, gtab, my_stg, tfull, tempty, lg, half, lane);
+            epilogue_tile<BN, EPI, NCG, NBUF>(g, tmem_d, it & 1, static_cast<uint32_t>(it >> 1) & 1u, static_cast<uint32_t>(rt), ct * BN,
+                                              s_bias + ct * BN, gtab, my_stg, tfull, tempty, lg, half, lane);
         }
     }
     tc::tc_fence_before();
@@ -638,6 +629,9 @@ cudaError_t wss_launch_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16*
     int S = static_cast<int>((SMEM_MAX - fixed) / STAGE);
     if (S > 8) S = 8;
     const size_t smem = fixed + static_cast<size_t>(S) * STAGE;
+    CUtensorMap amap{}, wmap{};
+    if (!tma::make_2d_bf16_sw128(&amap, g.A, g.M, g.K, g.lda, TC_BM) || !tma::make_2d_bf16_sw128(&wmap, Wb, g.N, g.K, g.K, BN))
+        return cudaErrorNotSupported;
     auto k = gemm_wss_kernel<BN, EPI>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -645,7 +639,7 @@ cudaError_t wss_launch_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16*
     const int col_tiles = g.N / BN;
     int grid = num_sms;
     if (grid > row_tiles * col_tiles) grid = row_tiles * col_tiles;
-    k<<<grid, THREADS, smem, stream>>>(g, Wb, row_tiles, col_tiles, g.K / 64, S);
+    k<<<grid, WssCfg<EPI>::THREADS, smem, stream>>>(g, amap, wmap, row_tiles, col_tiles, g.K / 64, S);
     return cudaGetLastError();
 }
 
@@ -653,7 +647,7 @@ cudaError_t wss_launch_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16*
 inline bool wss_supported(const GemmArgs<__nv_bfloat16>& g) {
     static const bool on = [] { const char* e = getenv("LEWIN_NO_WSS_GEMM"); return !(e && e[0] == '1'); }();
     return on && enabled() && !g.mapA && !g.a_row_scale && !g.aux && !g.mean && g.K % 64 == 0 && g.N % 128 == 0 && g.N <= 4096 &&
-           g.M >= 4 * TC_BM;
+           g.M >= 4 * TC_BM && (g.lda % 8) == 0 && tma::encode_fn() != nullptr;
 }
 template <int EPI>
 cudaError_t wss_launch(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, int num_sms, cudaStream_t stream) {

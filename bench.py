@@ -343,16 +343,20 @@ def main():
                             frac=ach / peak))
     dom = kernels[0]
     traffic = None
+    traffic_note = None
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.isfile(tpath):
         try:
             tj = json.load(open(tpath))
-            if tj.get("kernel") == dom["kernel"] and tj.get("dtype") == args.dtype:
-                traffic = tj.get("dram_bytes_per_launch")
+            ent = tj.get("kernels", {}).get(dom["kernel"])
+            if ent and tj.get("dtype") == args.dtype:
+                traffic = ent.get("dram_bytes_per_launch")
+                traffic_note = (f"ncu DRAM bytes of ONE launch ({tj.get('shape')}; {ent.get('ncu_kernel')}); algorithmic bytes of that "
+                                f"launch = {ent.get('algorithmic_bytes_per_launch')}; {tj.get('source')}")
         except Exception:
             pass
     roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
-                    traffic=traffic, kernel=dom["kernel"], peak_source=peaks["source"],
+                    traffic=traffic, traffic_note=traffic_note, kernel=dom["kernel"], peak_source=peaks["source"],
                     note="aggregate over the launches of this kernel type in one step (all 18 blocks), CUDA events via ABI timing hook")
 
     blocks = block_microbench(dev, args.dtype) if world == 1 else None

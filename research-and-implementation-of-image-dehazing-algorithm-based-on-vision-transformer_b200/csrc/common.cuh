@@ -148,6 +148,7 @@ __device__ uint16_t g_gelu_grad_tab[kGeluTabSize];     // bf16(gelu'(x)) on the 
 constexpr int kGelu2TabSize = 8192;
 constexpr uint32_t kGelu2Base = 99u << 7;              // bf16 bits of 2^-28
 __device__ uint16_t g_gelu_tab2[kGelu2TabSize];
+__device__ uint16_t g_gelu_grad_tab2[kGelu2TabSize];   // bf16(gelu'(x)) on the same index space (backward)
 
 __global__ void gelu_tab_init_kernel() {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,6 +156,7 @@ __global__ void gelu_tab_init_kernel() {
         const uint32_t sign2 = (i >> 12) & 1, em = kGelu2Base + (i & 4095);
         const float x2 = __uint_as_float((sign2 << 31) | (em << 16));
         g_gelu_tab2[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf(x2)));
+        g_gelu_grad_tab2[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf_grad(x2)));
     }
     if (i >= kGeluTabSize) return;
     const uint32_t sign = (i >> 11) & 1, e = 115 + ((i >> 7) & 15), m = i & 127;
@@ -197,6 +199,25 @@ __device__ __forceinline__ uint32_t gelu_pair_fast(const uint16_t* __restrict__ 
 }
 // true if any element accumulated into `oor` by gelu_pair_fast was outside the table
 __device__ __forceinline__ bool gelu_pair_oor(uint32_t oor) { return (oor & 0xF000F000u) != 0u; }
+__device__ __forceinline__ void gelu_grad_tab2_to_smem(uint16_t* dst, int tid, int nthreads) {
+    for (int i = tid; i < kGelu2TabSize / 8; i += nthreads)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(g_gelu_grad_tab2)[i];
+}
+// gelu'(x) of a packed bf16 pair as packed bf16 bits; outside the table: 0.5 (tiny), 1 or 0 (huge, by sign)
+__device__ __noinline__ uint32_t gelu_grad_pair_exact(const uint16_t* __restrict__ tab2g, uint32_t in2) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t u = (in2 >> (16 * h)) & 0xFFFFu;
+        const uint32_t r = (u & 0x7FFFu) - kGelu2Base;
+        uint32_t v;
+        if (r < 4096u) v = tab2g[r | ((u >> 3) & 0x1000u)];
+        else if (static_cast<int32_t>(r) < 0) v = 0x3F00u;
+        else v = (u & 0x8000u) ? 0u : 0x3F80u;
+        out |= v << (16 * h);
+    }
+    return out;
+}
 // exact for every bf16 input (table inside 2^-28 <= |x| < 16, closed forms outside: 0.5 x, x or -0)
 __device__ __noinline__ uint32_t gelu_pair_exact(const uint16_t* __restrict__ tab2, uint32_t in2) {
     uint32_t out = 0;

@@ -8,6 +8,7 @@
 // per output instead of 9).  HBM-bound: algorithmic traffic = read Ch + write Ch per pixel.
 #pragma once
 #include "common.cuh"
+#include "dwconv_stream.cuh"
 
 namespace lewin {
 
@@ -460,8 +461,18 @@ bool launch_dwconv_bwd_tiled(const T* g2, const T* a2, const T* h1, const T* a1,
     if (W % 16 == 0) {
         const unsigned grid = static_cast<unsigned>(B) * (H / 8) * (W / 16) * slabs;
         constexpr int smem16 = 2 * 10 * 18 * 128 + 9 * SLAB * 4 + kGeluTabSize * 2;
-        cudaFuncSetAttribute(dwconv_bwd_data_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16);
-        dwconv_bwd_data_kernel<T, 16><<<grid, 256, smem16, st>>>(g2, a2, a1, da1, da2_scratch, w, B, H, W, Ch);
+        bool fast = false;
+        if constexpr (Act<T>::kIsBf16) {
+            if (dws::bwd_enabled() && dws::supported(H, W, Ch)) {      // element-wise dGELU + streaming TMA kernel (dwconv_stream.cuh)
+                *err = dws::launch_bwd_data(g2, a2, a1, da1, da2_scratch, w, B, H, W, Ch, num_sms, st);
+                if (*err != cudaSuccess) return true;
+                fast = true;
+            }
+        }
+        if (!fast) {
+            cudaFuncSetAttribute(dwconv_bwd_data_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16);
+            dwconv_bwd_data_kernel<T, 16><<<grid, 256, smem16, st>>>(g2, a2, a1, da1, da2_scratch, w, B, H, W, Ch);
+        }
         const int ntiles = B * (H / 8) * (W / 16);
         int gx = (2 * num_sms + slabs - 1) / slabs; if (gx > ntiles) gx = ntiles;
         dwconv_bwd_wgrad_kernel<T, 16><<<dim3(gx, slabs), 256, 0, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);

@@ -40,6 +40,7 @@ struct Args {
     const __nv_bfloat16* x;      // [B, H, W, Ch]
     __nv_bfloat16* out;          // [B, H, W, Ch]
     __nv_bfloat16* preact;       // optional pre-GELU copy (training), may be null
+    const __nv_bfloat16* aux;    // BWD mode: a1 (pre-GELU linear1 output), da1 = conv^T(da2) * gelu'(a1)
     const float* w;              // [Ch, 9]
     const float* bias;           // [Ch]
     int B, H, W, Ch;
@@ -48,7 +49,9 @@ struct Args {
 
 // USE_TMA: the halo tile is ONE cp.async.bulk.tensor box per tile (issued by thread 0, zero-filled outside the map by
 // the TMA unit, completion on an mbarrier) instead of 2592 per-thread 16-byte cp.async with their index arithmetic.
-template <bool USE_TMA>
+// BWD: the same pipeline computes the data gradient of the depthwise conv: x = da2, taps flipped, no bias, and the
+// epilogue multiplies by gelu'(a1) instead of applying GELU (da1 = conv^T(da2) * gelu'(a1), autograd of :508-517).
+template <bool USE_TMA, bool BWD = false>
 __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((128u - (tma::smem_u32(smem_raw) & 127u)) & 127u);
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a,
     int t = blockIdx.x;
     if (t < a.total_tiles) fetch(t, 0);
     cp_async_commit();
-    gelu_tab2_to_smem(gtab, tid, THREADS);
+    if constexpr (BWD) gelu_grad_tab2_to_smem(gtab, tid, THREADS); else gelu_tab2_to_smem(gtab, tid, THREADS);
     uint32_t bphase[2] = {0u, 0u};
 
     float2 wk[9][2];                                       // taps x channel pairs (autocast: bf16-rounded weights)
@@ -121,9 +124,13 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a,
                 wk[k][0] = make_float2(Act<__nv_bfloat16>::round(__ldg(a.w + (c + 0) * 9 + k)), Act<__nv_bfloat16>::round(__ldg(a.w + (c + 1) * 9 + k)));
                 wk[k][1] = make_float2(Act<__nv_bfloat16>::round(__ldg(a.w + (c + 2) * 9 + k)), Act<__nv_bfloat16>::round(__ldg(a.w + (c + 3) * 9 + k)));
             }
-            const float4 b4 = *reinterpret_cast<const float4*>(a.bias + c);
-            bz[0] = make_float2(Act<__nv_bfloat16>::round(b4.x), Act<__nv_bfloat16>::round(b4.y));
-            bz[1] = make_float2(Act<__nv_bfloat16>::round(b4.z), Act<__nv_bfloat16>::round(b4.w));
+            if constexpr (BWD) {
+                bz[0] = make_float2(0.f, 0.f); bz[1] = bz[0];
+            } else {
+                const float4 b4 = *reinterpret_cast<const float4*>(a.bias + c);
+                bz[0] = make_float2(Act<__nv_bfloat16>::round(b4.x), Act<__nv_bfloat16>::round(b4.y));
+                bz[1] = make_float2(Act<__nv_bfloat16>::round(b4.z), Act<__nv_bfloat16>::round(b4.w));
+            }
         }
         if constexpr (USE_TMA) {
             tma::mbar_wait(&bars[bufi], bphase[bufi]);         // this tile's box has landed (async proxy -> visible after the wait)
@@ -150,25 +157,46 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a,
         const long long rstride = static_cast<long long>(a.W) * a.Ch;
         __nv_bfloat16* op = a.out + obase;
         __nv_bfloat16* pp = a.preact ? a.preact + obase : nullptr;
+        const __nv_bfloat16* ap = BWD ? a.aux + obase : nullptr;
 #pragma unroll
         for (int y = 0; y < TY; ++y) {
             ldrow(win[(y + 2) % 3], y + 2);
             float2 acc0 = bz[0], acc1 = bz[1];
+            if constexpr (BWD) {
+                // dh1[y,x] = sum_{ky,kx} da2[y - ky + 1, x - kx + 1] * w[ky,kx]  (same summation order as dwconv_bwd_data_kernel)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    ffma2(acc0, win[(y + ky) % 3][kx][0], wk[ky * 3 + kx][0]);
-                    ffma2(acc1, win[(y + ky) % 3][kx][1], wk[ky * 3 + kx][1]);
-                }
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc0.x, acc0.y), h1 = __floats2bfloat162_rn(acc1.x, acc1.y);
-            const uint32_t in0 = *reinterpret_cast<uint32_t*>(&h0), in1 = *reinterpret_cast<uint32_t*>(&h1);
-            uint32_t oor = 0;
-            uint32_t q0 = gelu_pair_fast(gtab, in0, oor), q1 = gelu_pair_fast(gtab, in1, oor);
-            if (__builtin_expect(gelu_pair_oor(oor), 0)) { q0 = gelu_pair_exact(gtab, in0); q1 = gelu_pair_exact(gtab, in1); }
-            if (pp) { *reinterpret_cast<uint2*>(pp) = make_uint2(in0, in1); pp += rstride; }
-            *reinterpret_cast<uint2*>(op) = make_uint2(q0, q1);
-            op += rstride;
+                    for (int kx = 0; kx < 3; ++kx) {
+                        ffma2(acc0, win[(y + 2 - ky) % 3][2 - kx][0], wk[ky * 3 + kx][0]);
+                        ffma2(acc1, win[(y + 2 - ky) % 3][2 - kx][1], wk[ky * 3 + kx][1]);
+                    }
+                const uint2 pa = *reinterpret_cast<const uint2*>(ap);
+                ap += rstride;
+                uint32_t oor = 0;
+                uint32_t g0 = gelu_pair_fast(gtab, pa.x, oor), g1 = gelu_pair_fast(gtab, pa.y, oor);     // gtab holds gelu' here
+                if (__builtin_expect(gelu_pair_oor(oor), 0)) { g0 = gelu_grad_pair_exact(gtab, pa.x); g1 = gelu_grad_pair_exact(gtab, pa.y); }
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(acc0.x * __uint_as_float(g0 << 16), acc0.y * __uint_as_float(g0 & 0xFFFF0000u));
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(acc1.x * __uint_as_float(g1 << 16), acc1.y * __uint_as_float(g1 & 0xFFFF0000u));
+                *reinterpret_cast<uint2*>(op) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                op += rstride;
+            } else {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        ffma2(acc0, win[(y + ky) % 3][kx][0], wk[ky * 3 + kx][0]);
+                        ffma2(acc1, win[(y + ky) % 3][kx][1], wk[ky * 3 + kx][1]);
+                    }
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(acc0.x, acc0.y), h1 = __floats2bfloat162_rn(acc1.x, acc1.y);
+                const uint32_t in0 = *reinterpret_cast<uint32_t*>(&h0), in1 = *reinterpret_cast<uint32_t*>(&h1);
+                uint32_t oor = 0;
+                uint32_t q0 = gelu_pair_fast(gtab, in0, oor), q1 = gelu_pair_fast(gtab, in1, oor);
+                if (__builtin_expect(gelu_pair_oor(oor), 0)) { q0 = gelu_pair_exact(gtab, in0); q1 = gelu_pair_exact(gtab, in1); }
+                if (pp) { *reinterpret_cast<uint2*>(pp) = make_uint2(in0, in1); pp += rstride; }
+                *reinterpret_cast<uint2*>(op) = make_uint2(q0, q1);
+                op += rstride;
+            }
         }
         __syncthreads();                                   // every thread is done with this buffer before it is refilled
     }
@@ -179,10 +207,11 @@ inline bool supported(int H, int W, int Ch) {
     return on && H % TY == 0 && W % TX == 0 && Ch % SLAB == 0;
 }
 
-inline cudaError_t launch(const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloat16* preact, const float* w, const float* bias,
-                          int B, int H, int W, int Ch, int num_sms, cudaStream_t stream) {
+template <bool BWD>
+inline cudaError_t launch_mode(const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloat16* preact, const __nv_bfloat16* aux, const float* w,
+                               const float* bias, int B, int H, int W, int Ch, int num_sms, cudaStream_t stream) {
     Args a{};
-    a.x = x; a.out = out; a.preact = preact; a.w = w; a.bias = bias;
+    a.x = x; a.out = out; a.preact = preact; a.aux = aux; a.w = w; a.bias = bias;
     a.B = B; a.H = H; a.W = W; a.Ch = Ch;
     a.tiles_x = W / TX; a.tiles_y = H / TY;
     a.spatial_tiles = B * a.tiles_x * a.tiles_y;
@@ -192,15 +221,63 @@ inline cudaError_t launch(const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloa
     static const bool tma_on = [] { const char* e = getenv("LEWIN_NO_TMA"); return !(e && e[0] == '1'); }();
     CUtensorMap map{};
     if (tma_on && tma::make_nhwc_bf16(&map, x, B, H, W, Ch, HY, HX, SLAB)) {
-        cudaError_t e = cudaFuncSetAttribute(dwconv_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM));
+        cudaError_t e = cudaFuncSetAttribute(dwconv_stream_kernel<true, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM));
         if (e != cudaSuccess) return e;
-        dwconv_stream_kernel<true><<<grid, THREADS, SMEM, stream>>>(a, map);
+        dwconv_stream_kernel<true, BWD><<<grid, THREADS, SMEM, stream>>>(a, map);
     } else {
-        cudaError_t e = cudaFuncSetAttribute(dwconv_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM));
+        cudaError_t e = cudaFuncSetAttribute(dwconv_stream_kernel<false, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM));
         if (e != cudaSuccess) return e;
-        dwconv_stream_kernel<false><<<grid, THREADS, SMEM, stream>>>(a, map);
+        dwconv_stream_kernel<false, BWD><<<grid, THREADS, SMEM, stream>>>(a, map);
     }
     return cudaGetLastError();
+}
+
+inline cudaError_t launch(const __nv_bfloat16* x, __nv_bfloat16* out, __nv_bfloat16* preact, const float* w, const float* bias,
+                          int B, int H, int W, int Ch, int num_sms, cudaStream_t stream) {
+    return launch_mode<false>(x, out, preact, nullptr, w, bias, B, H, W, Ch, num_sms, stream);
+}
+
+// ---- backward, data path:  da2 = g2 * gelu'(a2) (element-wise, also the weight-gradient kernel's input), then
+//      da1 = conv^T(da2) * gelu'(a1) on the streaming kernel above
+__global__ void __launch_bounds__(256) dgelu_mul_kernel(const __nv_bfloat16* __restrict__ g2, const __nv_bfloat16* __restrict__ a2,
+                                                        __nv_bfloat16* __restrict__ da2, long long n8) {
+    __shared__ __align__(16) uint16_t gtab[kGelu2TabSize];
+    gelu_grad_tab2_to_smem(gtab, threadIdx.x, 256);
+    __syncthreads();
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += static_cast<long long>(gridDim.x) * 256) {
+        const uint4 g = reinterpret_cast<const uint4*>(g2)[i];
+        const uint4 p = reinterpret_cast<const uint4*>(a2)[i];
+        const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, pw[4] = {p.x, p.y, p.z, p.w};
+        uint32_t o[4], oor = 0, d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = gelu_pair_fast(gtab, pw[j], oor);
+        if (__builtin_expect(gelu_pair_oor(oor), 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = gelu_grad_pair_exact(gtab, pw[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(gw[j] << 16) * __uint_as_float(d[j] << 16),
+                                                     __uint_as_float(gw[j] & 0xFFFF0000u) * __uint_as_float(d[j] & 0xFFFF0000u));
+            o[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        reinterpret_cast<uint4*>(da2)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+inline bool bwd_enabled() {
+    static const bool on = [] { const char* e = getenv("LEWIN_NO_BWD2"); return !(e && e[0] == '1'); }();
+    return on;
+}
+inline cudaError_t launch_bwd_data(const __nv_bfloat16* g2, const __nv_bfloat16* a2, const __nv_bfloat16* a1, __nv_bfloat16* da1,
+                                   __nv_bfloat16* da2, const float* w, int B, int H, int W, int Ch, int num_sms, cudaStream_t stream) {
+    const long long n8 = static_cast<long long>(B) * H * W * Ch / 8;
+    long long grid = static_cast<long long>(num_sms) * 8;
+    if (grid > (n8 + 255) / 256) grid = (n8 + 255) / 256;
+    dgelu_mul_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(g2, a2, da2, n8);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_mode<true>(da2, da1, nullptr, a1, w, nullptr, B, H, W, Ch, num_sms, stream);
 }
 
 }  // namespace dws

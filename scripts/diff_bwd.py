@@ -63,7 +63,7 @@ def main():
     import torch
     out_dir = "/tmp/diff_bwd"
     os.makedirs(out_dir, exist_ok=True)
-    variants = {"old": {"LEWIN_NO_WGRAD2": "1", "LEWIN_NO_BWD2": "1"}, "new": {}}
+    variants = {"old": {"LEWIN_NO_BWD2": "1"}, "new": {}}
     for tag, envx in variants.items():
         r = subprocess.run([sys.executable, __file__, "--child", tag, out_dir], env=dict(os.environ, **envx), timeout=300,
                            capture_output=True, text=True)

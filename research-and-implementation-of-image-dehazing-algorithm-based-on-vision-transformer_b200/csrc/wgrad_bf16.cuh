@@ -31,20 +31,28 @@ struct Smem {
     float mu[2][TOK], rs[2][TOK], sc[2][TOK];
 };
 
-template <int NT, int KT>
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], const void* p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+
+// WARPS_N warps along n (dW rows), 8 / WARPS_N along k: 4 x 2 for the 128- and 64-row tiles, 2 x 4 for the 32-row tiles of C = 32
+template <int NT, int KT, int WARPS_N>
 __global__ void __launch_bounds__(THREADS) wgrad_bf16_kernel(const WgradArgs<__nv_bfloat16> g) {
     using S = Smem<NT, KT>;
     constexpr int LDN = S::LDN, LDK = S::LDK;
-    constexpr int WN = NT / 4, WK = KT / 2;           // warp tile: 4 warps along n, 2 along k
+    constexpr int WARPS_K = 8 / WARPS_N;
+    constexpr int WN = NT / WARPS_N, WK = KT / WARPS_K;
+    static_assert(WN % 16 == 0 && WK % 8 == 0, "warp tile");
     constexpr int MT = WN / 16, NTL = WK / 8;         // m16 tiles, n8 tiles per warp
-    constexpr int DCH = TOK * NT / 8 / THREADS;       // 16-byte chunks per thread per stage (dY)
-    constexpr int XCH = TOK * KT / 8 / THREADS;
+    constexpr int DTOT = TOK * NT / 8, XTOT = TOK * KT / 8;       // 16-byte chunks per stage
+    constexpr int DCH = (DTOT + THREADS - 1) / THREADS, XCH = (XTOT + THREADS - 1) / THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S& s = *reinterpret_cast<S*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;
-    const int wn = warp & 3, wk = warp >> 2;
+    const int wn = warp % WARPS_N, wk = warp / WARPS_N;
     const int n0 = blockIdx.x * NT, k0 = blockIdx.y * KT;
     const long long m_begin = static_cast<long long>(blockIdx.z) * g.rows_per_split;
     long long m_end = m_begin + g.rows_per_split;
@@ -85,13 +93,13 @@ __global__ void __launch_bounds__(THREADS) wgrad_bf16_kernel(const WgradArgs<__n
 #pragma unroll
         for (int i = 0; i < DCH; ++i) {
             const int c = tid + i * THREADS, r = c / (NT / 8), ch = c % (NT / 8);
-            const long long o = s.offD[b][r];
+            const long long o = (DTOT % THREADS == 0 || c < DTOT) ? s.offD[b][r] : -1;
             dreg[i] = o >= 0 ? *reinterpret_cast<const uint4*>(g.dY + o + n0 + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int i = 0; i < XCH; ++i) {
             const int c = tid + i * THREADS, r = c / (KT / 8), ch = c % (KT / 8);
-            const long long o = s.offX[b][r];
+            const long long o = (XTOT % THREADS == 0 || c < XTOT) ? s.offX[b][r] : -1;
             xreg[i] = o >= 0 ? *reinterpret_cast<const uint4*>(g.X + o + k0 + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
         }
     };
@@ -105,6 +113,7 @@ __global__ void __launch_bounds__(THREADS) wgrad_bf16_kernel(const WgradArgs<__n
 #pragma unroll
         for (int i = 0; i < DCH; ++i) {
             const int c = tid + i * THREADS, r = c / (NT / 8), ch = c % (NT / 8);
+            if (DTOT % THREADS != 0 && c >= DTOT) break;
             uint4 v = dreg[i];
             if (g.dy_row_scale && s.offD[b][r] >= 0) {
                 float f[8];
@@ -118,6 +127,7 @@ __global__ void __launch_bounds__(THREADS) wgrad_bf16_kernel(const WgradArgs<__n
 #pragma unroll
         for (int i = 0; i < XCH; ++i) {
             const int c = tid + i * THREADS, r = c / (KT / 8), ch = c % (KT / 8);
+            if (XTOT % THREADS != 0 && c >= XTOT) break;
             uint4 v = xreg[i];
             if (has_ln && s.offX[b][r] >= 0) {
                 float f[8];
@@ -148,18 +158,28 @@ __global__ void __launch_bounds__(THREADS) wgrad_bf16_kernel(const WgradArgs<__n
         const __nv_bfloat16* xs = s.x[b];
 #pragma unroll
         for (int ks = 0; ks < TOK / 16; ++ks) {
-            uint32_t bf[NTL / 2][4];
+            uint32_t bf[(NTL + 1) / 2][4];
+            if constexpr (NTL == 1) {
+                uint32_t b2[2];
+                ldsm_x2_t(b2, xs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDK + wk * WK);
+                bf[0][0] = b2[0]; bf[0][1] = b2[1]; bf[0][2] = 0u; bf[0][3] = 0u;
+            } else {
 #pragma unroll
-            for (int jp = 0; jp < NTL / 2; ++jp)
-                pc::ldsm_x4_t(bf[jp], xs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDK + wk * WK + jp * 16 + (lane >> 4) * 8);
+                for (int jp = 0; jp < NTL / 2; ++jp)
+                    pc::ldsm_x4_t(bf[jp], xs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDK + wk * WK + jp * 16 + (lane >> 4) * 8);
+            }
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 uint32_t af[4];     // A[n][tok] = dY[tok][n], transposed on load
                 pc::ldsm_x4_t(af, dys + (ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * LDN + wn * WN + i * 16 + ((lane >> 3) & 1) * 8);
+                if constexpr (NTL == 1) {
+                    pc::mma16816(acc[i][0], af, bf[0][0], bf[0][1]);
+                } else {
 #pragma unroll
-                for (int jp = 0; jp < NTL / 2; ++jp) {
-                    pc::mma16816(acc[i][2 * jp], af, bf[jp][0], bf[jp][1]);
-                    pc::mma16816(acc[i][2 * jp + 1], af, bf[jp][2], bf[jp][3]);
+                    for (int jp = 0; jp < NTL / 2; ++jp) {
+                        pc::mma16816(acc[i][2 * jp], af, bf[jp][0], bf[jp][1]);
+                        pc::mma16816(acc[i][2 * jp + 1], af, bf[jp][2], bf[jp][3]);
+                    }
                 }
                 if (want_db) pc::mma16816(accb[i], af, 0x3F803F80u, 0x3F803F80u);      // x 1.0: column sums of dY
             }
@@ -182,10 +202,10 @@ __global__ void __launch_bounds__(THREADS) wgrad_bf16_kernel(const WgradArgs<__n
 
 inline bool supported(const WgradArgs<__nv_bfloat16>& g) {
     static const bool on = [] { const char* e = getenv("LEWIN_NO_WGRAD2"); return !(e && e[0] == '1'); }();
-    return on && !g.dy_aux && g.N % 64 == 0 && g.K % 64 == 0 && g.M < (1ll << 31);
+    return on && !g.dy_aux && g.N % 32 == 0 && g.K % 32 == 0 && g.M < (1ll << 31);
 }
 
-template <int NT, int KT>
+template <int NT, int KT, int WARPS_N>
 cudaError_t launch_t(WgradArgs<__nv_bfloat16> g, int num_sms, cudaStream_t st) {
     const long long tiles = static_cast<long long>(g.N / NT) * (g.K / KT);
     long long want = (static_cast<long long>(num_sms) * 3 + tiles - 1) / tiles;
@@ -196,7 +216,7 @@ cudaError_t launch_t(WgradArgs<__nv_bfloat16> g, int num_sms, cudaStream_t st) {
     rps = (rps + TOK - 1) / TOK * TOK;
     const unsigned splits = static_cast<unsigned>((g.M + rps - 1) / rps);
     g.rows_per_split = rps;
-    auto k = wgrad_bf16_kernel<NT, KT>;
+    auto k = wgrad_bf16_kernel<NT, KT, WARPS_N>;
     const size_t smem = sizeof(Smem<NT, KT>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -205,8 +225,13 @@ cudaError_t launch_t(WgradArgs<__nv_bfloat16> g, int num_sms, cudaStream_t st) {
 }
 
 inline cudaError_t launch(const WgradArgs<__nv_bfloat16>& g, int num_sms, cudaStream_t st) {
-    if (g.N % 128 == 0) return launch_t<128, 64>(g, num_sms, st);
-    return launch_t<64, 64>(g, num_sms, st);
+    if (g.K % 64 == 0) {
+        if (g.N % 128 == 0) return launch_t<128, 64, 4>(g, num_sms, st);
+        if (g.N % 64 == 0) return launch_t<64, 64, 4>(g, num_sms, st);
+        return launch_t<32, 64, 2>(g, num_sms, st);
+    }
+    if (g.N % 128 == 0) return launch_t<128, 32, 4>(g, num_sms, st);
+    return launch_t<32, 32, 2>(g, num_sms, st);
 }
 
 }  // namespace wg2

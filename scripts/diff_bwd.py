@@ -7,7 +7,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-CASES = [(64, 2, 2, 32, 32, 4), (128, 4, 2, 32, 32, 4), (256, 8, 2, 16, 16, 4), (64, 2, 32, 128, 128, 4), (128, 4, 32, 64, 64, 4)]
+CASES = [(32, 1, 2, 32, 32, 4), (64, 2, 2, 32, 32, 4), (128, 4, 2, 32, 32, 4), (256, 8, 2, 16, 16, 4), (64, 2, 32, 128, 128, 4), (128, 4, 32, 64, 64, 4), (32, 1, 32, 128, 128, 4)]
 
 
 def child(tag, out_dir):
@@ -63,7 +63,7 @@ def main():
     import torch
     out_dir = "/tmp/diff_bwd"
     os.makedirs(out_dir, exist_ok=True)
-    variants = {"old": {"LEWIN_NO_BWD2": "1"}, "new": {}}
+    variants = {"old": {k: "1" for k in os.environ.get("DIFF_OLD", "LEWIN_NO_BWD2,LEWIN_NO_WGRAD2,LEWIN_NO_CORE_BWD2").split(",")}, "new": {}}
     for tag, envx in variants.items():
         r = subprocess.run([sys.executable, __file__, "--child", tag, out_dir], env=dict(os.environ, **envx), timeout=300,
                            capture_output=True, text=True)

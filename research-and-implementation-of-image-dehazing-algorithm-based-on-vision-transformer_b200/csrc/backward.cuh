@@ -16,6 +16,8 @@
 #include "probsparse_core.cuh"
 #include "wgrad_args.cuh"
 #include "wgrad_bf16.cuh"
+#include "core_bwd_args.cuh"
+#include "probsparse_core_bwd_v2.cuh"
 
 namespace lewin {
 
@@ -475,19 +477,6 @@ cudaError_t launch_dwconv_bwd(const T* g2, const T* a2, const T* h1, const T* a1
 }
 
 // ------------------------------------------------------------------------------ ProbSparse core backward
-template <typename T>
-struct CoreBwdArgs {
-    const T* qkv;            // [B_*64, 3C]
-    const T* dctx;           // [B_*64, C]
-    T* dqkv;                 // [B_*64, 3C]
-    const uint8_t* top;      // [B_, nH, 25]
-    const float* rpb_table; const float* rpb_dense;
-    float* d_rpb_table;      // [225, nH] accumulated (null => skipped)
-    const float* mask; int nW_mask;
-    int B_, nH, C, use_rpb;
-    int shift, H, W, nWw, nWin;
-};
-
 struct CoreBwdSmem {
     float q[kTok * QK_LD];
     float k[kTok * QK_LD];
@@ -779,6 +768,9 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
 
 template <typename T>
 cudaError_t launch_core_bwd(const CoreBwdArgs<T>& a, int num_sms, cudaStream_t stream) {
+    if constexpr (Act<T>::kIsBf16) {
+        if (pcb2::enabled()) return pcb2::launch(a, num_sms, stream);      // register-resident bf16 path
+    }
     auto k = probsparse_core_bwd_kernel<T>;
     const size_t smem = sizeof(CoreBwdSmem);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

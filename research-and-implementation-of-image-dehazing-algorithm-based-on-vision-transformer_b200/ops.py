@@ -53,6 +53,21 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+def _zero_grads(like, device):
+    """fp32 zero gradient buffers for the given parameter tensors (None entries stay None): ONE flat allocation and one
+    fill kernel, handed out as views (the backward kernels accumulate into them with atomics)."""
+    sizes = [0 if t is None else t.numel() for t in like]
+    flat = torch.zeros(sum((n + 3) // 4 * 4 for n in sizes), dtype=torch.float32, device=device)
+    out, off = [], 0
+    for t, n in zip(like, sizes):
+        if t is None:
+            out.append(None)
+        else:
+            out.append(flat[off:off + n].view(t.shape))
+            off += (n + 3) // 4 * 4
+    return out
+
+
 def prepare_index_sample(index_sample, device):
     """int64 CPU tensor drawn as attn.py:91 -> int32 device tensor [64, 25]."""
     if index_sample.dtype != torch.int32 or index_sample.device != device:
@@ -150,9 +165,9 @@ class _AttnFn(torch.autograd.Function):
         C = x.shape[-1]
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        z = lambda t: None if t is None else torch.zeros_like(t, dtype=torch.float32)
-        d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out = z(ln_w), z(ln_b), z(w_qkv), z(b_qkv), z(w_out), z(b_out)
-        d_tab = z(tab) if tab is not None else (torch.zeros((225, nH), dtype=torch.float32, device=dev) if dense is not None else None)
+        tab_like = tab if tab is not None else (torch.empty((225, nH), device="meta") if dense is not None else None)
+        d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab = _zero_grads(
+            (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab_like), dev)
         fwd = _lib.LewinAttnFwdArgs(
             B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
             analytic_shift_mask=int(analytic), nW_mask=0 if mask is None else mask.shape[0],
@@ -230,8 +245,7 @@ class _LeffFn(torch.autograd.Function):
         hidden = w1.shape[0]
         dout = dout.contiguous()
         dy = torch.empty_like(y)
-        z = lambda t: None if t is None else torch.zeros_like(t, dtype=torch.float32)
-        d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2 = z(ln_w), z(ln_b), z(w1), z(b1), z(wdw), z(bdw), z(w2), z(b2)
+        d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2 = _zero_grads((ln_w, ln_b, w1, b1, wdw, bdw, w2, b2), dev)
         fwd = _lib.LewinLeffFwdArgs(
             B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=1, reserved=0,
             y=_ptr(y), out=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w1=_ptr(w1), b1=_ptr(b1),

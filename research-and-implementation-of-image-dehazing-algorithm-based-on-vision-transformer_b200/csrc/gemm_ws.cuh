@@ -75,7 +75,21 @@ __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const flo
 // fixed shared memory besides the weight tile and the A ring
 template <int BN, int EPI, int NEW>
 constexpr size_t fixed_smem() {
-    return 1024 /*align*/ + NEW * 2 * STG_BUF + BN * 4 + (2 * 8 + 4) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGelu2TabSize * 2 : 0);
+    return 1024 /*align*/ + NEW * 2 * STG_BUF + BN * 4 + (2 * 8 + 8) * 8 + 16 + (EPI == EPI_BIAS_GELU ? kGelu2TabSize * 2 : 0);
+}
+
+// residual rows of one warp's 32 rows x 32 columns of tile `tile` -> staging buffer (cp.async, coalesced 64-byte row pieces)
+template <int NCG>
+__device__ __forceinline__ void resid_prefetch(const GemmArgs<__nv_bfloat16>& g, uint32_t tile, int col0, unsigned char* sbuf, int lg, int lane) {
+    const uint32_t m = tile * TC_BM + lg * 32 + lane;
+    long long oy = -1;
+    if (m < g.M) oy = static_cast<long long>(g.mapY ? g.map.token32(m) : m) * g.ldy;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
+        const long long o = __shfl_sync(0xffffffffu, oy, rl);
+        if (o >= 0) cp_async16(sbuf + rl * STG_ROW + cc * 16, g.R + o + col0 + cc * 8);
+    }
 }
 
 // One warp's share of one output tile: wait for the accumulator, tcgen05.ld 32-column chunks (thread == TMEM lane == tile
@@ -83,10 +97,15 @@ constexpr size_t fixed_smem() {
 template <int BN, int EPI, int NCG, int NBUF = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, uint32_t tmem_d, int acc, uint32_t aph, uint32_t tile,
                                               int n0, const float* s_bias, const uint16_t* gtab, unsigned char* my_stg,
-                                              uint64_t* tfull, uint64_t* tempty, int lg, int half, int lane) {
+                                              uint64_t* tfull, uint64_t* tempty, int lg, int half, int lane,
+                                              long long tile_next = -1, int parity = 0) {
     using T = __nv_bfloat16;
     constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     constexpr int NCH = BN / 32;
+    // One chunk per warp (BN <= 32 * NCG): the residual rows of the NEXT tile are prefetched into the other staging buffer
+    // while this tile is processed -- at C <= 64 a tile is so small that waiting for this tile's own residual (one DRAM
+    // latency per tile and warp) was the critical path.  The caller issues the first tile's prefetch (resid_prefetch).
+    constexpr bool XT = (EPI == EPI_BIAS_RESID) && (NCH <= NCG) && NBUF == 2;
     static_assert(NBUF == 2 || EPI != EPI_BIAS_RESID, "the residual prefetch uses two staging buffers");
         const uint32_t m = tile * TC_BM + lg * 32 + lane;
         long long oy = -1;
@@ -96,7 +115,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
             oy = static_cast<long long>(ry) * g.ldy;
             if (EPI == EPI_BIAS_RESID && g.drop_scale) sc = g.drop_scale[ry / static_cast<uint32_t>(g.tokens_per_image)];
         }
-        if (EPI == EPI_BIAS_RESID) {            // residual rows of my first two chunks -> staging (async, coalesced)
+        if constexpr (XT) {
+            if (tile_next >= 0 && half < NCH) resid_prefetch<NCG>(g, static_cast<uint32_t>(tile_next), n0 + half * 32, my_stg + (parity ^ 1) * STG_BUF, lg, lane);
+            cp_async_commit();
+        } else if (EPI == EPI_BIAS_RESID) {     // residual rows of my first two chunks -> staging (async, coalesced)
             int q = 0;
             for (int c = half; c < NCH && q < 2; c += NCG, ++q) {
 #pragma unroll
@@ -110,7 +132,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
         }
         tc::mbar_wait(&tfull[acc], aph);
         tc::tc_fence_after();
-        if (EPI == EPI_BIAS_RESID) { cp_async_wait<0>(); __syncwarp(); }
+        if constexpr (XT) { cp_async_wait<1>(); __syncwarp(); }      // this tile's residual landed (the next tile's may still fly)
+        else if (EPI == EPI_BIAS_RESID) { cp_async_wait<0>(); __syncwarp(); }
         const uint32_t t_addr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(acc * ACC);
         int q = 0;
         for (int c = half; c < NCH; c += NCG, ++q) {
@@ -120,7 +143,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
                 tc::tc_fence_before();
                 mbar_arrive(&tempty[acc]);
             }
-            unsigned char* sb = my_stg + (NBUF == 2 ? (q & 1) : 0) * STG_BUF;
+            unsigned char* sb = my_stg + (XT ? parity : (NBUF == 2 ? (q & 1) : 0)) * STG_BUF;
             unsigned char* srow = sb + lane * STG_ROW;
             const float2* bs2 = reinterpret_cast<const float2*>(s_bias + c * 32);
 #pragma unroll
@@ -214,7 +237,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
     constexpr int W_CHUNK = BN * KC * 2;
     constexpr int STAGE = CPS * A_CHUNK;
     constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM columns per accumulator stage
-    constexpr int TMEM_COLS = 2 * ACC;
+    constexpr int NACC = ACC <= 128 ? 4 : 2;           // accumulator stages: narrow tiles are handshake-latency bound, give the MMA more run-ahead
+    constexpr int TMEM_COLS = NACC * ACC;
     constexpr int NCH = BN / 32;                       // 32-column epilogue chunks
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                (static_cast<uint32_t>(TC_BM >> 4) << 24);
@@ -230,9 +254,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
     float* s_bias = reinterpret_cast<float*>(stg + NEW * 2 * STG_BUF);
     uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + BN);      // [8]
     uint64_t* empty = full + 8;                                     // [8]
-    uint64_t* tfull = empty + 8;                                    // [2]
-    uint64_t* tempty = tfull + 2;                                   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tfull = empty + 8;                                    // [NACC]
+    uint64_t* tempty = tfull + 4;                                   // [NACC]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
     uint16_t* gtab = reinterpret_cast<uint16_t*>(tmem_slot + 4);    // EPI_BIAS_GELU only
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -254,7 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
     if (EPI == EPI_BIAS_GELU) gelu_tab2_to_smem(gtab, tid, THREADS);
     if (tid == 0) {
         for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], NPW * 32); tc::mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], NEW * 32); }
+        for (int i = 0; i < NACC; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], NEW * 32); }
         tc::fence_barrier_init();
     }
     if (warp == MMA_WARP) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -442,8 +466,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
             int s = 0;
             uint32_t ph = 0;
             for (int it = 0; it < my_tiles; ++it) {
-                const int acc = it & 1;
-                const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+                const int acc = it % NACC;
+                const uint32_t aph = static_cast<uint32_t>(it / NACC) & 1u;
                 tc::mbar_wait(&tempty[acc], aph ^ 1u);             // epilogue drained this accumulator
                 tc::tc_fence_after();
                 const uint32_t d_addr = tmem_d + static_cast<uint32_t>(acc * ACC);
@@ -468,9 +492,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
         // ============================================================ epilogue: thread == TMEM lane == tile row
         const int lg = warp & 3, half = warp >> 2;     // TMEM lane group, column group
         unsigned char* my_stg = stg + warp * 2 * STG_BUF;
+        constexpr bool XT = (EPI == EPI_BIAS_RESID) && (BN / 32 <= NCG);
+        if (XT && my_tiles > 0) {
+            if (half < BN / 32) resid_prefetch<NCG>(g, blockIdx.x, n0 + half * 32, my_stg, lg, lane);
+            cp_async_commit();
+        }
         for (int it = 0; it < my_tiles; ++it) {
-            epilogue_tile<BN, EPI, NCG>(g, tmem_d, it & 1, static_cast<uint32_t>(it >> 1) & 1u, blockIdx.x + static_cast<uint32_t>(it) * gridDim.x,
-                                        n0, s_bias, gtab, my_stg, tfull, tempty, lg, half, lane);
+            const long long tnext = (XT && it + 1 < my_tiles) ? static_cast<long long>(blockIdx.x) + static_cast<long long>(it + 1) * gridDim.x : -1;
+            epilogue_tile<BN, EPI, NCG>(g, tmem_d, it % NACC, static_cast<uint32_t>(it / NACC) & 1u, blockIdx.x + static_cast<uint32_t>(it) * gridDim.x,
+                                        n0, s_bias, gtab, my_stg, tfull, tempty, lg, half, lane, tnext, it & 1);
         }
     }
 

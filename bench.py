@@ -207,6 +207,7 @@ def main():
                          "inference precision, always reported as well under 'fp32')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the config 2 / 4 training-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -322,6 +323,18 @@ def main():
         fl, by = kernel_work(op, name, info)
         a = agg.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
         a["ms"] += ms; a["flops"] += fl; a["bytes"] += by; a["launches"] += 1
+    # BASELINE configs 2 / 4: one training step (batch 32 per GPU, bf16, Charbonnier, AdamW; DDP + NCCL all-reduce at N > 1)
+    train = None
+    if not args.no_train_step:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("train_step", os.path.join(ROOT, "scripts", "train_step.py"))
+            ts = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(ts)
+            torch.cuda.empty_cache()
+            train, _ = ts.run(batch=32, steps=5, warmup=3, dtype="bf16")
+        except Exception as e:      # the headline line must survive a failure of the secondary measurement
+            train = {"error": repr(e)[:300]}
     lt = torch.tensor([float(launches)], device=dev)
     if world > 1:
         dist.all_reduce(lt)
@@ -379,7 +392,8 @@ def main():
                    "tiles_per_rank_max": -(-N_TILES // world), "l2": "working set (>=354 MB per level-0 tensor) exceeds the 126 MB L2",
                    "convs": "in/out/down/up projections are stock cuDNN (out of hot-path scope)",
                    "launch": "python launches" if args.no_graph else "CUDA graph replay of the per-rank tile-batch forward",
-                   "lewin_compute": "3xTF32 mma.sync (fp32-grade)" if args.dtype == "f32" else "bf16 operands, fp32 accumulate"},
+                   "lewin_compute": "3xTF32 mma.sync (fp32-grade)" if args.dtype == "f32" else
+                                    "bf16 operands, fp32 accumulate: warp-specialised tcgen05 GEMMs (TMEM, TMA at C >= 256), mma.sync ProbSparse core, TMA-fed depthwise conv"},
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "images/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo},
         "gpu_launches": int(lt.item()),
         "roofline": roofline,
@@ -390,6 +404,7 @@ def main():
             "e2e": 1e3 / (ms_other_e2e / args.steps),
             "note": "same workload at the other precision (f32 = 3xTF32 error-compensated kernels, strict parity path)"},
         "lewin_block_us": blocks,
+        "train_step": train,
         "kernels": kernels,
     }
     print(json.dumps(line), flush=True)

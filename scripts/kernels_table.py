@@ -7,3 +7,5 @@ for k in d.get("kernels", []):
 if "lewin_block_us" in d:
     b = d["lewin_block_us"]
     print("  block us:", " ".join(f"{l['level']}:{l['fwd_us']:.0f}/{l['fwd_bwd_us']:.0f}" for l in b["per_level"]))
+if d.get("train_step"):
+    print("  train_step:", d["train_step"])

@@ -1,0 +1,72 @@
+"""BASELINE configs 2 / 4: one Uformer_ProbSparse training step (batch 32 x 3 x 128 x 128 per GPU, bf16 autocast,
+Charbonnier loss eps 1e-3, AdamW 2e-4 / wd 0.02; My_train.py:221-250) on the sm_100a LeWin ops; under torchrun the
+model is wrapped with parallel.wrap_ddp (NCCL gradient all-reduce).  The VGG19 contrastive term of the reference loss
+(My_CR.py) is a SURVEY section 8(f) 'next' row and is NOT included.  Prints one JSON line (rank 0)."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def charbonnier(x, y, eps=1e-3):
+    d = x.float() - y.float()
+    return torch.mean(torch.sqrt(d * d + eps * eps))
+
+
+def run(batch=32, steps=10, warmup=3, dtype="bf16"):
+    global torch
+    import torch
+    import torch.distributed as dist
+    import lewin_b200 as L
+    from lewin_b200 import parallel
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)
+    model = L.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff").to(dev).train()
+    parallel.freeze_dead_parameters(model)
+    net = parallel.wrap_ddp(model, dev) if world > 1 else model
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x = torch.rand(batch, 3, 128, 128, generator=g).to(dev)
+    y = torch.rand(batch, 3, 128, 128, generator=g).to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", torch.bfloat16, enabled=(dtype == "bf16")):
+            out = net(x)
+        loss = charbonnier(out, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        loss = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    res = dict(step_ms=float(ms.item()), patches_per_s=batch * world / (float(ms.item()) / 1e3), batch_per_gpu=batch, n_gpus=world,
+               dtype=dtype, loss=float(loss.item()), loss_terms="Charbonnier (VGG contrastive term not included)",
+               optimizer="AdamW(2e-4, wd 0.02)", parallelism="ddp" if world > 1 else "single")
+    return res, rank
+
+
+if __name__ == "__main__":
+    r, rank = run(batch=int(sys.argv[1]) if len(sys.argv) > 1 else 32)
+    if rank == 0:
+        print(json.dumps(r), flush=True)

@@ -130,6 +130,14 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return 0.5f * x + 0.5f * fabsf(x) * e;
 }
 
+// exp(x - mx) for the softmaxes of the bf16 core kernels: one FFMA + one MUFU.EX2 (ftz).  __expf() costs 3 FMUL + FSETP +
+// MUFU because the non-ftz ex2 rescales around denormal results, which are below a bf16 ulp of any probability here.
+__device__ __forceinline__ float exp_sub(float x, float mxl2 /* mx * log2(e) */) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(x, 1.4426950408889634f, -mxl2)));
+    return r;
+}
+
 // ---------------------------------------------------------------- exact bf16 GELU by table
 // In the bf16 path GELU always acts on a value that was just rounded to bf16 (the linear / conv output), and its
 // result is rounded to bf16 again, so it is a 16-bit -> 16-bit function.  Outside 2^-12 <= |x| < 16 the result is

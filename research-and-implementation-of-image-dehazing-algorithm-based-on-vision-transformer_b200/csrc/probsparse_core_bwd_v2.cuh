@@ -131,14 +131,16 @@ __global__ void __launch_bounds__(THREADS, 3) core_bwd_v2_kernel(const CoreBwdAr
             }
             // forward recompute: P1 = softmax(S), P2 = bf16(softmax(P1 + rpb + mask))
             float p1[8][2];
+            float mxl;
             float mx = x[0][0];
 #pragma unroll
             for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fmaxf(x[j][0], x[j][1]));
             mx = group_max<4>(mx);
+            mxl = mx * 1.4426950408889634f;
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                p1[j][0] = __expf(x[j][0] - mx); p1[j][1] = __expf(x[j][1] - mx);
+                p1[j][0] = exp_sub(x[j][0], mxl); p1[j][1] = exp_sub(x[j][1], mxl);
                 sum += p1[j][0]; sum += p1[j][1];
             }
             float inv = __fdividef(1.0f, group_sum<4>(sum));
@@ -175,10 +177,11 @@ __global__ void __launch_bounds__(THREADS, 3) core_bwd_v2_kernel(const CoreBwdAr
 #pragma unroll
             for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fmaxf(x[j][0], x[j][1]));
             mx = group_max<4>(mx);
+            mxl = mx * 1.4426950408889634f;
             sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                x[j][0] = __expf(x[j][0] - mx); x[j][1] = __expf(x[j][1] - mx);
+                x[j][0] = exp_sub(x[j][0], mxl); x[j][1] = exp_sub(x[j][1], mxl);
                 sum += x[j][0]; sum += x[j][1];
             }
             inv = __fdividef(1.0f, group_sum<4>(sum));

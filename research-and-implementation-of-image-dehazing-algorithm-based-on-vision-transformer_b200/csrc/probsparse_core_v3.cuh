@@ -208,14 +208,16 @@ __global__ void __launch_bounds__(THREADS, 5) probsparse_core_v3_kernel(const Co
                 }
             }
             // softmax 1
+            float mxl;
             float mx = acc[0][0];
 #pragma unroll
             for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fmaxf(acc[j][0], acc[j][1]));
             mx = group_max<4>(mx);
+            mxl = mx * 1.4426950408889634f;
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                acc[j][0] = __expf(acc[j][0] - mx); acc[j][1] = __expf(acc[j][1] - mx);
+                acc[j][0] = exp_sub(acc[j][0], mxl); acc[j][1] = exp_sub(acc[j][1], mxl);
                 sum += acc[j][0]; sum += acc[j][1];
             }
             float inv = __fdividef(1.0f, group_sum<4>(sum));
@@ -254,10 +256,11 @@ __global__ void __launch_bounds__(THREADS, 5) probsparse_core_v3_kernel(const Co
 #pragma unroll
             for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fmaxf(acc[j][0], acc[j][1]));
             mx = group_max<4>(mx);
+            mxl = mx * 1.4426950408889634f;
             sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                acc[j][0] = __expf(acc[j][0] - mx); acc[j][1] = __expf(acc[j][1] - mx);
+                acc[j][0] = exp_sub(acc[j][0], mxl); acc[j][1] = exp_sub(acc[j][1], mxl);
                 sum += acc[j][0]; sum += acc[j][1];
             }
             inv = __fdividef(1.0f, group_sum<4>(sum));

@@ -16,7 +16,7 @@ def charbonnier(x, y, eps=1e-3):
     return torch.mean(torch.sqrt(d * d + eps * eps))
 
 
-def run(batch=32, steps=10, warmup=3, dtype="bf16"):
+def run(batch=32, steps=10, warmup=3, dtype="bf16", graph=True):
     global torch
     import torch
     import torch.distributed as dist
@@ -37,14 +37,48 @@ def run(batch=32, steps=10, warmup=3, dtype="bf16"):
     x = torch.rand(batch, 3, 128, 128, generator=g).to(dev)
     y = torch.rand(batch, 3, 128, 128, generator=g).to(dev)
 
+    idx_static = model.draw_index_samples().to(dev, dtype=torch.int32)       # refreshed before every step (attn.py:91 draws)
+
     def step():
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", torch.bfloat16, enabled=(dtype == "bf16")):
-            out = net(x)
+            out = net(x, index_samples=idx_static)
         loss = charbonnier(out, y)
         loss.backward()
         opt.step()
         return loss
+
+    eager_step = step
+    mode = "eager"
+    if graph and world == 1:
+        # whole-step CUDA graph (forward + backward + AdamW): the deep levels are launch-bound in eager mode
+        try:
+            opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), eps=1e-8,
+                                    weight_decay=0.02, capturable=True)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    eager_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(gph):
+                with torch.autocast("cuda", torch.bfloat16, enabled=(dtype == "bf16")):
+                    out_s = net(x, index_samples=idx_static)
+                loss_s = charbonnier(out_s, y)
+                loss_s.backward()
+                opt.step()
+
+            def step():
+                idx_static.copy_(model.draw_index_samples(), non_blocking=True)   # fresh key samples every step, as the reference
+                gph.replay()
+                return loss_s
+            mode = "cuda-graph (forward + backward + optimizer)"
+        except Exception as e:
+            step = eager_step
+            mode = "eager (graph capture failed: %s)" % repr(e)[:120]
 
     for _ in range(warmup):
         loss = step()
@@ -62,7 +96,7 @@ def run(batch=32, steps=10, warmup=3, dtype="bf16"):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     res = dict(step_ms=float(ms.item()), patches_per_s=batch * world / (float(ms.item()) / 1e3), batch_per_gpu=batch, n_gpus=world,
                dtype=dtype, loss=float(loss.item()), loss_terms="Charbonnier (VGG contrastive term not included)",
-               optimizer="AdamW(2e-4, wd 0.02)", parallelism="ddp" if world > 1 else "single")
+               optimizer="AdamW(2e-4, wd 0.02)", parallelism="ddp" if world > 1 else "single", launch=mode)
     return res, rank
 
 

@@ -98,7 +98,7 @@ template <int BN, int EPI, int NCG, int NBUF = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, uint32_t tmem_d, int acc, uint32_t aph, uint32_t tile,
                                               int n0, const float* s_bias, const uint16_t* gtab, unsigned char* my_stg,
                                               uint64_t* tfull, uint64_t* tempty, int lg, int half, int lane,
-                                              long long tile_next = -1, int parity = 0) {
+                                              long long tile_next = -1, int parity = 0, const CUtensorMap* ymap = nullptr) {
     using T = __nv_bfloat16;
     constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     constexpr int NCH = BN / 32;
@@ -107,6 +107,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
     // latency per tile and warp) was the critical path.  The caller issues the first tile's prefetch (resid_prefetch).
     constexpr bool XT = (EPI == EPI_BIAS_RESID) && (NCH <= NCG) && NBUF == 2;
     static_assert(NBUF == 2 || EPI != EPI_BIAS_RESID, "the residual prefetch uses two staging buffers");
+        if (EPI != EPI_BIAS_RESID && ymap != nullptr) {      // staging buffers restart at 0 every tile: drain my outstanding box stores
+            if (lane == 0) tma::store_wait_read<0>();
+            __syncwarp();
+        }
         const uint32_t m = tile * TC_BM + lg * 32 + lane;
         long long oy = -1;
         float sc = 1.f;
@@ -203,6 +207,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
 #pragma unroll
                     for (int h = 0; h < 16; ++h) pk[h] = ge[h];
                 }
+                if (EPI != EPI_BIAS_RESID && ymap != nullptr) {
+                    // TMA store: dense 64-byte rows, 16-byte chunks XOR-swizzled (SWIZZLE_64B) -> conflict-free row writes;
+                    // one elected lane hands the 32 x 32 box to the TMA unit, nobody reads the tile back
+                    if (lane == 0) tma::store_wait_read<NBUF - 1>();       // the box stored from this buffer NBUF chunks ago is drained
+                    __syncwarp();
+                    unsigned char* drow = sb + lane * 64;
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(drow + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    tma::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma::store_2d(ymap, sb, n0 + c * 32, static_cast<int>(tile * TC_BM) + lg * 32);
+                        tma::store_commit();
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<uint4*>(srow + j * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -226,7 +248,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
 // BN: tile columns; KC: k-chunk (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); CPS: k-chunks per ring stage (LN needs the
 // whole row in one stage: CPS * KC == K); LN: LayerNorm prologue over the K channels of the A row.
 template <int BN, int KC, int CPS, int EPI, bool LN, int NEW>
-__global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv_bfloat16> g, int row_tiles, int nkc, int S) {
+__global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv_bfloat16> g, int row_tiles, int nkc, int S,
+                                                             const __grid_constant__ CUtensorMap ymap, int use_ymap) {
     using T = __nv_bfloat16;
     constexpr int NPW = WARPS - 1 - NEW;               // producer warps
     constexpr int MMA_WARP = NEW;
@@ -500,8 +523,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_ws_kernel(const GemmArgs<__nv
         for (int it = 0; it < my_tiles; ++it) {
             const long long tnext = (XT && it + 1 < my_tiles) ? static_cast<long long>(blockIdx.x) + static_cast<long long>(it + 1) * gridDim.x : -1;
             epilogue_tile<BN, EPI, NCG>(g, tmem_d, it % NACC, static_cast<uint32_t>(it / NACC) & 1u, blockIdx.x + static_cast<uint32_t>(it) * gridDim.x,
-                                        n0, s_bias, gtab, my_stg, tfull, tempty, lg, half, lane, tnext, it & 1);
+                                        n0, s_bias, gtab, my_stg, tfull, tempty, lg, half, lane, tnext, it & 1, use_ymap ? &ymap : nullptr);
         }
+        if (use_ymap && lane == 0) tma::store_wait_read<0>();      // my box stores have read their staging tiles
     }
 
     // ---------------------------------------------------------------- teardown
@@ -528,7 +552,11 @@ cudaError_t launch_inst(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaStrea
     int gx = num_sms / col_tiles;
     if (gx < 1) gx = 1;
     if (gx > row_tiles) gx = row_tiles;
-    k<<<dim3(gx, col_tiles), THREADS, smem, stream>>>(g, row_tiles, nkc, S);
+    CUtensorMap ymap{};
+    static const bool tma_store = [] { const char* e = getenv("LEWIN_NO_TMA_STORE"); return !(e && e[0] == '1'); }();
+    const int use_ymap = (tma_store && EPI != EPI_BIAS_RESID && !g.mapY && (g.ldy % 8) == 0 &&
+                          tma::make_2d_bf16_store32(&ymap, g.Y, g.M, g.N, g.ldy)) ? 1 : 0;
+    k<<<dim3(gx, col_tiles), THREADS, smem, stream>>>(g, row_tiles, nkc, S, ymap, use_ymap);
     return cudaGetLastError();
 }
 
@@ -554,7 +582,8 @@ constexpr size_t wss_fixed_smem(int N) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(WssCfg<EPI>::THREADS, 1) gemm_wss_kernel(const GemmArgs<__nv_bfloat16> g, const __grid_constant__ CUtensorMap amap,
                                                                          const __grid_constant__ CUtensorMap wmap,
-                                                                         int row_tiles, int col_tiles, int nkc, int S) {
+                                                                         int row_tiles, int col_tiles, int nkc, int S,
+                                                                         const __grid_constant__ CUtensorMap ymap, int use_ymap) {
     using T = __nv_bfloat16;
     constexpr int NEW = WssCfg<EPI>::NEW, NBUF = WssCfg<EPI>::NBUF, THREADS_ = WssCfg<EPI>::THREADS;
     constexpr int MMA_WARP = NEW, TMA_WARP = NEW + 1, NCG = NEW / 4;
@@ -643,8 +672,9 @@ __global__ void __launch_bounds__(WssCfg<EPI>::THREADS, 1) gemm_wss_kernel(const
             const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
             const int rt = t / col_tiles, ct = t - rt * col_tiles;
             epilogue_tile<BN, EPI, NCG, NBUF>(g, tmem_d, it & 1, static_cast<uint32_t>(it >> 1) & 1u, static_cast<uint32_t>(rt), ct * BN,
-                                              s_bias + ct * BN, gtab, my_stg, tfull, tempty, lg, half, lane);
+                                              s_bias + ct * BN, gtab, my_stg, tfull, tempty, lg, half, lane, -1, 0, use_ymap ? &ymap : nullptr);
         }
+        if (use_ymap && lane == 0) tma::store_wait_read<0>();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -669,7 +699,11 @@ cudaError_t wss_launch_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16*
     const int col_tiles = g.N / BN;
     int grid = num_sms;
     if (grid > row_tiles * col_tiles) grid = row_tiles * col_tiles;
-    k<<<grid, WssCfg<EPI>::THREADS, smem, stream>>>(g, amap, wmap, row_tiles, col_tiles, g.K / 64, S);
+    CUtensorMap ymap{};
+    static const bool tma_store = [] { const char* e = getenv("LEWIN_NO_TMA_STORE"); return !(e && e[0] == '1'); }();
+    const int use_ymap = (tma_store && EPI != EPI_BIAS_RESID && !g.mapY && (g.ldy % 8) == 0 &&
+                          tma::make_2d_bf16_store32(&ymap, g.Y, g.M, g.N, g.ldy)) ? 1 : 0;
+    k<<<grid, WssCfg<EPI>::THREADS, smem, stream>>>(g, amap, wmap, row_tiles, col_tiles, g.K / 64, S, ymap, use_ymap);
     return cudaGetLastError();
 }
 

@@ -177,8 +177,15 @@ def block_microbench(dev, dtype, batch=32, iters=5):
             blk.zero_grad(set_to_none=True)
             blk(xr, None, idx).backward(dy)
 
-        res = {}
-        for key, fn in (("fwd_us", fwd), ("fwd_bwd_us", fwd_bwd)):
+        idx_dev = idx.to(dev, dtype=torch.int32)
+        xg = x.detach().clone().requires_grad_(True)
+
+        def fwd_bwd_static():           # static buffers: capturable (the key-sample indices are refreshed outside the graph)
+            xg.grad = None
+            blk.zero_grad(set_to_none=True)
+            blk(xg, None, idx_dev).backward(dy)
+
+        def timeit(fn):
             for _ in range(2):
                 fn()
             torch.cuda.synchronize()
@@ -188,12 +195,42 @@ def block_microbench(dev, dtype, batch=32, iters=5):
                 fn()
             e1.record()
             torch.cuda.synchronize()
-            res[key] = e0.elapsed_time(e1) / iters * 1e3
+            return e0.elapsed_time(e1) / iters * 1e3
+
+        res = {"fwd_us_eager": timeit(fwd), "fwd_bwd_us_eager": timeit(fwd_bwd)}
+        # device time without host launch gaps: the same call sequences replayed as CUDA graphs (as the training step does)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    with torch.no_grad():
+                        blk(x, None, idx_dev)
+                    fwd_bwd_static()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                with torch.no_grad():
+                    y_static = blk(x, None, idx_dev)
+            xg.grad = None
+            blk.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g2):
+                blk(xg, None, idx_dev).backward(dy)
+            res["fwd_us"] = timeit(g1.replay)
+            res["fwd_bwd_us"] = timeit(g2.replay)
+            res["launch"] = "cuda-graph replay (eager numbers alongside)"
+            del g1, g2, y_static
+        except Exception as e:
+            res["fwd_us"], res["fwd_bwd_us"] = res["fwd_us_eager"], res["fwd_bwd_us_eager"]
+            res["launch"] = "eager (graph capture failed: %s)" % repr(e)[:100]
         out.append(dict(level=name, C=C, map=hw, windows=batch * (hw // 8) ** 2, **res))
         del blk, x, dy
     return dict(batch=batch, dtype=dtype, per_level=out,
                 mean_fwd_us=sum(o["fwd_us"] for o in out) / len(out),
-                mean_fwd_bwd_us=sum(o["fwd_bwd_us"] for o in out) / len(out))
+                mean_fwd_bwd_us=sum(o["fwd_bwd_us"] for o in out) / len(out),
+                mean_fwd_us_eager=sum(o["fwd_us_eager"] for o in out) / len(out),
+                mean_fwd_bwd_us_eager=sum(o["fwd_bwd_us_eager"] for o in out) / len(out))
 
 
 def main():

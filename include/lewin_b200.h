@@ -219,6 +219,27 @@ size_t lewin_leff_fwd_workspace_bytes(const LewinLeffFwdArgs* a, int dtype);
 size_t lewin_leff_bwd_workspace_bytes(const LewinLeffBwdArgs* a, int dtype);
 
 /* Library / build identification. */
+/* ------------------------------------------------------------------------------------------
+ * SURVEY section 8(f) rank 2 (first step beyond the block): Upsample.forward, My_model_1.py:633-648 —
+ * nn.ConvTranspose2d(in, out, kernel_size=2, stride=2) on the token map.  Kernel 2 / stride 2 never
+ * overlaps, so it is a token GEMM  [B*H*W, Cin] x [Cin, 4*Cout]  whose output row (b, i, j) / column
+ * block (di, dj) lands at pixel (2i+di, 2j+dj): the pixel shuffle is the epilogue's row address, the
+ * bias is fused, and `out` may be the left half of the [.., 2*Cout] buffer that torch.cat([up, skip])
+ * would build (My_model_1.py:1189-1204; ld_out = row stride of `out` in elements).  bf16 inference.
+ */
+typedef struct LewinUpsampleFwdArgs {
+    int32_t B, H, W;               /* input map */
+    int32_t Cin, Cout;
+    int32_t ld_out;                /* elements between consecutive output tokens (>= Cout) */
+    int32_t reserved0, reserved1;
+    const void*  x;                /* [B, H, W, Cin] bf16 */
+    const float* weight;           /* [Cin, Cout, 2, 2] (ConvTranspose2d.weight) */
+    const float* bias;             /* [Cout] */
+    void*        out;              /* [B, 2H, 2W, ld_out] bf16; columns [0, Cout) are written */
+} LewinUpsampleFwdArgs;
+int    lewin_upsample_fwd_bf16(const LewinUpsampleFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+size_t lewin_upsample_fwd_workspace_bytes(const LewinUpsampleFwdArgs* a, int dtype);
+
 int         lewin_abi_version(void);     /* == LEWIN_ABI_VERSION */
 long long   lewin_launch_count(void);    /* kernels launched by this library in this process (diagnostic counter) */
 const char* lewin_build_info(void);      /* "sm_100a nvcc <ver> ..." */

@@ -44,6 +44,9 @@ struct GemmArgs {
     // backward helpers
     const float* a_row_scale;  // [B] or null: A row (token) is multiplied by a_row_scale[token / tokens_per_image]
     const T* aux;              // EPI_MUL_GELUGRAD: pre-activation, indexed like Y; result = acc * gelu'(aux)
+    // pixel-shuffle output addressing of the 2x2 / stride-2 transposed convolution (gemm_ws.cuh only): row m = (b, i, j) of an
+    // up_H x up_W map, column block q = col / up_C = 2*di + dj  ->  output token (b, 2i + di, 2j + dj), channel col % up_C
+    int up2, up_H, up_W, up_C;
 };
 
 constexpr int GEMM_BM = 128;

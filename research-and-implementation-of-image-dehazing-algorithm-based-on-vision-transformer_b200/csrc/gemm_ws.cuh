@@ -114,11 +114,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
         const uint32_t m = tile * TC_BM + lg * 32 + lane;
         long long oy = -1;
         float sc = 1.f;
+        uint32_t up_t00 = 0;                          // up2: output token of (di, dj) = (0, 0)
         if (m < g.M) {
             const uint32_t ry = g.mapY ? g.map.token32(m) : m;
             oy = static_cast<long long>(ry) * g.ldy;
             if (EPI == EPI_BIAS_RESID && g.drop_scale) sc = g.drop_scale[ry / static_cast<uint32_t>(g.tokens_per_image)];
+            if (g.up2) {
+                const uint32_t hw = static_cast<uint32_t>(g.up_H) * g.up_W;
+                const uint32_t b = m / hw, rem = m - b * hw, i = rem / static_cast<uint32_t>(g.up_W), j = rem - i * g.up_W;
+                up_t00 = (b * 2u * g.up_H + 2u * i) * 2u * g.up_W + 2u * j;
+            }
         }
+        const long long oy_plain = oy;
         if constexpr (XT) {
             if (tile_next >= 0 && half < NCH) resid_prefetch<NCG>(g, static_cast<uint32_t>(tile_next), n0 + half * 32, my_stg + (parity ^ 1) * STG_BUF, lg, lane);
             cp_async_commit();
@@ -148,6 +155,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
                 mbar_arrive(&tempty[acc]);
             }
             unsigned char* sb = my_stg + (XT ? parity : (NBUF == 2 ? (q & 1) : 0)) * STG_BUF;
+            if (g.up2 && oy_plain >= 0) {             // pixel shuffle: this chunk's column block selects the output pixel
+                const int col = n0 + c * 32, qb = col / g.up_C, cb = col - qb * g.up_C;
+                oy = static_cast<long long>(up_t00 + (qb >> 1) * 2u * g.up_W + (qb & 1)) * g.ldy + cb - col;
+            }
             unsigned char* srow = sb + lane * STG_ROW;
             const float2* bs2 = reinterpret_cast<const float2*>(s_bias + c * 32);
 #pragma unroll
@@ -554,7 +565,7 @@ cudaError_t launch_inst(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaStrea
     if (gx > row_tiles) gx = row_tiles;
     CUtensorMap ymap{};
     static const bool tma_store = [] { const char* e = getenv("LEWIN_NO_TMA_STORE"); return !(e && e[0] == '1'); }();
-    const int use_ymap = (tma_store && EPI != EPI_BIAS_RESID && !g.mapY && (g.ldy % 8) == 0 &&
+    const int use_ymap = (tma_store && EPI != EPI_BIAS_RESID && !g.mapY && !g.up2 && (g.ldy % 8) == 0 &&
                           tma::make_2d_bf16_store32(&ymap, g.Y, g.M, g.N, g.ldy)) ? 1 : 0;
     k<<<dim3(gx, col_tiles), THREADS, smem, stream>>>(g, row_tiles, nkc, S, ymap, use_ymap);
     return cudaGetLastError();
@@ -701,7 +712,7 @@ cudaError_t wss_launch_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16*
     if (grid > row_tiles * col_tiles) grid = row_tiles * col_tiles;
     CUtensorMap ymap{};
     static const bool tma_store = [] { const char* e = getenv("LEWIN_NO_TMA_STORE"); return !(e && e[0] == '1'); }();
-    const int use_ymap = (tma_store && EPI != EPI_BIAS_RESID && !g.mapY && (g.ldy % 8) == 0 &&
+    const int use_ymap = (tma_store && EPI != EPI_BIAS_RESID && !g.mapY && !g.up2 && (g.ldy % 8) == 0 &&
                           tma::make_2d_bf16_store32(&ymap, g.Y, g.M, g.N, g.ldy)) ? 1 : 0;
     k<<<grid, WssCfg<EPI>::THREADS, smem, stream>>>(g, amap, wmap, row_tiles, col_tiles, g.K / 64, S, ymap, use_ymap);
     return cudaGetLastError();

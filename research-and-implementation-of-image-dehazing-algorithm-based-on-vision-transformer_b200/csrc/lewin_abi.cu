@@ -442,6 +442,47 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     return 0;
 }
 
+// ------------------------------------------------------------------ Upsample
+// Wb[(2*di + dj) * Cout + co][ci] = bf16(w[ci][co][di][dj]);  bias4[q * Cout + co] = bias[co]
+__global__ void upsample_prep_kernel(const float* __restrict__ w, const float* __restrict__ bias, __nv_bfloat16* __restrict__ wb,
+                                     float* __restrict__ bias4, int Cin, int Cout) {
+    const int n = blockIdx.x;                       // output column (q, co)
+    const int q = n / Cout, co = n - q * Cout;
+    for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x)
+        wb[static_cast<long long>(n) * Cin + ci] = __float2bfloat16_rn(w[(static_cast<long long>(ci) * Cout + co) * 4 + q]);
+    if (threadIdx.x == 0) bias4[n] = bias[co];
+}
+
+size_t upsample_ws(const LewinUpsampleFwdArgs* a) {
+    return align_up(static_cast<size_t>(4) * a->Cout * a->Cin * 2, 256) + align_up(static_cast<size_t>(4) * a->Cout * 4, 256);
+}
+
+int upsample_fwd_bf16(const LewinUpsampleFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!a || !a->x || !a->weight || !a->bias || !a->out) return LEWIN_E_NULL;
+    if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->Cin % 64 || a->Cout % 32 || a->Cout <= 0 || a->ld_out < a->Cout || a->ld_out % 8)
+        return LEWIN_E_SHAPE;
+    if (!aligned16(a->x) || !aligned16(a->out)) return LEWIN_E_ALIGN;
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    if (!ws || ws_bytes < upsample_ws(a)) return LEWIN_E_WORKSPACE;
+    if (!aligned16(ws)) return LEWIN_E_ALIGN;
+    __nv_bfloat16* wb = static_cast<__nv_bfloat16*>(ws);
+    float* bias4 = reinterpret_cast<float*>(static_cast<unsigned char*>(ws) + align_up(static_cast<size_t>(4) * a->Cout * a->Cin * 2, 256));
+    upsample_prep_kernel<<<4 * a->Cout, 128, 0, stream>>>(a->weight, a->bias, wb, bias4, a->Cin, a->Cout);
+    CK(cudaGetLastError());
+    GemmArgs<__nv_bfloat16> g{};
+    g.A = static_cast<const __nv_bfloat16*>(a->x); g.lda = a->Cin;
+    g.Wt = nullptr; g.bias = bias4;
+    g.Y = static_cast<__nv_bfloat16*>(a->out); g.ldy = a->ld_out;
+    g.M = static_cast<long long>(a->B) * a->H * a->W; g.N = 4 * a->Cout; g.K = a->Cin;
+    g.tokens_per_image = a->H * a->W;
+    g.up2 = 1; g.up_H = a->H; g.up_W = a->W; g.up_C = a->Cout;
+    if (!ws::wss_supported(g)) return LEWIN_E_SHAPE;       // M >= 512, Cin % 64, 4*Cout % 128 (no fallback kernel for this op)
+    CK((ws::wss_launch<EPI_BIAS>(g, wb, di.sms, stream)));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -497,6 +538,11 @@ size_t lewin_attn_fwd_workspace_bytes(const LewinAttnFwdArgs* a, int) { return a
 size_t lewin_leff_fwd_workspace_bytes(const LewinLeffFwdArgs* a, int) { return a ? leff_fwd_ws(a) : 0; }
 size_t lewin_attn_bwd_workspace_bytes(const LewinAttnBwdArgs* a, int dtype) { return a ? lewin::attn_bwd_ws(a, dtype) : 0; }
 size_t lewin_leff_bwd_workspace_bytes(const LewinLeffBwdArgs* a, int dtype) { return a ? lewin::leff_bwd_ws(a, dtype) : 0; }
+
+int lewin_upsample_fwd_bf16(const LewinUpsampleFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return upsample_fwd_bf16(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+size_t lewin_upsample_fwd_workspace_bytes(const LewinUpsampleFwdArgs* a, int) { return a ? upsample_ws(a) : 0; }
 
 int lewin_abi_version(void) { return LEWIN_ABI_VERSION; }
 long long lewin_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -305,3 +305,31 @@ def probsparse_core(qkv, *, num_heads, index_sample, rpb_table=None, rpb_dense=N
     with torch.cuda.device(dev):
         _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_probsparse_core_fwd_{dt}")
     return (out, top) if return_top else out
+
+
+def upsample_supported(x, Cin, Cout, tokens):
+    """The 2x2 / stride-2 transposed convolution runs as a token GEMM on the streamed-W tcgen05 kernel (bf16, no autograd)."""
+    import os
+    return (x.is_cuda and x.dtype == torch.bfloat16 and Cin % 64 == 0 and Cout % 32 == 0 and tokens >= 512 and
+            os.environ.get("LEWIN_NO_WS_GEMM") != "1" and os.environ.get("LEWIN_NO_WSS_GEMM") != "1" and
+            os.environ.get("LEWIN_NO_UPSAMPLE_GEMM") != "1")
+
+
+def lewin_upsample(x, weight, bias, *, B, H, W, out=None):
+    """Upsample.forward (My_model_1.py:633-648): x [B, H*W, Cin] bf16 -> [B, 4*H*W, Cout].  ``out`` may be a wider
+    [B, 4*H*W, ld] buffer (ld >= Cout): columns [0, Cout) are written (the left half of torch.cat([up, skip], -1))."""
+    lib = _lib.load()
+    x = x.contiguous()
+    Cin = x.shape[-1]
+    Cout = weight.shape[1]
+    dev = x.device
+    if out is None:
+        out = torch.empty((B, 4 * H * W, Cout), dtype=x.dtype, device=dev)
+    assert out.is_contiguous() and out.shape[0] == B and out.shape[1] == 4 * H * W and out.shape[2] >= Cout
+    w_, b_ = _f32c(weight), _f32c(bias)
+    a = _lib.LewinUpsampleFwdArgs(B=B, H=H, W=W, Cin=Cin, Cout=Cout, ld_out=out.shape[2], reserved0=0, reserved1=0,
+                                  x=_ptr(x), weight=_ptr(w_), bias=_ptr(b_), out=_ptr(out))
+    ws = _workspace(lib.lewin_upsample_fwd_workspace_bytes(a, _lib.DTYPE_TAG["bf16"]), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lewin_upsample_fwd_bf16(a, ws.data_ptr(), ws.numel(), _stream()), "lewin_upsample_fwd_bf16")
+    return out

@@ -63,10 +63,38 @@ class Upsample(nn.Module):
         self.deconv = nn.Sequential(nn.ConvTranspose2d(in_channel, out_channel, kernel_size=2, stride=2))
         self.in_channel, self.out_channel = in_channel, out_channel
 
-    def forward(self, x):
+    def _gemm_path(self, x):
+        """bf16 inference: the non-overlapping transposed convolution is a token GEMM with a pixel-shuffle row address
+        (lewin_upsample_fwd_bf16); training / fp32 keep cuDNN."""
+        from . import ops
         d = self.deconv[0]
+        if torch.is_grad_enabled() and (x.requires_grad or d.weight.requires_grad):
+            return False
+        xb = x if x.dtype == torch.bfloat16 else None
+        if xb is None and x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+            xb = x.to(torch.bfloat16)
+        if xb is None or not ops.upsample_supported(xb, self.in_channel, self.out_channel, x.shape[0] * x.shape[1]):
+            return False
+        return xb
+
+    def forward(self, x, skip=None):
+        """``skip`` given: returns torch.cat([up(x), skip], -1) (My_model_1.py:1189-1204) with the up half written in place."""
+        d = self.deconv[0]
+        xb = self._gemm_path(x)
+        if xb is not False:
+            from . import ops
+            B, L, _ = x.shape
+            H = W = int(math.sqrt(L))
+            if skip is None:
+                return ops.lewin_upsample(xb, d.weight, d.bias, B=B, H=H, W=W)
+            C = self.out_channel
+            buf = torch.empty((B, 4 * L, C + skip.shape[-1]), dtype=xb.dtype, device=x.device)
+            ops.lewin_upsample(xb, d.weight, d.bias, B=B, H=H, W=W, out=buf)
+            buf[..., C:] = skip
+            return buf
         y = torch.nn.functional.conv_transpose2d(_tokens_to_nchw(x), _cl(d.weight), d.bias, stride=2)
-        return _nchw_to_tokens(y)
+        y = _nchw_to_tokens(y)
+        return y if skip is None else torch.cat([y, skip], -1)
 
 
 class InputProj(nn.Module):
@@ -220,13 +248,9 @@ class Uformer(nn.Module):
         conv3 = self.encoderlayer_3(pool2, mask, sl(3))
         pool3 = self.dowsample_3(conv3)
         conv4 = self.conv(pool3, mask, sl(4))
-        up0 = self.upsample_0(conv4)
-        deconv0 = self.decoderlayer_0(torch.cat([up0, conv3], -1), mask, sl(5))
-        up1 = self.upsample_1(deconv0)
-        deconv1 = self.decoderlayer_1(torch.cat([up1, conv2], -1), mask, sl(6))
-        up2 = self.upsample_2(deconv1)
-        deconv2 = self.decoderlayer_2(torch.cat([up2, conv1], -1), mask, sl(7))
-        up3 = self.upsample_3(deconv2)
-        deconv3 = self.decoderlayer_3(torch.cat([up3, conv0], -1), mask, sl(8))
+        deconv0 = self.decoderlayer_0(self.upsample_0(conv4, conv3), mask, sl(5))      # cat([up, skip], -1)
+        deconv1 = self.decoderlayer_1(self.upsample_1(deconv0, conv2), mask, sl(6))
+        deconv2 = self.decoderlayer_2(self.upsample_2(deconv1, conv1), mask, sl(7))
+        deconv3 = self.decoderlayer_3(self.upsample_3(deconv2, conv0), mask, sl(8))
         y = self.output_proj(deconv3)
         return x + y.to(x.dtype)

@@ -116,3 +116,31 @@ def test_gelu_table_edges_through_leff():
     tol = 2.0 ** -7 * ref.float().abs().clamp(min=1.0)
     assert torch.isfinite(out.float()).all()
     assert (err <= tol).all(), float((err / tol).max())
+
+
+@pytest.mark.parametrize("Cin,Cout,B,hw", [(128, 32, 2, 16), (256, 64, 2, 16), (512, 128, 3, 16), (512, 256, 8, 8)])
+def test_upsample_gemm_matches_conv_transpose(Cin, Cout, B, hw):
+    """Upsample.forward (My_model_1.py:633-648) as a token GEMM with pixel-shuffle addressing vs torch's ConvTranspose2d in
+    fp32 on the same bf16-rounded operands; also the fused torch.cat([up, skip], -1) form."""
+    import lewin_b200 as L
+    from lewin_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(B, hw * hw, Cin, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(Cin, Cout, 2, 2, generator=g) * Cin ** -0.5).to(dev)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(dev)
+    skip = torch.randn(B, 4 * hw * hw, Cout, generator=g).to(dev).to(torch.bfloat16)
+    assert ops.upsample_supported(x, Cin, Cout, B * hw * hw)
+    y = ops.lewin_upsample(x, w, b, B=B, H=hw, W=hw)
+    xr = x.float().reshape(B, hw, hw, Cin).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv_transpose2d(xr, w.to(torch.bfloat16).float(), b.to(torch.bfloat16).float(), stride=2)
+    ref = ref.permute(0, 2, 3, 1).reshape(B, 4 * hw * hw, Cout)
+    err = (y.float() - ref).abs()
+    tol = 2.0 ** -7 * ref.abs().clamp(min=1.0)             # bf16 output: 2 ulps
+    assert (err <= tol).all(), float((err / tol).max())
+    up = L.uformer.Upsample(Cin, Cout).to(dev)
+    with torch.no_grad():
+        up.deconv[0].weight.copy_(w); up.deconv[0].bias.copy_(b)
+        cat = up(x, skip)
+    assert cat.shape == (B, 4 * hw * hw, 2 * Cout)
+    assert torch.equal(cat[..., :Cout], y) and torch.equal(cat[..., Cout:], skip)

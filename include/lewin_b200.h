@@ -240,6 +240,20 @@ typedef struct LewinUpsampleFwdArgs {
 int    lewin_upsample_fwd_bf16(const LewinUpsampleFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 size_t lewin_upsample_fwd_workspace_bytes(const LewinUpsampleFwdArgs* a, int dtype);
 
+/* InputProj.forward, My_model_1.py:659-682: Conv2d(3 -> Cout, 3x3, pad 1) + LeakyReLU, NCHW fp32 image in, token-major
+ * bf16 [B, H*W, Cout] out, with the autocast rounding points (conv -> bf16, + bias -> bf16, LeakyReLU -> bf16) in ONE pass
+ * (the stock path is a cuDNN convolution + a bias-add pass + an activation pass over the 32-channel map). */
+typedef struct LewinInputProjArgs {
+    int32_t B, H, W, Cin, Cout;    /* Cin <= 4, Cout in {32, 64} */
+    float   negative_slope;        /* nn.LeakyReLU default 0.01 */
+    int32_t reserved0, reserved1;
+    const float* x;                /* [B, Cin, H, W] fp32 */
+    const float* weight;           /* [Cout, Cin, 3, 3] */
+    const float* bias;             /* [Cout] */
+    void*        out;              /* [B, H*W, Cout] bf16 */
+} LewinInputProjArgs;
+int lewin_input_proj_fwd_bf16(const LewinInputProjArgs* a, lewin_stream_t stream);
+
 int         lewin_abi_version(void);     /* == LEWIN_ABI_VERSION */
 long long   lewin_launch_count(void);    /* kernels launched by this library in this process (diagnostic counter) */
 const char* lewin_build_info(void);      /* "sm_100a nvcc <ver> ..." */

@@ -77,6 +77,14 @@ class LewinUpsampleFwdArgs(C.Structure):
     ]
 
 
+class LewinInputProjArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+        ("negative_slope", C.c_float), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("x", c_ptr), ("weight", c_ptr), ("bias", c_ptr), ("out", c_ptr),
+    ]
+
+
 # every symbol include/lewin_b200.h declares (tests check the .so exports all of them)
 EXPORTS = (
     "lewin_attn_fwd_f32", "lewin_attn_fwd_bf16", "lewin_attn_bwd_f32", "lewin_attn_bwd_bf16",
@@ -86,7 +94,7 @@ EXPORTS = (
     "lewin_probsparse_core_fwd_f32", "lewin_probsparse_core_fwd_bf16", "lewin_probsparse_core_fwd_workspace_bytes",
     "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count", "lewin_leff_fwd_is_fused",
     "lewin_attn_fwd_kernel_mask", "lewin_leff_fwd_kernel_mask",
-    "lewin_upsample_fwd_bf16", "lewin_upsample_fwd_workspace_bytes",
+    "lewin_upsample_fwd_bf16", "lewin_upsample_fwd_workspace_bytes", "lewin_input_proj_fwd_bf16",
 )
 
 ABI_VERSION = 1
@@ -119,6 +127,8 @@ def load():
     lib.lewin_upsample_fwd_bf16.restype = C.c_int
     lib.lewin_upsample_fwd_workspace_bytes.argtypes = [C.POINTER(LewinUpsampleFwdArgs), C.c_int]
     lib.lewin_upsample_fwd_workspace_bytes.restype = C.c_size_t
+    lib.lewin_input_proj_fwd_bf16.argtypes = [C.POINTER(LewinInputProjArgs), C.c_void_p]
+    lib.lewin_input_proj_fwd_bf16.restype = C.c_int
     lib.lewin_abi_version.restype = C.c_int
     lib.lewin_leff_fwd_is_fused.argtypes = [C.POINTER(LewinLeffFwdArgs), C.c_int]
     lib.lewin_leff_fwd_is_fused.restype = C.c_int

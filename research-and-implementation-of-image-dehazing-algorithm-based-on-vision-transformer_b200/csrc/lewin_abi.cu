@@ -483,6 +483,82 @@ int upsample_fwd_bf16(const LewinUpsampleFwdArgs* a, void* ws, size_t ws_bytes, 
     return 0;
 }
 
+// ------------------------------------------------------------------ InputProj
+// thread == pixel, COUT accumulators; weights (bf16-rounded) broadcast from shared memory; one 2 x COUT-byte row store
+template <int COUT>
+__global__ void __launch_bounds__(128) input_proj_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ out, int B, int H, int W, int Cin, float slope) {
+    __shared__ __align__(16) float ws[4 * 9 * COUT];
+    __shared__ float bs[COUT];
+    for (int i = threadIdx.x; i < Cin * 9 * COUT; i += 128) {     // ws[(ci * 9 + tap) * COUT + co]
+        const int co = i % COUT, t = i / COUT;
+        ws[i] = Act<__nv_bfloat16>::round(w[co * Cin * 9 + t]);
+    }
+    for (int i = threadIdx.x; i < COUT; i += 128) bs[i] = Act<__nv_bfloat16>::round(bias[i]);
+    __syncthreads();
+    const long long p = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+    const long long total = static_cast<long long>(B) * H * W;
+    if (p >= total) return;
+    const int xx = static_cast<int>(p % W);
+    const int yy = static_cast<int>((p / W) % H);
+    const long long b = p / (static_cast<long long>(W) * H);
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+        const float* plane = x + (b * Cin + ci) * static_cast<long long>(H) * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int y2 = yy + ky - 1, x2 = xx + kx - 1;
+                float v = 0.f;
+                if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) v = Act<__nv_bfloat16>::round(plane[static_cast<long long>(y2) * W + x2]);
+                const float4* wr = reinterpret_cast<const float4*>(ws + (ci * 9 + ky * 3 + kx) * COUT);
+#pragma unroll
+                for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                    const float4 w4 = wr[c4];
+                    acc[4 * c4] = fmaf(v, w4.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(v, w4.y, acc[4 * c4 + 1]);
+                    acc[4 * c4 + 2] = fmaf(v, w4.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(v, w4.w, acc[4 * c4 + 3]);
+                }
+            }
+    }
+    uint4* orow = reinterpret_cast<uint4*>(out + p * COUT);
+#pragma unroll
+    for (int c8 = 0; c8 < COUT / 8; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float v2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = c8 * 8 + 2 * h + e;
+                float t = Act<__nv_bfloat16>::round(Act<__nv_bfloat16>::round(acc[c]) + bs[c]);      // conv -> bf16, + bias -> bf16
+                v2[e] = t >= 0.f ? t : t * slope;                                                      // LeakyReLU -> bf16 (by the pack)
+            }
+            __nv_bfloat162 hh = __floats2bfloat162_rn(v2[0], v2[1]);
+            pk[h] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        orow[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+int input_proj_fwd_bf16(const LewinInputProjArgs* a, cudaStream_t stream) {
+    if (!a || !a->x || !a->weight || !a->bias || !a->out) return LEWIN_E_NULL;
+    if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->Cin <= 0 || a->Cin > 4 || (a->Cout != 32 && a->Cout != 64)) return LEWIN_E_SHAPE;
+    if (!aligned16(a->out)) return LEWIN_E_ALIGN;
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    const long long total = static_cast<long long>(a->B) * a->H * a->W;
+    const unsigned grid = static_cast<unsigned>((total + 127) / 128);
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a->out);
+    if (a->Cout == 32) input_proj_kernel<32><<<grid, 128, 0, stream>>>(a->x, a->weight, a->bias, out, a->B, a->H, a->W, a->Cin, a->negative_slope);
+    else input_proj_kernel<64><<<grid, 128, 0, stream>>>(a->x, a->weight, a->bias, out, a->B, a->H, a->W, a->Cin, a->negative_slope);
+    CK(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -543,6 +619,10 @@ int lewin_upsample_fwd_bf16(const LewinUpsampleFwdArgs* a, void* ws, size_t n, l
     return upsample_fwd_bf16(a, ws, n, reinterpret_cast<cudaStream_t>(s));
 }
 size_t lewin_upsample_fwd_workspace_bytes(const LewinUpsampleFwdArgs* a, int) { return a ? upsample_ws(a) : 0; }
+
+int lewin_input_proj_fwd_bf16(const LewinInputProjArgs* a, lewin_stream_t s) {
+    return input_proj_fwd_bf16(a, reinterpret_cast<cudaStream_t>(s));
+}
 
 int lewin_abi_version(void) { return LEWIN_ABI_VERSION; }
 long long lewin_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

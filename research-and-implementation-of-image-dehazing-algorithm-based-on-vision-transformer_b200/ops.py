@@ -333,3 +333,21 @@ def lewin_upsample(x, weight, bias, *, B, H, W, out=None):
     with torch.cuda.device(dev):
         _lib.check(lib.lewin_upsample_fwd_bf16(a, ws.data_ptr(), ws.numel(), _stream()), "lewin_upsample_fwd_bf16")
     return out
+
+
+def lewin_input_proj(x, weight, bias, negative_slope=0.01):
+    """InputProj.forward (My_model_1.py:659-682) under bf16 autocast: x [B, Cin, H, W] fp32 CUDA -> tokens [B, H*W, Cout] bf16,
+    convolution + bias + LeakyReLU in one kernel."""
+    lib = _lib.load()
+    if not (x.is_cuda and x.dtype == torch.float32):
+        raise RuntimeError("lewin_input_proj takes an fp32 CUDA image")
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    Cout = weight.shape[0]
+    out = torch.empty((B, H * W, Cout), dtype=torch.bfloat16, device=x.device)
+    w_, b_ = _f32c(weight), _f32c(bias)
+    a = _lib.LewinInputProjArgs(B=B, H=H, W=W, Cin=Cin, Cout=Cout, negative_slope=float(negative_slope), reserved0=0, reserved1=0,
+                                x=_ptr(x), weight=_ptr(w_), bias=_ptr(b_), out=_ptr(out))
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lewin_input_proj_fwd_bf16(a, _stream()), "lewin_input_proj_fwd_bf16")
+    return out

@@ -37,6 +37,16 @@ def _nchw_to_tokens(y):
     return y.permute(0, 2, 3, 1).reshape(B, H * W, C)
 
 
+def _autocast_bf16():
+    """bf16 CUDA autocast active (torch >= 2.4 API, older fallback)."""
+    if not torch.is_autocast_enabled():
+        return False
+    try:
+        return torch.get_autocast_dtype("cuda") == torch.bfloat16
+    except (AttributeError, TypeError):
+        return torch.get_autocast_gpu_dtype() == torch.bfloat16
+
+
 def _cl(w):
     return w.contiguous(memory_format=torch.channels_last)
 
@@ -71,7 +81,7 @@ class Upsample(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or d.weight.requires_grad):
             return False
         xb = x if x.dtype == torch.bfloat16 else None
-        if xb is None and x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+        if xb is None and x.is_cuda and _autocast_bf16():
             xb = x.to(torch.bfloat16)
         if xb is None or not ops.upsample_supported(xb, self.in_channel, self.out_channel, x.shape[0] * x.shape[1]):
             return False
@@ -109,7 +119,15 @@ class InputProj(nn.Module):
         self.in_channel, self.out_channel = in_channel, out_channel
 
     def forward(self, x):
-        x = _nchw_to_tokens(self.proj(x.contiguous(memory_format=torch.channels_last)))
+        conv, act = self.proj[0], self.proj[1]
+        fast = (x.is_cuda and x.dtype == torch.float32 and _autocast_bf16() and isinstance(act, nn.LeakyReLU) and
+                conv.in_channels <= 4 and conv.out_channels in (32, 64) and conv.stride == (1, 1) and
+                not (torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad)))
+        if fast:        # bf16 inference: convolution + bias + LeakyReLU in one kernel (lewin_input_proj_fwd_bf16)
+            from . import ops
+            x = ops.lewin_input_proj(x, conv.weight, conv.bias, act.negative_slope)
+        else:
+            x = _nchw_to_tokens(self.proj(x.contiguous(memory_format=torch.channels_last)))
         return self.norm(x) if self.norm is not None else x
 
 

@@ -144,3 +144,20 @@ def test_upsample_gemm_matches_conv_transpose(Cin, Cout, B, hw):
         cat = up(x, skip)
     assert cat.shape == (B, 4 * hw * hw, 2 * Cout)
     assert torch.equal(cat[..., :Cout], y) and torch.equal(cat[..., Cout:], skip)
+
+
+def test_input_proj_fused_matches_autocast_reference():
+    """InputProj (My_model_1.py:659-682): fused conv3x3 + bias + LeakyReLU kernel vs the stock torch path under bf16 autocast."""
+    import lewin_b200 as L
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    ip = L.uformer.InputProj(in_channel=3, out_channel=32, kernel_size=3, stride=1, act_layer=torch.nn.LeakyReLU).to(dev)
+    x = torch.rand(5, 3, 40, 24, device=dev)
+    with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+        y = ip(x)                                                           # fused kernel
+        ref = ip.proj(x.contiguous(memory_format=torch.channels_last))      # cuDNN + bias + LeakyReLU
+    ref = ref.permute(0, 2, 3, 1).reshape(5, 40 * 24, 32)
+    assert y.dtype == torch.bfloat16 and y.shape == ref.shape
+    err = (y.float() - ref.float()).abs()
+    tol = 2.0 ** -7 * ref.float().abs().clamp(min=0.25)
+    assert (err <= tol).all(), float((err / tol).max())

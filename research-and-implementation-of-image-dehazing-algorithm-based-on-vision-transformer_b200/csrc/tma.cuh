@@ -25,7 +25,8 @@ inline EncodeTiledFn encode_fn() {
 
 // bf16 channel-last map [B, H, W, C] viewed as a 4-D tensor (C innermost); box = [1, box_h, box_w, box_c], no swizzle,
 // out-of-bounds elements are filled with zeros (== the convolution's zero padding).
-inline bool make_nhwc_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, int box_h, int box_w, int box_c) {
+inline bool make_nhwc_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, int box_h, int box_w, int box_c,
+                           bool swizzle128 = false) {          // swizzle128: box_c * 2 must be 128 bytes, destination 1024-byte aligned
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
@@ -34,7 +35,7 @@ inline bool make_nhwc_bf16(CUtensorMap* map, const void* base, int B, int H, int
     const cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // row-major bf16 matrix [rows, cols] (row stride ld elements), box = [box_rows x 64 columns] delivered in the K-major

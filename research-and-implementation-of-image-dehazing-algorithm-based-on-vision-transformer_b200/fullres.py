@@ -156,3 +156,49 @@ def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=
         out = torch.cat(parts, 0)
     restored = from_tiles(out, L, ps)
     return restored[:, :, :H, :W].clamp(0, 1)
+
+
+class StreamingDehazer:
+    """Streams HOST images through a device dehazing function with the copies off the compute stream.
+
+    test_long_GPU.py:74-120 restores a folder of images one after the other: load (host) -> cuda -> model -> cpu -> save.
+    Here the host->device copy of image i+1 and the device->host copy of result i-1 run on two side streams while image i
+    is computed (double-buffered device images, event-ordered; every image is still copied in and its result copied out
+    in full), so a sequence runs at max(compute, copy) per image instead of their sum.  `fn(device_image) -> restored`
+    is e.g. ``lambda x: dehaze_tiled(model, x, graphed=g)``; host tensors should be pinned."""
+
+    def __init__(self, fn, shape, device, depth=2, dtype=torch.float32):
+        self.fn, self.dev, self.depth = fn, device, depth
+        self.s_in, self.s_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        self.x = [torch.empty(shape, device=device, dtype=dtype) for _ in range(depth)]
+        self.y = [torch.empty(shape, device=device, dtype=dtype) for _ in range(depth)]
+        mk = lambda: [torch.cuda.Event() for _ in range(depth)]
+        self.loaded, self.consumed, self.drained = mk(), mk(), mk()
+        self.n = 0
+
+    @torch.no_grad()
+    def submit(self, img_host, out_host):
+        """Enqueue one image; `out_host` is valid after `flush()` (or after a later submit that reuses its slot)."""
+        i, first = self.n % self.depth, self.n < self.depth
+        self.n += 1
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.s_in):
+            if not first:
+                self.s_in.wait_event(self.consumed[i])       # the compute that read this slot has finished
+            self.x[i].copy_(img_host, non_blocking=True)
+            self.loaded[i].record(self.s_in)
+        cur.wait_event(self.loaded[i])
+        if not first:
+            cur.wait_event(self.drained[i])                  # the previous result of this slot has left the device
+        self.y[i].copy_(self.fn(self.x[i]))
+        self.consumed[i].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.consumed[i])
+            out_host.copy_(self.y[i], non_blocking=True)
+            self.drained[i].record(self.s_out)
+
+    def flush(self):
+        """Make the current stream wait for every outstanding device->host copy (then synchronise or record an event)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for i in range(min(self.n, self.depth)):
+            cur.wait_event(self.drained[i])

@@ -117,3 +117,40 @@ def test_uformer_forward_matches_reference_golden_f32(golden_dir):
     assert np.median(e) < 1e-4
     assert (e > 1e-3).mean() < 0.02
     assert psnr > 50.0
+    # north_star: dehazed-image PSNR must agree within 0.01 dB.  Score both outputs against the same target image (the
+    # model's input stands in for the ground truth of the synthetic fixture).
+    def psnr_to(a, t):
+        return 10 * np.log10(1.0 / float(((np.clip(a, 0, 1) - t) ** 2).mean()))
+    p_ours, p_ref = psnr_to(y.cpu().numpy(), z["x"]), psnr_to(z["y"], z["x"])
+    print(f"image PSNR vs target: ours {p_ours:.4f} dB, reference {p_ref:.4f} dB")
+    assert abs(p_ours - p_ref) < 0.01
+    # bf16 autocast path (BASELINE's compute dtype) on the same fixture
+    with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+        yb = model(x, index_samples=idx).float()
+    p_bf16 = psnr_to(yb.cpu().numpy(), z["x"])
+    print(f"image PSNR vs target: bf16 {p_bf16:.4f} dB")
+    assert abs(p_bf16 - p_ref) < 0.01
+
+
+def test_streaming_dehazer_matches_direct_calls():
+    """fullres.StreamingDehazer (side-stream H2D / D2H, double-buffered) returns, image for image, exactly what the direct
+    dehaze_tiled call returns; 5 different images through 2 slots exercise slot reuse in both directions."""
+    import lewin_b200 as L
+    from lewin_b200 import fullres
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    model = L.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff").to(dev).eval()
+    idx = model.draw_index_samples()
+    H, W = 200, 300                                           # canvas 384^2 = 9 tiles
+    g = torch.Generator().manual_seed(6)
+    imgs = [torch.rand(1, 3, H, W, generator=g).pin_memory() for _ in range(5)]
+    outs = [torch.empty(1, 3, H, W).pin_memory() for _ in range(5)]
+    fn = lambda x: fullres.dehaze_tiled(model, x, ps=128, index_samples=idx)
+    pipe = fullres.StreamingDehazer(fn, (1, 3, H, W), dev)
+    for a, b in zip(imgs, outs):
+        pipe.submit(a, b)
+    pipe.flush()
+    torch.cuda.synchronize()
+    for a, b in zip(imgs, outs):
+        ref = fn(a.to(dev)).cpu()
+        assert torch.equal(ref, b)

@@ -332,6 +332,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     step_e2e()
+    step_e2e_serial()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -379,7 +380,10 @@ def main():
             ts = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(ts)
             torch.cuda.empty_cache()
-            train, _ = ts.run(batch=32, steps=5, warmup=3, dtype="bf16")
+            train, _ = ts.run(batch=32, steps=5, warmup=3, dtype="bf16", contrast=True)      # config 2 as BASELINE states it
+            torch.cuda.empty_cache()
+            t2, _ = ts.run(batch=32, steps=5, warmup=3, dtype="bf16", contrast=False)       # the LeWin path alone
+            train["without_contrast"] = {k: t2[k] for k in ("step_ms", "patches_per_s", "loss", "loss_terms", "launch")}
         except Exception as e:      # the headline line must survive a failure of the secondary measurement
             train = {"error": repr(e)[:300]}
     lt = torch.tensor([float(launches)], device=dev)

@@ -78,17 +78,39 @@ def main():
                         torch.cuda.synchronize()
                         return e0.elapsed_time(e1) / args.iters * 1e3
 
-                    f_us, fb_us = timeit(fwd), timeit(fwd_bwd)
+                    f_eager, fb_eager = timeit(fwd), timeit(fwd_bwd)
+                    # device time without the host's launch gaps (~110 us of Python / ctypes per block at the small sizes):
+                    # the same call sequences replayed as CUDA graphs, as bench.py's block microbench and the training step do
+                    launch = "cuda-graph replay"
+                    try:
+                        side = torch.cuda.Stream(device=dev)
+                        side.wait_stream(torch.cuda.current_stream(dev))
+                        with torch.cuda.stream(side):
+                            fwd(); fwd_bwd()
+                        torch.cuda.current_stream(dev).wait_stream(side)
+                        torch.cuda.synchronize()
+                        for t in [x] + list(p.values()) + list(q.values()):
+                            t.grad = None
+                        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g1):
+                            y_static = fwd()
+                        with torch.cuda.graph(g2):
+                            fwd_bwd()
+                        f_us, fb_us = timeit(g1.replay), timeit(g2.replay)
+                        del g1, g2, y_static
+                    except Exception as e:
+                        f_us, fb_us, launch = f_eager, fb_eager, "eager (graph capture failed: %s)" % repr(e)[:80]
                     tokens = windows * 64
                     s = 2 if dtype == "bf16" else 4
                     flops = tokens * (24 * C * C + 222 * C)
                     ideal_us = max(flops / (tf * 1e12), tokens * 4 * C * s / (hbm * 1e9)) * 1e6
                     rows.append(dict(dtype=dtype, heads=heads, C=C, windows=windows, H=H, W=W, shift=shift, fwd_us=f_us,
-                                     fwd_bwd_us=fb_us, fwd_tflops=flops / f_us / 1e6, ideal_fwd_us=ideal_us))
+                                     fwd_bwd_us=fb_us, fwd_us_eager=f_eager, fwd_bwd_us_eager=fb_eager, launch=launch, fwd_tflops=flops / f_us / 1e6, ideal_fwd_us=ideal_us))
                     print(f"{dtype} heads={heads:2d} C={C:3d} windows={windows:4d} ({H}x{W}) shift={shift}: fwd {f_us:8.1f} us  "
-                          f"fwd+bwd {fb_us:8.1f} us  {flops / f_us / 1e6:7.1f} TFLOP/s fwd  (fused-ideal {ideal_us:6.1f} us)", flush=True)
+                          f"fwd+bwd {fb_us:8.1f} us (eager {f_eager:7.1f} / {fb_eager:7.1f})  {flops / f_us / 1e6:7.1f} TFLOP/s fwd  "
+                          f"(fused-ideal {ideal_us:6.1f} us)", flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    json.dump(dict(config="BASELINE config 5", launch="eager python launches through the C ABI (includes host launch gaps at the small sizes)",
+    json.dump(dict(config="BASELINE config 5", launch="CUDA-graph replay of the C-ABI call sequence (eager python launch numbers alongside)",
                    iters=args.iters, rows=rows), open(args.out, "w"), indent=1)
 
 

@@ -1,7 +1,8 @@
 """BASELINE configs 2 / 4: one Uformer_ProbSparse training step (batch 32 x 3 x 128 x 128 per GPU, bf16 autocast,
-Charbonnier loss eps 1e-3, AdamW 2e-4 / wd 0.02; My_train.py:221-250) on the sm_100a LeWin ops; under torchrun the
-model is wrapped with parallel.wrap_ddp (NCCL gradient all-reduce).  The VGG19 contrastive term of the reference loss
-(My_CR.py) is a SURVEY section 8(f) 'next' row and is NOT included.  Prints one JSON line (rank 0)."""
+restored = clamp(model(input), 0, 1), loss = Charbonnier(eps 1e-3) + ContrastLoss(VGG19, random init: no weight file
+offline), AdamW 2e-4 / wd 0.02; My_train.py:221-250) on the sm_100a LeWin ops; under torchrun the model is wrapped with
+parallel.wrap_ddp (NCCL gradient all-reduce).  `contrast=False` drops the VGG term (the LeWin path alone).
+Prints one JSON line (rank 0)."""
 import json
 import os
 import sys
@@ -16,7 +17,7 @@ def charbonnier(x, y, eps=1e-3):
     return torch.mean(torch.sqrt(d * d + eps * eps))
 
 
-def run(batch=32, steps=10, warmup=3, dtype="bf16", graph=True):
+def run(batch=32, steps=10, warmup=3, dtype="bf16", graph=True, contrast=True):
     global torch
     import torch
     import torch.distributed as dist
@@ -38,12 +39,24 @@ def run(batch=32, steps=10, warmup=3, dtype="bf16", graph=True):
     y = torch.rand(batch, 3, 128, 128, generator=g).to(dev)
 
     idx_static = model.draw_index_samples().to(dev, dtype=torch.int32)       # refreshed before every step (attn.py:91 draws)
+    crit_cr = None
+    if contrast:
+        from lewin_b200.losses import ContrastLoss
+        torch.manual_seed(0)
+        crit_cr = ContrastLoss(ablation=False, pretrained=False, device=dev)  # frozen VGG19, seed 0
+
+    def loss_fn():
+        # My_train.py:224-238: forward, clamp and both criteria inside autocast; w_loss_* = 1 (options.py:16-17)
+        with torch.autocast("cuda", torch.bfloat16, enabled=(dtype == "bf16")):
+            restored = torch.clamp(net(x, index_samples=idx_static), 0, 1)
+            loss = charbonnier(restored, y)
+            if crit_cr is not None:
+                loss = loss + crit_cr(restored, y, x)[0]
+        return loss
 
     def step():
         opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", torch.bfloat16, enabled=(dtype == "bf16")):
-            out = net(x, index_samples=idx_static)
-        loss = charbonnier(out, y)
+        loss = loss_fn()
         loss.backward()
         opt.step()
         return loss
@@ -65,9 +78,7 @@ def run(batch=32, steps=10, warmup=3, dtype="bf16", graph=True):
             gph = torch.cuda.CUDAGraph()
             opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(gph):
-                with torch.autocast("cuda", torch.bfloat16, enabled=(dtype == "bf16")):
-                    out_s = net(x, index_samples=idx_static)
-                loss_s = charbonnier(out_s, y)
+                loss_s = loss_fn()
                 loss_s.backward()
                 opt.step()
 
@@ -95,7 +106,9 @@ def run(batch=32, steps=10, warmup=3, dtype="bf16", graph=True):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     res = dict(step_ms=float(ms.item()), patches_per_s=batch * world / (float(ms.item()) / 1e3), batch_per_gpu=batch, n_gpus=world,
-               dtype=dtype, loss=float(loss.item()), loss_terms="Charbonnier (VGG contrastive term not included)",
+               dtype=dtype, loss=float(loss.item()),
+               loss_terms="Charbonnier + ContrastLoss (VGG19 random init, p / n passes batched under no_grad, channels-last bf16)"
+               if contrast else "Charbonnier only",
                optimizer="AdamW(2e-4, wd 0.02)", parallelism="ddp" if world > 1 else "single", launch=mode)
     return res, rank
 

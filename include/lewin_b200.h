@@ -39,7 +39,7 @@ extern "C" {
 typedef struct CUstream_st* lewin_stream_t; /* == cudaStream_t */
 typedef struct CUevent_st*  lewin_event_t;  /* == cudaEvent_t  */
 
-#define LEWIN_ABI_VERSION 1
+#define LEWIN_ABI_VERSION 2
 
 /* error codes (negative) */
 #define LEWIN_E_NULL      (-1)  /* a required pointer is NULL */
@@ -106,6 +106,12 @@ typedef struct {
     /* optional per-kernel timing: caller-owned events, 2 per kernel (begin, end) recorded on `stream`
      * around each launch, in the order LEWIN_ATTN_K_*; NULL = off */
     lewin_event_t* timing;
+
+    /* optional (bf16 calls, C >= 256): the caller's own bf16 images of w_qkv [3C, C] and w_out [C, C] (round-to-nearest
+     * of the fp32 weights).  When both are given the library skips its per-call weight conversion kernels (inference:
+     * the weights are constants, the caller converts once); NULL = convert into the workspace on every call. */
+    const void* w_qkv_bf16;
+    const void* w_out_bf16;
 } LewinAttnFwdArgs;
 
 #define LEWIN_ATTN_K_LNSTATS 0
@@ -180,6 +186,10 @@ typedef struct {
     void* a2;                      /* pre-GELU dwconv output  (only if save_for_backward) */
 
     lewin_event_t* timing;         /* optional, 2 events per kernel in the order LEWIN_LEFF_K_*; NULL = off */
+
+    /* optional (bf16 calls, C >= 256): caller's bf16 images of w1 [hidden, C] and w2 [C, hidden]; see LewinAttnFwdArgs */
+    const void* w1_bf16;
+    const void* w2_bf16;
 } LewinLeffFwdArgs;
 
 #define LEWIN_LEFF_K_LNSTATS 0

@@ -28,6 +28,7 @@ class LewinAttnFwdArgs(C.Structure):
         ("drop_scale", c_ptr),
         ("qkv", c_ptr), ("ctx", c_ptr), ("top", c_ptr),
         ("timing", c_ptr),
+        ("w_qkv_bf16", c_ptr), ("w_out_bf16", c_ptr),
     ]
 
 
@@ -57,6 +58,7 @@ class LewinLeffFwdArgs(C.Structure):
         ("drop_scale", c_ptr),
         ("h1", c_ptr), ("h2", c_ptr), ("a1", c_ptr), ("a2", c_ptr),
         ("timing", c_ptr),
+        ("w1_bf16", c_ptr), ("w2_bf16", c_ptr),
     ]
 
 
@@ -97,7 +99,7 @@ EXPORTS = (
     "lewin_upsample_fwd_bf16", "lewin_upsample_fwd_workspace_bytes", "lewin_input_proj_fwd_bf16",
 )
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 DTYPE_TAG = {"f32": 0, "bf16": 1}
 
 _lib = None

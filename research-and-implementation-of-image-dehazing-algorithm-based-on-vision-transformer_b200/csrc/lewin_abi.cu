@@ -87,7 +87,8 @@ int check_attn(const LewinAttnFwdArgs* a) {
     if (a->windowed && (a->shift != 0 || a->analytic_shift_mask)) return LEWIN_E_SHAPE;
     if (a->mask && a->nW_mask <= 0) return LEWIN_E_SHAPE;
     if (a->mask && ((a->B * (a->H / 8) * (a->W / 8)) % a->nW_mask)) return LEWIN_E_SHAPE;
-    const void* ps[] = {a->x, a->y, a->ln_w, a->ln_b, a->w_qkv, a->b_qkv, a->w_out, a->b_out, a->qkv, a->ctx, a->mask};
+    const void* ps[] = {a->x, a->y, a->ln_w, a->ln_b, a->w_qkv, a->b_qkv, a->w_out, a->b_out, a->qkv, a->ctx, a->mask,
+                        a->w_qkv_bf16, a->w_out_bf16};
     for (const void* p : ps)
         if (p && !aligned16(p)) return LEWIN_E_ALIGN;
     return 0;
@@ -144,8 +145,13 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
             xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
             wqkv_b = reinterpret_cast<__nv_bfloat16*>(q);
             wout_b = wqkv_b + static_cast<size_t>(3) * C * C;
-            CK(launch_convert_w(a->w_qkv, wqkv_b, static_cast<long long>(3) * C * C, stream));
-            CK(launch_convert_w(a->w_out, wout_b, static_cast<long long>(C) * C, stream));
+            if (a->w_qkv_bf16 && a->w_out_bf16) {        // caller-converted constants (inference): no per-call conversion
+                wqkv_b = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a->w_qkv_bf16));
+                wout_b = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a->w_out_bf16));
+            } else {
+                CK(launch_convert_w(a->w_qkv, wqkv_b, static_cast<long long>(3) * C * C, stream));
+                CK(launch_convert_w(a->w_out, wout_b, static_cast<long long>(C) * C, stream));
+            }
         }
     }
     {   // q | k | v projections (attn.py:420-422) with LN1 + roll + window_partition as the A prologue
@@ -283,7 +289,8 @@ int check_leff(const LewinLeffFwdArgs* a) {
     if (a->save_for_backward && (!a->a1 || !a->a2)) return LEWIN_E_NULL;
     if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->hidden <= 0) return LEWIN_E_SHAPE;
     if (a->C % 32 || a->hidden % 32) return LEWIN_E_SHAPE;
-    const void* ps[] = {a->y, a->out, a->ln_w, a->ln_b, a->w1, a->b1, a->w_dw, a->b_dw, a->w2, a->b2, a->h1, a->h2, a->a1, a->a2};
+    const void* ps[] = {a->y, a->out, a->ln_w, a->ln_b, a->w1, a->b1, a->w_dw, a->b_dw, a->w2, a->b2, a->h1, a->h2, a->a1, a->a2,
+                        a->w1_bf16, a->w2_bf16};
     for (const void* p : ps)
         if (p && !aligned16(p)) return LEWIN_E_ALIGN;
     return 0;
@@ -359,8 +366,13 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
             xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
             w1b = reinterpret_cast<__nv_bfloat16*>(q);
             w2b = w1b + static_cast<size_t>(C) * Ch;
-            CK(launch_convert_w(a->w1, w1b, static_cast<long long>(C) * Ch, stream));
-            CK(launch_convert_w(a->w2, w2b, static_cast<long long>(C) * Ch, stream));
+            if (a->w1_bf16 && a->w2_bf16) {
+                w1b = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a->w1_bf16));
+                w2b = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(a->w2_bf16));
+            } else {
+                CK(launch_convert_w(a->w1, w1b, static_cast<long long>(C) * Ch, stream));
+                CK(launch_convert_w(a->w2, w2b, static_cast<long long>(C) * Ch, stream));
+            }
         }
     }
     if (plan.ln_stats) {

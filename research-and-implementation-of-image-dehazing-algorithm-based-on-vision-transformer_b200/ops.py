@@ -11,6 +11,9 @@ lewin_leff(y, ...)   LeFF half (My_model_1.py:873) or, with ``fused=False``, LeF
 """
 from __future__ import annotations
 
+import os
+import weakref
+
 import torch
 
 from . import _lib
@@ -113,6 +116,25 @@ class KernelTimer:
         return out
 
 
+_BF16_IMAGES = {}
+_WEIGHT_IMAGES_ON = os.environ.get("LEWIN_NO_WEIGHT_CACHE", "0") != "1"      # knob for scripts/diff_paths.py
+
+
+def _bf16_image(w):
+    """bf16 image of a constant fp32 weight for the C >= 256 GEMMs (the ABI's optional w*_bf16 fields).  Converted once and
+    reused while the tensor object, its storage and its version counter are unchanged (inference); any in-place update
+    (optimizer step, load_state_dict) bumps `_version` and the image is rebuilt."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+    ent = _BF16_IMAGES.get(key)
+    if ent is not None and ent[0]() is w:
+        return ent[1]
+    if len(_BF16_IMAGES) > 1024:
+        _BF16_IMAGES.clear()
+    img = w.detach().to(torch.bfloat16).contiguous()
+    _BF16_IMAGES[key] = (weakref.ref(w), img)
+    return img
+
+
 class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
@@ -140,6 +162,9 @@ class _AttnFn(torch.autograd.Function):
             w_out=_ptr(w_out_), b_out=_ptr(b_out_), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
             index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
             qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
+        if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:      # constants of an inference call: convert once
+            wq_b, wo_b = _bf16_image(w_qkv_), _bf16_image(w_out_)
+            a.w_qkv_bf16, a.w_out_bf16 = _ptr(wq_b), _ptr(wo_b)
         if KernelTimer.active is not None:
             mask = lib.lewin_attn_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
             tim = KernelTimer.active.events_for("attn", dict(tokens=tokens, C=C, nH=nH, dtype=dt),
@@ -219,6 +244,9 @@ class _LeffFn(torch.autograd.Function):
             y=_ptr(y), out=_ptr(out), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w1=_ptr(w1_), b1=_ptr(b1_),
             w_dw=_ptr(wdw_), b_dw=_ptr(bdw_), w2=_ptr(w2_), b2=_ptr(b2_), drop_scale=_ptr(ds_),
             h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
+        if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:
+            w1_b, w2_b = _bf16_image(w1_), _bf16_image(w2_)
+            a.w1_bf16, a.w2_bf16 = _ptr(w1_b), _ptr(w2_b)
         if KernelTimer.active is not None:
             mask = lib.lewin_leff_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
             tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt),

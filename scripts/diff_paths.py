@@ -77,7 +77,7 @@ def main():
     import torch
     out_dir = "/tmp/diff_paths"
     os.makedirs(out_dir, exist_ok=True)
-    variants = {"old": {"LEWIN_NO_WS_GEMM": "1", "LEWIN_NO_STREAM_DWCONV": "1", "LEWIN_NO_CORE_V3": "1"}, "new": {}, "oldcore": {"LEWIN_NO_CORE_V3": "1"}, "notma": {"LEWIN_NO_TMA": "1"}, "notmastore": {"LEWIN_NO_TMA_STORE": "1"}, "mmadw": {"LEWIN_MMA_DWCONV": "1"},
+    variants = {"old": {"LEWIN_NO_WS_GEMM": "1", "LEWIN_NO_STREAM_DWCONV": "1", "LEWIN_NO_CORE_V3": "1"}, "new": {}, "oldcore": {"LEWIN_NO_CORE_V3": "1"}, "notma": {"LEWIN_NO_TMA": "1"}, "notmastore": {"LEWIN_NO_TMA_STORE": "1"}, "mmadw": {"LEWIN_MMA_DWCONV": "1"}, "nowcache": {"LEWIN_NO_WEIGHT_CACHE": "1"},
                 "old_unfused": {"LEWIN_NO_WS_GEMM": "1", "LEWIN_NO_FUSED_LEFF": "1", "LEWIN_NO_STREAM_DWCONV": "1"}}
     sel = sys.argv[1:] or list(variants)
     for timed in ("0", "1"):

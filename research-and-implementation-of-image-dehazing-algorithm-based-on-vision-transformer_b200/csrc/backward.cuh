@@ -803,7 +803,24 @@ inline size_t attn_bwd_ws(const LewinAttnBwdArgs* a, int dtype) {
     const size_t es = dtype == LEWIN_DTYPE_BF16 ? 2 : 4;
     const size_t C = f.C;
     return 2 * bw_align(tokens * 4) + bw_align(tokens * C * es) + bw_align(tokens * 3 * C * es) +
-           bw_align(tokens * C * es) + bw_align(C * C * 4) + bw_align(3 * C * C * 4);
+           bw_align(tokens * C * es) + bw_align(C * C * 4) + bw_align(3 * C * C * 4) +
+           (dtype == LEWIN_DTYPE_BF16 ? bw_align(3 * C * C * 2) : 0);      // bf16 image of W_qkv^T for the streamed-W GEMM
+}
+
+// Data-gradient GEMM dX = dY . W (W^T staged as the [N, K] operand).  bf16 at the C >= 256 levels: the forward's
+// warp-specialised streamed-W tcgen05 kernel (TMA operands, 3x the first-generation kernel's rate) whenever the operand
+// needs no row gather / row scale; `wT_bf16` is workspace for the bf16 image of the transposed weight.
+template <typename T>
+inline cudaError_t launch_dgrad_gemm(const GemmArgs<T>& g, __nv_bfloat16* wT_bf16, int sms, cudaStream_t st) {
+    if constexpr (Act<T>::kIsBf16) {
+        static const bool on = [] { const char* e = getenv("LEWIN_NO_WSS_DGRAD"); return !(e && e[0] == '1'); }();
+        if (on && wT_bf16 && g.K >= 256 && g.N >= 256 && ws::wss_supported(g)) {
+            cudaError_t e = launch_convert_w(g.Wt, wT_bf16, static_cast<long long>(g.N) * g.K, st);
+            if (e != cudaSuccess) return e;
+            return ws::wss_launch<EPI_BIAS>(g, wT_bf16, sms, st);
+        }
+    }
+    return launch_gemm_any<T, EPI_BIAS>(g, st);
 }
 
 template <typename T>
@@ -829,7 +846,8 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     T* dqkv = reinterpret_cast<T*>(p); p += bw_align(tokens * 3 * C * sizeof(T));
     T* dxh = reinterpret_cast<T*>(p); p += bw_align(tokens * C * sizeof(T));
     float* woT = reinterpret_cast<float*>(p); p += bw_align(static_cast<size_t>(C) * C * 4);
-    float* wqkvT = reinterpret_cast<float*>(p);
+    float* wqkvT = reinterpret_cast<float*>(p); p += bw_align(static_cast<size_t>(3) * C * C * 4);
+    __nv_bfloat16* wqkvT_b = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
 
     const T* x = static_cast<const T*>(f.x);
     const T* dy = static_cast<const T*>(a->dy);
@@ -881,7 +899,7 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.A = dqkv; g.lda = 3 * C; g.Wt = wqkvT; g.bias = nullptr;
         g.Y = f.windowed ? static_cast<T*>(a->dx) : dxh; g.ldy = C; g.M = tokens; g.N = C; g.K = 3 * C;
         g.mapA = 0; g.mapY = mapped; g.map = map; g.tokens_per_image = tpi;
-        BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
+        BCK(launch_dgrad_gemm<T>(g, wqkvT_b, sms, st));
     }
     if (!f.windowed)   // dx = dy + LN1_bwd(dxh)
         BCK(launch_ln_bwd<T>(dxh, x, dy, static_cast<T*>(a->dx), f.ln_w, a->d_ln_w, a->d_ln_b, tokens, C, sms, st));
@@ -893,7 +911,8 @@ inline size_t leff_bwd_ws(const LewinLeffBwdArgs* a, int dtype) {
     const size_t tokens = static_cast<size_t>(f.B) * f.H * f.W;
     const size_t es = dtype == LEWIN_DTYPE_BF16 ? 2 : 4;
     const size_t C = f.C, Ch = f.hidden;
-    return 2 * bw_align(tokens * 4) + 3 * bw_align(tokens * Ch * es) + bw_align(tokens * C * es) + 2 * bw_align(C * Ch * 4);
+    return 2 * bw_align(tokens * 4) + 3 * bw_align(tokens * Ch * es) + bw_align(tokens * C * es) + 2 * bw_align(C * Ch * 4) +
+           (dtype == LEWIN_DTYPE_BF16 ? 2 * bw_align(C * Ch * 2) : 0);     // bf16 images of W2^T, W1^T
 }
 
 template <typename T>
@@ -919,7 +938,9 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     T* da2 = reinterpret_cast<T*>(p); p += bw_align(tokens * Ch * sizeof(T));
     T* dz = reinterpret_cast<T*>(p); p += bw_align(tokens * C * sizeof(T));
     float* w2T = reinterpret_cast<float*>(p); p += bw_align(static_cast<size_t>(C) * Ch * 4);
-    float* w1T = reinterpret_cast<float*>(p);
+    float* w1T = reinterpret_cast<float*>(p); p += bw_align(static_cast<size_t>(C) * Ch * 4);
+    __nv_bfloat16* w2T_b = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
+    __nv_bfloat16* w1T_b = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p + bw_align(static_cast<size_t>(C) * Ch * 2)) : nullptr;
 
     const T* y = static_cast<const T*>(f.y);
     const T* dout = static_cast<const T*>(a->dout);
@@ -941,7 +962,7 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.A = dout; g.lda = C; g.Wt = w2T; g.bias = nullptr;
         g.Y = dh2; g.ldy = Ch; g.M = tokens; g.N = Ch; g.K = C;
         g.tokens_per_image = tpi; g.a_row_scale = dscale;
-        BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
+        BCK(launch_dgrad_gemm<T>(g, w2T_b, sms, st));          // streamed-W kernel when no DropPath row scale is active
     }
     // depthwise conv backward: da1 = conv^T(dh2 * gelu'(a2)) * gelu'(a1); dWdw, dbdw
     {
@@ -968,7 +989,7 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.A = da1; g.lda = Ch; g.Wt = w1T; g.bias = nullptr;
         g.Y = f.fused ? dz : static_cast<T*>(a->dy); g.ldy = C; g.M = tokens; g.N = C; g.K = Ch;
         g.tokens_per_image = tpi;
-        BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
+        BCK(launch_dgrad_gemm<T>(g, w1T_b, sms, st));
     }
     if (f.fused)   // dy = dout + LN2_bwd(dz)
         BCK(launch_ln_bwd<T>(dz, y, dout, static_cast<T*>(a->dy), f.ln_w, a->d_ln_w, a->d_ln_b, tokens, C, sms, st));

@@ -7,7 +7,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-CASES = [(32, 1, 2, 32, 32, 4), (64, 2, 2, 32, 32, 4), (128, 4, 2, 32, 32, 4), (256, 8, 2, 16, 16, 4), (64, 2, 32, 128, 128, 4), (128, 4, 32, 64, 64, 4), (32, 1, 32, 128, 128, 4)]
+CASES = [(32, 1, 2, 32, 32, 4), (64, 2, 2, 32, 32, 4), (128, 4, 2, 32, 32, 4), (256, 8, 2, 16, 16, 4), (512, 16, 3, 16, 16, 4),
+         (64, 2, 32, 128, 128, 4), (128, 4, 32, 64, 64, 4), (32, 1, 32, 128, 128, 4), (256, 8, 32, 32, 32, 4), (512, 16, 32, 16, 16, 4)]
 
 
 def child(tag, out_dir):

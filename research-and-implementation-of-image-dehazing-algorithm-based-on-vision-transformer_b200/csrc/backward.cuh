@@ -804,20 +804,62 @@ inline size_t attn_bwd_ws(const LewinAttnBwdArgs* a, int dtype) {
     const size_t C = f.C;
     return 2 * bw_align(tokens * 4) + bw_align(tokens * C * es) + bw_align(tokens * 3 * C * es) +
            bw_align(tokens * C * es) + bw_align(C * C * 4) + bw_align(3 * C * C * 4) +
-           (dtype == LEWIN_DTYPE_BF16 ? bw_align(3 * C * C * 2) : 0);      // bf16 image of W_qkv^T for the streamed-W GEMM
+           (dtype == LEWIN_DTYPE_BF16 ? bw_align(3 * C * C * 2) + bw_align(C * C * 2) + bw_align(tokens * C * 2) : 0);
+           // bf16: images of W_qkv^T / W_out^T and the scaled, window-ordered dy rows for the streamed-W GEMMs
 }
 
 // Data-gradient GEMM dX = dY . W (W^T staged as the [N, K] operand).  bf16 at the C >= 256 levels: the forward's
 // warp-specialised streamed-W tcgen05 kernel (TMA operands, 3x the first-generation kernel's rate) whenever the operand
 // needs no row gather / row scale; `wT_bf16` is workspace for the bf16 image of the transposed weight.
+// out[m, :] = bf16(scale[row / tokens_per_image] * in[row, :]),  row = window-order source token of m (mapped) or m:
+// the DropPath scale and the roll + window_partition gather of a data-gradient GEMM's A operand as a pre-pass, so that the
+// GEMM itself can stream plain rows by TMA (same rounding point as the in-GEMM prologue of gemm_tc.cuh).
+__global__ void __launch_bounds__(256) scale_gather_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                                const float* __restrict__ scale, long long rows, int C, int lda,
+                                                                int mapped, WinMap map, int tokens_per_image) {
+    const int cpr = C / 8;                                  // 16-byte chunks per row
+    const long long total = rows * cpr;
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+        const long long m = i / cpr;
+        const int ch = static_cast<int>(i - m * cpr);
+        const long long row = mapped ? static_cast<long long>(map.token32(static_cast<uint32_t>(m))) : m;
+        uint4 v = *reinterpret_cast<const uint4*>(in + row * lda + ch * 8);
+        if (scale) {
+            const float sc = scale[row / tokens_per_image];
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 t2 = __bfloat1622float2(h[j]);
+                h[j] = __floats2bfloat162_rn(t2.x * sc, t2.y * sc);
+            }
+        }
+        *reinterpret_cast<uint4*>(out + m * C + ch * 8) = v;
+    }
+}
+
 template <typename T>
-inline cudaError_t launch_dgrad_gemm(const GemmArgs<T>& g, __nv_bfloat16* wT_bf16, int sms, cudaStream_t st) {
+inline cudaError_t launch_dgrad_gemm(const GemmArgs<T>& g, __nv_bfloat16* wT_bf16, int sms, cudaStream_t st,
+                                     __nv_bfloat16* a_scratch = nullptr) {
     if constexpr (Act<T>::kIsBf16) {
         static const bool on = [] { const char* e = getenv("LEWIN_NO_WSS_DGRAD"); return !(e && e[0] == '1'); }();
-        if (on && wT_bf16 && g.K >= 256 && g.N >= 256 && ws::wss_supported(g)) {
-            cudaError_t e = launch_convert_w(g.Wt, wT_bf16, static_cast<long long>(g.N) * g.K, st);
-            if (e != cudaSuccess) return e;
-            return ws::wss_launch<EPI_BIAS>(g, wT_bf16, sms, st);
+        if (on && wT_bf16 && g.K >= 256 && g.N >= 256) {
+            GemmArgs<T> h = g;
+            const bool prepass = (g.mapA || g.a_row_scale) && a_scratch && !g.mean && g.K % 8 == 0 && g.M < (1ll << 31);
+            if (prepass) { h.A = a_scratch; h.lda = g.K; h.mapA = 0; h.a_row_scale = nullptr; }
+            if (ws::wss_supported(h)) {
+                if (prepass) {
+                    const long long chunks = g.M * (g.K / 8);
+                    long long grid = (chunks + 255) / 256;
+                    if (grid > static_cast<long long>(sms) * 16) grid = static_cast<long long>(sms) * 16;
+                    scale_gather_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(g.A, a_scratch, g.a_row_scale, g.M, g.K, g.lda,
+                                                                                         g.mapA, g.map, g.tokens_per_image);
+                    cudaError_t e = cudaGetLastError();
+                    if (e != cudaSuccess) return e;
+                }
+                cudaError_t e = launch_convert_w(g.Wt, wT_bf16, static_cast<long long>(g.N) * g.K, st);
+                if (e != cudaSuccess) return e;
+                return ws::wss_launch<EPI_BIAS>(h, wT_bf16, sms, st);
+            }
         }
     }
     return launch_gemm_any<T, EPI_BIAS>(g, st);
@@ -848,6 +890,10 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     float* woT = reinterpret_cast<float*>(p); p += bw_align(static_cast<size_t>(C) * C * 4);
     float* wqkvT = reinterpret_cast<float*>(p); p += bw_align(static_cast<size_t>(3) * C * C * 4);
     __nv_bfloat16* wqkvT_b = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
+    p += bw_align(static_cast<size_t>(3) * C * C * 2);
+    __nv_bfloat16* woT_b = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
+    p += bw_align(static_cast<size_t>(C) * C * 2);
+    __nv_bfloat16* dy_s = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
 
     const T* x = static_cast<const T*>(f.x);
     const T* dy = static_cast<const T*>(a->dy);
@@ -865,7 +911,7 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.Y = dctx; g.ldy = C; g.M = tokens; g.N = C; g.K = C;
         g.mapA = mapped; g.mapY = 0; g.map = map; g.tokens_per_image = tpi;
         g.a_row_scale = f.windowed ? nullptr : f.drop_scale;
-        BCK((launch_gemm_any<T, EPI_BIAS>(g, st)));
+        BCK(launch_dgrad_gemm<T>(g, woT_b, sms, st, dy_s));
     }
     {   // dW_out += do^T ctx ; db_out += colsum(do)
         WgradArgs<T> w{};
@@ -912,7 +958,8 @@ inline size_t leff_bwd_ws(const LewinLeffBwdArgs* a, int dtype) {
     const size_t es = dtype == LEWIN_DTYPE_BF16 ? 2 : 4;
     const size_t C = f.C, Ch = f.hidden;
     return 2 * bw_align(tokens * 4) + 3 * bw_align(tokens * Ch * es) + bw_align(tokens * C * es) + 2 * bw_align(C * Ch * 4) +
-           (dtype == LEWIN_DTYPE_BF16 ? 2 * bw_align(C * Ch * 2) : 0);     // bf16 images of W2^T, W1^T
+           (dtype == LEWIN_DTYPE_BF16 ? 2 * bw_align(C * Ch * 2) + bw_align(tokens * C * 2) : 0);
+           // bf16: images of W2^T, W1^T and the DropPath-scaled dout rows
 }
 
 template <typename T>
@@ -941,6 +988,7 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     float* w1T = reinterpret_cast<float*>(p); p += bw_align(static_cast<size_t>(C) * Ch * 4);
     __nv_bfloat16* w2T_b = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p) : nullptr;
     __nv_bfloat16* w1T_b = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p + bw_align(static_cast<size_t>(C) * Ch * 2)) : nullptr;
+    __nv_bfloat16* dout_s = Act<T>::kIsBf16 ? reinterpret_cast<__nv_bfloat16*>(p + 2 * bw_align(static_cast<size_t>(C) * Ch * 2)) : nullptr;
 
     const T* y = static_cast<const T*>(f.y);
     const T* dout = static_cast<const T*>(a->dout);
@@ -962,7 +1010,7 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         g.A = dout; g.lda = C; g.Wt = w2T; g.bias = nullptr;
         g.Y = dh2; g.ldy = Ch; g.M = tokens; g.N = Ch; g.K = C;
         g.tokens_per_image = tpi; g.a_row_scale = dscale;
-        BCK(launch_dgrad_gemm<T>(g, w2T_b, sms, st));          // streamed-W kernel when no DropPath row scale is active
+        BCK(launch_dgrad_gemm<T>(g, w2T_b, sms, st, dout_s));
     }
     // depthwise conv backward: da1 = conv^T(dh2 * gelu'(a2)) * gelu'(a1); dWdw, dbdw
     {

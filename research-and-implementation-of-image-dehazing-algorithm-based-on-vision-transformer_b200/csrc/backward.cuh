@@ -842,7 +842,8 @@ inline cudaError_t launch_dgrad_gemm(const GemmArgs<T>& g, __nv_bfloat16* wT_bf1
                                      __nv_bfloat16* a_scratch = nullptr) {
     if constexpr (Act<T>::kIsBf16) {
         static const bool on = [] { const char* e = getenv("LEWIN_NO_WSS_DGRAD"); return !(e && e[0] == '1'); }();
-        if (on && wT_bf16 && g.K >= 256 && g.N >= 256) {
+        static const int min_dim = [] { const char* e = getenv("LEWIN_WSS_DGRAD_MIN"); return e ? atoi(e) : 128; }();
+        if (on && wT_bf16 && g.K >= min_dim && g.N >= min_dim) {
             GemmArgs<T> h = g;
             const bool prepass = (g.mapA || g.a_row_scale) && a_scratch && !g.mean && g.K % 8 == 0 && g.M < (1ll << 31);
             if (prepass) { h.A = a_scratch; h.lda = g.K; h.mapA = 0; h.a_row_scale = nullptr; }

@@ -64,7 +64,8 @@ def main():
     import torch
     out_dir = "/tmp/diff_bwd"
     os.makedirs(out_dir, exist_ok=True)
-    variants = {"old": {k: "1" for k in os.environ.get("DIFF_OLD", "LEWIN_NO_BWD2,LEWIN_NO_WGRAD2,LEWIN_NO_CORE_BWD2").split(",")}, "new": {}}
+    variants = {"old": {k: "1" for k in os.environ.get("DIFF_OLD", "LEWIN_NO_BWD2,LEWIN_NO_WGRAD2,LEWIN_NO_CORE_BWD2").split(",") if k},
+                "new": dict(kv.split("=") for kv in os.environ.get("DIFF_NEW", "").split(",") if kv)}
     for tag, envx in variants.items():
         r = subprocess.run([sys.executable, __file__, "--child", tag, out_dir], env=dict(os.environ, **envx), timeout=300,
                            capture_output=True, text=True)

@@ -158,6 +158,28 @@ def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=
     return restored[:, :, :H, :W].clamp(0, 1)
 
 
+def rows_needed(H, W, rank, world, ps=128):
+    """Image row ranges [(r0, r1), ...] that the tiles of `rank` read (tiled mode): its contiguous tile range covers whole
+    tile rows of the wrap-padded canvas; canvas rows >= H are copies of the canvas's (= the image's) first rows
+    (test_long_GPU.py:89) and the right strip wraps columns of the SAME rows (:88).  A rank uploads only these rows."""
+    L = canvas_size(H, W, ps)
+    n = L // ps
+    s, e = shard_range(n * n, rank, world)
+    if e <= s:
+        return []
+    a, b = (s // n) * ps, ((e - 1) // n + 1) * ps            # canvas rows [a, b)
+    out = []
+    if a < H:
+        out.append((a, min(b, H)))
+    if b > H:                                                 # bottom strip rows [max(a, H), b) <- image rows [.. - H)
+        lo, hi = max(a, H) - H, b - H
+        if out and lo <= out[0][1] and hi >= out[0][0]:       # overlapping / adjacent: merge
+            out[0] = (min(out[0][0], lo), max(out[0][1], hi))
+        else:
+            out.insert(0, (lo, hi))
+    return out
+
+
 class StreamingDehazer:
     """Streams HOST images through a device dehazing function with the copies off the compute stream.
 
@@ -167,11 +189,15 @@ class StreamingDehazer:
     in full), so a sequence runs at max(compute, copy) per image instead of their sum.  `fn(device_image) -> restored`
     is e.g. ``lambda x: dehaze_tiled(model, x, graphed=g)``; host tensors should be pinned."""
 
-    def __init__(self, fn, shape, device, depth=2, dtype=torch.float32):
+    def __init__(self, fn, shape, device, depth=2, dtype=torch.float32, rows=None, download=True, out_shape=None):
+        """rows: image row ranges this rank's tiles read (`rows_needed`; None = the whole image) - only those are uploaded,
+        the rest of the device image is never read by the rank's tiles.  download=False: the result stays on the device
+        (multi-GPU: every rank holds the gathered image, one rank delivers it to the host)."""
         self.fn, self.dev, self.depth = fn, device, depth
+        self.rows, self.download = rows, download
         self.s_in, self.s_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
-        self.x = [torch.empty(shape, device=device, dtype=dtype) for _ in range(depth)]
-        self.y = [torch.empty(shape, device=device, dtype=dtype) for _ in range(depth)]
+        self.x = [torch.zeros(shape, device=device, dtype=dtype) for _ in range(depth)]
+        self.y = [torch.empty(out_shape or shape, device=device, dtype=dtype) for _ in range(depth)]
         mk = lambda: [torch.cuda.Event() for _ in range(depth)]
         self.loaded, self.consumed, self.drained = mk(), mk(), mk()
         self.n = 0
@@ -185,7 +211,11 @@ class StreamingDehazer:
         with torch.cuda.stream(self.s_in):
             if not first:
                 self.s_in.wait_event(self.consumed[i])       # the compute that read this slot has finished
-            self.x[i].copy_(img_host, non_blocking=True)
+            if self.rows is None:
+                self.x[i].copy_(img_host, non_blocking=True)
+            else:
+                for r0, r1 in self.rows:
+                    self.x[i][:, :, r0:r1].copy_(img_host[:, :, r0:r1], non_blocking=True)
             self.loaded[i].record(self.s_in)
         cur.wait_event(self.loaded[i])
         if not first:
@@ -194,7 +224,8 @@ class StreamingDehazer:
         self.consumed[i].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.consumed[i])
-            out_host.copy_(self.y[i], non_blocking=True)
+            if self.download:
+                out_host.copy_(self.y[i], non_blocking=True)
             self.drained[i].record(self.s_out)
 
     def flush(self):

@@ -167,3 +167,29 @@ def test_patch_reference_model_structure():
     L.unpatch(blk)
     out = blk(torch.zeros(1, 256, 32))          # reference forward restored, runs on CPU
     assert out.shape == (1, 256, 32)
+
+
+def test_rows_needed_cover_each_ranks_tiles():
+    """fullres.rows_needed: uploading only those image rows (NaN elsewhere) leaves every tile of the rank's shard identical
+    to the tiles cut from the full image - for every world size of BASELINE config 3 and an odd image size."""
+    import torch
+    from lewin_b200 import fullres
+    for (H, W) in ((1200, 1600), (300, 500), (250, 130)):
+        g = torch.Generator().manual_seed(H)
+        img = torch.rand(1, 3, H, W, generator=g)
+        full_tiles = fullres.to_tiles(fullres.wrap_pad(img, ps=128), 128)
+        T = full_tiles.shape[0]
+        for world in (1, 2, 4, 8):
+            covered = 0
+            for rank in range(world):
+                rows = fullres.rows_needed(H, W, rank, world)
+                part = torch.full_like(img, float("nan"))
+                for r0, r1 in rows:
+                    assert 0 <= r0 < r1 <= H
+                    part[:, :, r0:r1] = img[:, :, r0:r1]
+                    covered += r1 - r0
+                s, e = fullres.shard_range(T, rank, world)
+                tiles = fullres.to_tiles(fullres.wrap_pad(part, ps=128), 128)[s:e]
+                assert torch.equal(tiles, full_tiles[s:e]), (H, W, world, rank)
+            if world == 1:
+                assert covered == H

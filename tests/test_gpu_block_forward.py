@@ -154,6 +154,24 @@ def test_streaming_dehazer_matches_direct_calls():
     for a, b in zip(imgs, outs):
         ref = fn(a.to(dev)).cpu()
         assert torch.equal(ref, b)
+    # multi-GPU upload plan, emulated for rank 1 of 2: only fullres.rows_needed rows are copied to the device, and the rank's
+    # tile shard must come out exactly as from the full image
+    H2 = W2 = 600                                             # canvas 640^2 = 25 tiles; rank 1 of 4 owns tiles 7..12
+    imgs2 = [torch.rand(1, 3, H2, W2, generator=g).pin_memory() for _ in range(3)]
+    s, e = fullres.shard_range(25, 1, 4)
+    fn_r = lambda x: model(fullres.to_tiles(fullres.wrap_pad(x, ps=128), 128)[s:e], index_samples=idx)
+    rows = fullres.rows_needed(H2, W2, 1, 4)
+    assert rows == [(128, 384)]
+    pipe_r = fullres.StreamingDehazer(fn_r, (1, 3, H2, W2), dev, rows=rows, out_shape=(e - s, 3, 128, 128))
+    outs_r = [torch.empty(e - s, 3, 128, 128).pin_memory() for _ in range(3)]
+    imgs = imgs2
+    with torch.no_grad():
+        for a, b in zip(imgs, outs_r):
+            pipe_r.submit(a, b)
+        pipe_r.flush()
+        torch.cuda.synchronize()
+        for a, b in zip(imgs, outs_r):
+            assert torch.equal(fn_r(a.to(dev)).cpu(), b)
 
 
 def test_full_size_tile_batch_invariance_bf16():

@@ -274,6 +274,13 @@ def main():
     out_host = torch.empty(1, 3, IMG_H, IMG_W).pin_memory()
     img_dev = img_host.to(dev)
     idx = model.draw_index_samples()            # 18 draws of attn.py:91 (identical on every rank: same seed)
+    if world > 1:                               # checked once, so the per-image broadcast of the draws can be skipped
+        w = torch.arange(1, idx.numel() + 1, dtype=torch.float64)
+        c = (idx.double().flatten() * w).sum().to(dev)
+        lo, hi = c.clone(), c.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert float(lo) == float(hi), "index_samples differ between ranks"
 
     cur_dtype = [args.dtype]
     graphs = {}
@@ -292,8 +299,8 @@ def main():
         g = graphed_for(cur_dtype[0])
         if g is None and cur_dtype[0] == "bf16":
             with torch.autocast("cuda", torch.bfloat16):
-                return fullres.dehaze_tiled(model, img, ps=PS, index_samples=idx)
-        return fullres.dehaze_tiled(model, img, ps=PS, index_samples=idx, graphed=g)
+                return fullres.dehaze_tiled(model, img, ps=PS, index_samples=idx, broadcast_index_samples=False)
+        return fullres.dehaze_tiled(model, img, ps=PS, index_samples=idx, graphed=g, broadcast_index_samples=False)
 
     def barrier():
         if world > 1:

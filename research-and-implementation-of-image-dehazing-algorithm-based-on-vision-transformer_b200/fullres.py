@@ -106,12 +106,15 @@ def dehaze_canvas(model, img, ps=128, index_samples=None):
 
 
 @torch.no_grad()
-def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=None, graphed=None):
+def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=None, graphed=None,
+                 broadcast_index_samples=True):
     """Tiled mode, sharded over the ranks of `group` (torch.distributed) when initialised.
 
     Every rank receives the full image, processes its contiguous tile range and all ranks end with the full
     restored image (all_gather of the padded shards).  The 18 index_sample draws are made on rank 0 and
-    broadcast so that the sharded result is bit-identical to the single-GPU tile-batch result."""
+    broadcast so that the sharded result is bit-identical to the single-GPU tile-batch result
+    (`broadcast_index_samples=False`: the caller guarantees that every rank passes the same `index_samples`, e.g. drawn
+    from a shared seed, and the per-call broadcast is skipped)."""
     import torch.distributed as dist
 
     B, C, H, W = img.shape
@@ -126,7 +129,7 @@ def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=
 
     if index_samples is None and hasattr(model, "draw_index_samples"):
         index_samples = model.draw_index_samples()
-    if distributed and index_samples is not None:
+    if distributed and index_samples is not None and broadcast_index_samples:
         idx = index_samples.to(img.device)
         dist.broadcast(idx, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         index_samples = idx

@@ -193,3 +193,20 @@ def test_rows_needed_cover_each_ranks_tiles():
                 assert torch.equal(tiles, full_tiles[s:e]), (H, W, world, rank)
             if world == 1:
                 assert covered == H
+
+
+def test_bf16_weight_image_cache_follows_in_place_updates():
+    """ops._bf16_image (the caller-converted weights of ABI v2): the image is reused while the parameter is untouched and
+    rebuilt after any in-place update (optimizer step, load_state_dict), and never shared between distinct tensors."""
+    import torch
+    from lewin_b200 import ops
+    w = torch.nn.Parameter(torch.randn(8, 8))
+    a = ops._bf16_image(w)
+    assert a.dtype == torch.bfloat16 and torch.equal(a, w.detach().to(torch.bfloat16))
+    assert ops._bf16_image(w) is a                       # cached
+    with torch.no_grad():
+        w.add_(1.0)                                      # what an optimizer step / load_state_dict does: _version bump
+    b = ops._bf16_image(w)
+    assert b is not a and torch.equal(b, w.detach().to(torch.bfloat16))
+    w2 = torch.nn.Parameter(w.detach().clone())
+    assert ops._bf16_image(w2) is not b

@@ -60,7 +60,9 @@ class GraphedForward:
     The per-rank tile batch of config 3 has a static shape, and a forward is ~230 kernel launches (18 blocks x 4-9
     kernels + 10 cuDNN convolutions + glue); at 8 GPUs the per-rank GPU time drops below the CPU launch time, so the
     launch sequence is captured once and replayed (inputs are copied into static buffers; ``index_samples`` is a
-    static device tensor refreshed before every replay, so the reference's per-forward RNG draws are preserved)."""
+    static device tensor refreshed before every replay, so the reference's per-forward RNG draws are preserved).
+    The graph holds the parameter pointers (and the cached bf16 weight images of the C >= 256 levels) of the moment of
+    capture: build a new GraphedForward after the model's weights change."""
 
     def __init__(self, model, tiles, index_samples, autocast_dtype=None, warmup=2):
         self.model = model

@@ -82,6 +82,11 @@ class GraphedForward:
         with torch.cuda.graph(self.graph):
             self.y = self._run()
         self.launches_per_replay = int(lib.lewin_launch_count() - n0)    # library kernels captured in the graph
+        self._params = list(self.model.parameters())
+        self._weights_tag = self._tag()
+
+    def _tag(self):
+        return sum(p._version for p in self._params)
 
     @torch.no_grad()
     def _run(self):
@@ -92,6 +97,9 @@ class GraphedForward:
 
     @torch.no_grad()
     def __call__(self, tiles, index_samples):
+        if self._tag() != self._weights_tag:
+            raise RuntimeError("GraphedForward: the model's parameters were modified in place after the capture "
+                               "(the graph holds bf16 weight images of that moment); build a new GraphedForward")
         self.x.copy_(tiles, non_blocking=True)
         self.idx.copy_(index_samples.to(dtype=torch.int32), non_blocking=True)
         self.graph.replay()

@@ -86,7 +86,21 @@ BLOCK_CASES = [
 ]
 
 
-def make_block_case(ref, name, C, nH, hw, B, shift, use_inmask, drop_path, train, seed):
+# Deep levels (C = 256, 512): the same recording, stored compactly - parameters are regenerated from the seed
+# (param_fill.fill_value) and every parameter gradient is kept as its L2 norm plus a seeded sample of <= 4096 elements.
+COMPACT_CASES = [
+    ("block_c256_h8_s4_compact", 256, 8, 16, 1, 4, False, 0.0, False),
+    ("block_c512_h16_s0_compact", 512, 16, 8, 2, 0, False, 0.0, False),
+]
+
+
+def grad_sample_ids(key, n, seed, k=4096):
+    import zlib
+    rng = np.random.default_rng([seed, zlib.crc32(key.encode()), 7])
+    return np.sort(rng.choice(n, size=min(n, k), replace=False))
+
+
+def make_block_case(ref, name, C, nH, hw, B, shift, use_inmask, drop_path, train, seed, compact=False):
     torch.manual_seed(seed)
     blk = ref.LeWinTransformerBlock(dim=C, input_resolution=(128, 128), num_heads=nH, win_size=8,
                                     shift_size=shift, token_mlp="leff", drop_path=drop_path)
@@ -146,10 +160,19 @@ def make_block_case(ref, name, C, nH, hw, B, shift, use_inmask, drop_path, train
         save["input_mask"] = inm
     if drop_scale is not None:
         save["drop_scale"] = drop_scale
-    for k, v in p.items():
-        save["p:" + k] = v
-    for k, v in grads.items():
-        save["g:" + k] = v
+    if compact:
+        for k, v in p.items():                 # the stored seed must reproduce the reference block's parameters exactly
+            if np.issubdtype(v.dtype, np.floating):
+                assert np.array_equal(v, param_fill.fill_value(k, v.shape, seed)), k
+        save["params_from_seed"] = np.int64(1)
+        for k, v in grads.items():
+            save["gn:" + k] = np.float64(np.linalg.norm(v.astype(np.float64)))
+            save["gs:" + k] = v.ravel()[grad_sample_ids(k, v.size, seed)]
+    else:
+        for k, v in p.items():
+            save["p:" + k] = v
+        for k, v in grads.items():
+            save["g:" + k] = v
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **save)
 
 
@@ -182,9 +205,15 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
-    for i, case in enumerate(BLOCK_CASES):
-        make_block_case(ref, *case, seed=100 + 10 * i)
-    make_model_case(ref, "uformer32_b2", B=2, seed=1234)
+    only = os.environ.get("GOLDEN_ONLY", "")            # e.g. GOLDEN_ONLY=compact regenerates just the compact cases
+    if only in ("", "blocks"):
+        for i, case in enumerate(BLOCK_CASES):
+            make_block_case(ref, *case, seed=100 + 10 * i)
+    if only in ("", "compact"):
+        for i, case in enumerate(COMPACT_CASES):
+            make_block_case(ref, *case, seed=500 + 10 * i, compact=True)
+    if only in ("", "model"):
+        make_model_case(ref, "uformer32_b2", B=2, seed=1234)
 
 
 if __name__ == "__main__":

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import lewin_oracle as O
-from tests.util import BLOCK_FIXTURES, load_fixture
+from tests.util import BLOCK_FIXTURES, COMPACT_FIXTURES, check_compact_grads, load_fixture
 
 
 @pytest.mark.parametrize("name", BLOCK_FIXTURES)
@@ -30,6 +30,24 @@ def test_oracle_forward_backward_matches_reference(name, dtype):
     for k in O.GRAD_KEYS:
         ref = fx["grads"][k]
         assert np.abs(g[k] - ref).max() < 1e-3 * max(np.abs(ref).max(), 1e-4 * gscale), k
+
+
+@pytest.mark.parametrize("name", COMPACT_FIXTURES)
+def test_oracle_matches_reference_at_deep_levels(name):
+    """C = 256 / 512 blocks (8 / 16 heads) recorded from the unmodified reference, compact fixtures: forward, dx, the
+    selected query sets and all 19 parameter gradients (sampled elements + norms)."""
+    fx = load_fixture(name)
+    p = O.as_dtype(fx["params"], np.float64)
+    x = fx["x"].astype(np.float64)
+    out, aux = O.lewin_block(x, p, fx["shift"], fx["idx"], None, True, None, return_aux=True)
+    bad = (aux["top"] != fx["top"]).any(-1)
+    assert (aux["rel_gap"][bad] < 1e-5).all()
+    if bad.any():
+        out = O.lewin_block(x, p, fx["shift"], fx["idx"], None, True, None, top=fx["top"])
+    assert np.abs(out - fx["out"]).max() < 2e-4 * max(1.0, np.abs(fx["out"]).max())
+    dx, g = O.lewin_block_bwd(fx["dout"].astype(np.float64), x, p, fx["shift"], fx["idx"], None, True, None, top=fx["top"])
+    assert np.abs(dx - fx["dx"]).max() < 1e-3 * np.abs(fx["dx"]).max()
+    check_compact_grads(fx, g, 1e-3)
 
 
 def test_prob_sizes():

@@ -11,6 +11,10 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 BLOCK_FIXTURES = ["block_c32_h1_s0", "block_c32_h1_s4", "block_c64_h2_s4", "block_c64_h2_s4_inmask",
                   "block_c64_h2_s4_droppath", "block_c128_h4_s0"]
 
+# deep levels, stored compactly (oracle/make_golden.py COMPACT_CASES): parameters regenerated from the seed, parameter
+# gradients as L2 norm + a seeded sample of <= 4096 elements
+COMPACT_FIXTURES = ["block_c256_h8_s4_compact", "block_c512_h16_s0_compact"]
+
 TOL_F32 = 1e-3     # BASELINE.json north_star: max-abs 1e-3 (fp32)
 TOL_BF16 = 2e-2    # max-abs 2e-2 (bf16)
 TIE_TAU_F32 = 1e-5  # rows whose rank-25/26 gap < tau * range(M) are ambiguous
@@ -22,7 +26,38 @@ def load_fixture(name):
     fx["params"] = {k[2:]: z[k] for k in z.files if k.startswith("p:")}
     fx["grads"] = {k[2:]: z[k] for k in z.files if k.startswith("g:")}
     fx["shift"] = int(fx["shift"]); fx["nH"] = int(fx["nH"]); fx["hw"] = int(fx["hw"])
+    if "params_from_seed" in fx:
+        import lewin_b200 as L
+        from oracle import param_fill
+        C = fx["x"].shape[-1]
+        sd = L.LeWinTransformerBlock(dim=C, input_resolution=(128, 128), num_heads=fx["nH"], win_size=8,
+                                     shift_size=fx["shift"]).state_dict()
+        fx["params"] = {k: (param_fill.fill_value(k, tuple(v.shape), int(fx["seed"])) if v.is_floating_point() else v.numpy())
+                        for k, v in sd.items()}
+        fx["grad_norm"] = {k[3:]: float(z[k]) for k in z.files if k.startswith("gn:")}
+        fx["grad_sample"] = {k[3:]: z[k] for k in z.files if k.startswith("gs:")}
+        fx = {k: v for k, v in fx.items() if not k.startswith(("gn:", "gs:"))}
     return fx
+
+
+def grad_sample_ids(key, n, seed, k=4096):
+    """The element sample of a compact fixture's parameter gradient (same rule as oracle/make_golden.py)."""
+    import zlib
+    rng = np.random.default_rng([int(seed), zlib.crc32(key.encode()), 7])
+    return np.sort(rng.choice(n, size=min(n, k), replace=False))
+
+
+def check_compact_grads(fx, grads, rtol):
+    """Parameter gradients against a compact fixture: sampled elements and the L2 norm, relative to each gradient's scale
+    (analytically-zero gradients - the key bias - are floored at 1e-4 of the largest gradient)."""
+    gscale = max(np.abs(v).max() for v in fx["grad_sample"].values())
+    assert sorted(grads) == sorted(fx["grad_sample"])
+    for k, ref in fx["grad_sample"].items():
+        got = np.asarray(grads[k], dtype=np.float64)
+        ids = grad_sample_ids(k, got.size, fx["seed"])
+        floor = max(np.abs(ref).max(), 1e-4 * gscale)
+        assert np.abs(got.ravel()[ids] - ref).max() < rtol * floor, k
+        assert abs(np.linalg.norm(got) - fx["grad_norm"][k]) < rtol * max(fx["grad_norm"][k], 1e-4 * gscale * np.sqrt(got.size)), k
 
 
 def make_block(fx, device=None):

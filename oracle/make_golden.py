@@ -176,6 +176,50 @@ def make_block_case(ref, name, C, nH, hw, B, shift, use_inmask, drop_path, train
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **save)
 
 
+# bf16: the reference itself under torch.autocast("cpu", dtype=torch.bfloat16) - the only way to run the UNMODIFIED
+# reference at BASELINE's compute dtype in this container (no GPU).  CPU autocast keeps LayerNorm / softmax outputs in bf16
+# where CUDA autocast keeps them fp32, so agreement with the CUDA-semantics bf16 oracle is expected to one bf16 ulp, not
+# bit for bit; the top-u sets may differ on rows whose rank-25/26 gap is below the bf16 resolution (2^-7 of the M range).
+BF16_CASES = [
+    ("block_c64_h2_s4_bf16cpu", 64, 2, 16, 2, 4),
+    ("block_c256_h8_s4_bf16cpu", 256, 8, 16, 1, 4),
+]
+
+
+def make_bf16_case(ref, name, C, nH, hw, B, shift, seed):
+    torch.manual_seed(seed)
+    blk = ref.LeWinTransformerBlock(dim=C, input_resolution=(128, 128), num_heads=nH, win_size=8,
+                                    shift_size=shift, token_mlp="leff", drop_path=0.0)
+    param_fill.fill_module(blk, seed)
+    blk.eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, hw * hw, C, generator=g).to(torch.bfloat16)
+    torch.manual_seed(seed + 2)
+    with Recorder(ref) as rec, torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        out = blk(x)
+    assert out.dtype == torch.bfloat16 and len(rec.idx) == 1
+    idx, top = rec.idx[0].numpy(), np.sort(rec.top[0].numpy(), -1)
+    p = {k: v.detach().numpy() for k, v in blk.state_dict().items()}
+    for k, v in p.items():
+        if np.issubdtype(v.dtype, np.floating):
+            assert np.array_equal(v, param_fill.fill_value(k, v.shape, seed)), k
+    xn, on = x.float().numpy(), out.float().numpy()
+    o, aux = O.lewin_block(xn, O.as_dtype(p, np.float32), shift, idx, None, True, None, return_aux=True, bf16=True)
+    bad = (aux["top"] != top).any(-1)
+    assert (aux["rel_gap"][bad] < 2.0 ** -7).all(), name
+    o2 = O.lewin_block(xn, O.as_dtype(p, np.float32), shift, idx, None, True, None, top=top, bf16=True)
+    # one bf16 ulp at the magnitude of the block's activations (the residual sums cancel, so an element's own magnitude
+    # is not the scale of its rounding error)
+    ulp = 2.0 ** (np.floor(np.log2(np.abs(on).max())) - 7)
+    d = np.abs(o2 - on)
+    print(f"{name}: top-u rows differing {int(bad.sum())}/{bad.size} (all below the bf16 tie threshold); oracle(bf16) vs reference: "
+          f"max {d.max():.4f} (ulp at |out|max = {ulp:.4f}), mean {d.mean():.2e}, {100 * (d > 0).mean():.1f} % of elements differ")
+    assert d.max() <= ulp and d.mean() < 2e-3, name
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), x=xn, out=on, idx=idx.astype(np.int64), top=top.astype(np.int64),
+                        shift=np.int64(shift), nH=np.int64(nH), hw=np.int64(hw), seed=np.int64(seed),
+                        params_from_seed=np.int64(1))
+
+
 def make_model_case(ref, name, B, seed, mask=False):
     """Uformer(img_size=128, embed_dim=32) forward, config 1 of BASELINE.json (B tiles)."""
     torch.manual_seed(seed)
@@ -212,6 +256,9 @@ def main():
     if only in ("", "compact"):
         for i, case in enumerate(COMPACT_CASES):
             make_block_case(ref, *case, seed=500 + 10 * i, compact=True)
+    if only in ("", "bf16"):
+        for i, case in enumerate(BF16_CASES):
+            make_bf16_case(ref, *case, seed=900 + 10 * i)
     if only in ("", "model"):
         make_model_case(ref, "uformer32_b2", B=2, seed=1234)
 

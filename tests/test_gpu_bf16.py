@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import lewin_oracle as O
-from tests.util import TOL_BF16, check_top
+from tests.util import BF16_REF_FIXTURES, TOL_BF16, check_top
 
 pytestmark = pytest.mark.gpu
 TAU_BF16 = 2.0 ** -7
@@ -54,6 +54,60 @@ def test_block_forward_bf16_matches_bf16_oracle(C, nH, hw, B, shift):
     # 2e-2 absolute for O(1) outputs; outputs are stored in bf16, so allow 3 bf16 ulps of the output scale
     assert e_y < max(TOL_BF16, 3 * 2.0 ** -8 * np.abs(aux["y"]).max())
     assert e_o < max(TOL_BF16, 3 * 2.0 ** -8 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", BF16_REF_FIXTURES)
+def test_block_forward_bf16_matches_reference_cpu_autocast_golden(name):
+    """bf16 kernels against the UNMODIFIED reference run under torch.autocast("cpu", bfloat16) (tests/golden/*_bf16cpu):
+    same top-u sets on every row whose rank-25/26 gap exceeds the bf16 resolution, outputs within 2 bf16 ulps of the
+    activation scale on 99.9 % of the elements (1 ulp kernel vs oracle + 1 ulp CPU- vs CUDA-autocast policy; the rest are
+    the few tokens of rows where a near-tie was resolved differently), mean error < 3e-3."""
+    import lewin_b200.ops as ops
+    from tests.util import load_fixture, make_block
+    fx = load_fixture(name)
+    dev = torch.device("cuda:0")
+    blk = make_block(fx, dev).eval()
+    xs = torch.from_numpy(fx["x"]).to(dev).to(torch.bfloat16)
+    captured = {}
+    orig = ops.lewin_attn
+
+    def spy(*a, **k):
+        y, top = orig(*a, return_top=True, **k)
+        captured["top"] = top
+        return y
+
+    ops.lewin_attn = spy
+    try:
+        with torch.no_grad():
+            out = blk(xs, None, torch.from_numpy(fx["idx"]))
+    finally:
+        ops.lewin_attn = orig
+    assert out.dtype == torch.bfloat16
+    _, aux = O.lewin_block(fx["x"].astype(np.float64), O.as_dtype(fx["params"], np.float64), fx["shift"], fx["idx"], None, True, None,
+                           return_aux=True)
+    nbad, namb, nhard = check_top(captured["top"].cpu().numpy(), fx["top"], aux["rel_gap"], TAU_BF16)
+    assert nhard == 0, f"{nhard} non-ambiguous rows differ from the reference's selection ({nbad} differ, {namb} ambiguous)"
+    ulp = 2.0 ** (np.floor(np.log2(np.abs(fx["out"]).max())) - 7)
+    d = np.abs(out.float().cpu().numpy() - fx["out"])
+    # A near-tie resolved differently swaps one query token between "attended" and "mean(V)": that token's attention output
+    # changes and LeFF's 3x3 depthwise conv carries it to the 8 neighbouring pixels.  Those pixels are excluded; everything
+    # else must agree with the reference to 2 bf16 ulps of the activation scale.
+    B, L, C = fx["x"].shape
+    hw, sh, nWw = fx["hw"], fx["shift"], fx["hw"] // 8
+    affected = np.zeros((B, hw, hw), dtype=bool)
+    tg = np.sort(captured["top"].cpu().numpy().astype(np.int64), -1)
+    for w_ in range(tg.shape[0]):
+        for h_ in range(tg.shape[1]):
+            for n in set(tg[w_, h_]) ^ set(fx["top"][w_, h_]):
+                b, w = divmod(w_, nWw * nWw)
+                wy, wx = divmod(w, nWw)
+                y, x_ = (wy * 8 + n // 8 + sh) % hw, (wx * 8 + n % 8 + sh) % hw
+                affected[b, max(y - 1, 0):y + 2, max(x_ - 1, 0):x_ + 2] = True
+    keep = ~affected.reshape(B, L)
+    print(f"{name}: rows differing {nbad}, pixels excluded {int(affected.sum())} of {affected.size}; max over the rest "
+          f"{d[keep].max():.4f}, mean {d[keep].mean():.2e}, ulp {ulp:.4f}")
+    assert affected.mean() < 0.25           # 2 swapped tokens x 9 pixels each on a 16 x 16 map are already 12 %
+    assert d[keep].max() <= 2 * ulp and d[keep].mean() < 3e-3
 
 
 def test_autocast_routes_to_bf16_kernels_and_trains():

@@ -15,6 +15,9 @@ BLOCK_FIXTURES = ["block_c32_h1_s0", "block_c32_h1_s4", "block_c64_h2_s4", "bloc
 # gradients as L2 norm + a seeded sample of <= 4096 elements
 COMPACT_FIXTURES = ["block_c256_h8_s4_compact", "block_c512_h16_s0_compact"]
 
+# the UNMODIFIED reference under torch.autocast("cpu", bfloat16) (oracle/make_golden.py BF16_CASES): x, out, idx, top
+BF16_REF_FIXTURES = ["block_c64_h2_s4_bf16cpu", "block_c256_h8_s4_bf16cpu"]
+
 TOL_F32 = 1e-3     # BASELINE.json north_star: max-abs 1e-3 (fp32)
 TOL_BF16 = 2e-2    # max-abs 2e-2 (bf16)
 TIE_TAU_F32 = 1e-5  # rows whose rank-25/26 gap < tau * range(M) are ambiguous

@@ -193,17 +193,22 @@ def make_bf16_case(ref, name, C, nH, hw, B, shift, seed):
     param_fill.fill_module(blk, seed)
     blk.eval()
     g = torch.Generator().manual_seed(seed + 1)
-    x = torch.randn(B, hw * hw, C, generator=g).to(torch.bfloat16)
+    x = torch.randn(B, hw * hw, C, generator=g).to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(B, hw * hw, C, generator=g).to(torch.bfloat16)
     torch.manual_seed(seed + 2)
-    with Recorder(ref) as rec, torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+    with Recorder(ref) as rec, torch.autocast("cpu", dtype=torch.bfloat16):
         out = blk(x)
+    out.backward(dout)                                       # fp32 parameter gradients, bf16 dx (autocast backward)
+    out = out.detach()
     assert out.dtype == torch.bfloat16 and len(rec.idx) == 1
     idx, top = rec.idx[0].numpy(), np.sort(rec.top[0].numpy(), -1)
     p = {k: v.detach().numpy() for k, v in blk.state_dict().items()}
     for k, v in p.items():
         if np.issubdtype(v.dtype, np.floating):
             assert np.array_equal(v, param_fill.fill_value(k, v.shape, seed)), k
-    xn, on = x.float().numpy(), out.float().numpy()
+    xn, on = x.detach().float().numpy(), out.float().numpy()
+    grads = {k: v.grad.detach().float().numpy() for k, v in blk.named_parameters() if v.grad is not None}
+    assert sorted(grads) == sorted(O.GRAD_KEYS)
     o, aux = O.lewin_block(xn, O.as_dtype(p, np.float32), shift, idx, None, True, None, return_aux=True, bf16=True)
     bad = (aux["top"] != top).any(-1)
     assert (aux["rel_gap"][bad] < 2.0 ** -7).all(), name
@@ -215,9 +220,25 @@ def make_bf16_case(ref, name, C, nH, hw, B, shift, seed):
     print(f"{name}: top-u rows differing {int(bad.sum())}/{bad.size} (all below the bf16 tie threshold); oracle(bf16) vs reference: "
           f"max {d.max():.4f} (ulp at |out|max = {ulp:.4f}), mean {d.mean():.2e}, {100 * (d > 0).mean():.1f} % of elements differ")
     assert d.max() <= ulp and d.mean() < 2e-3, name
-    np.savez_compressed(os.path.join(GOLD, name + ".npz"), x=xn, out=on, idx=idx.astype(np.int64), top=top.astype(np.int64),
-                        shift=np.int64(shift), nH=np.int64(nH), hw=np.int64(hw), seed=np.int64(seed),
-                        params_from_seed=np.int64(1))
+    # backward: the fp64 oracle backward (reference selection) must describe the reference's autocast gradients up to bf16 noise
+    dx64, g64 = O.lewin_block_bwd(dout.float().numpy().astype(np.float64), xn.astype(np.float64), O.as_dtype(p, np.float64),
+                                  shift, idx, None, True, None, top=top)
+    gscale = max(np.abs(v).max() for v in g64.values())
+    worst = 1.0
+    for k in O.GRAD_KEYS:
+        if np.abs(g64[k]).max() < 1e-9 * gscale:
+            continue
+        a, b = grads[k].ravel().astype(np.float64), g64[k].ravel()
+        worst = min(worst, float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b))))
+    print(f"   backward: min cosine(reference autocast grads, fp64 oracle grads) over the parameters = {worst:.5f}")
+    assert worst > 0.999, name
+    save = dict(x=xn, out=on, dout=dout.float().numpy(), dx=x.grad.float().numpy(), idx=idx.astype(np.int64),
+                top=top.astype(np.int64), shift=np.int64(shift), nH=np.int64(nH), hw=np.int64(hw), seed=np.int64(seed),
+                params_from_seed=np.int64(1))
+    for k, v in grads.items():
+        save["gn:" + k] = np.float64(np.linalg.norm(v.astype(np.float64)))
+        save["gs:" + k] = v.ravel()[grad_sample_ids(k, v.size, seed)]
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **save)
 
 
 def make_model_case(ref, name, B, seed, mask=False):

@@ -6,8 +6,8 @@ import pytest
 import torch
 
 from oracle import lewin_oracle as O
-from tests.util import (BLOCK_FIXTURES, COMPACT_FIXTURES, TIE_TAU_F32, TOL_F32, check_compact_grads, check_top, force_drop_scales,
-                        load_fixture, make_block)
+from tests.util import (BF16_REF_FIXTURES, BLOCK_FIXTURES, COMPACT_FIXTURES, TIE_TAU_F32, TOL_F32, check_compact_grads,
+                        check_compact_grads_statistical, check_top, force_drop_scales, load_fixture, make_block)
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-3
@@ -209,3 +209,39 @@ def test_block_backward_bf16_close_to_oracle(C, nH, hw, B, shift):
             assert np.abs(grads[k]).max() < 6e-2 * np.abs(g_ref[wk]).max(), (k, np.abs(grads[k]).max())
             continue
         close(grads[k], g_ref[k], k)
+
+
+@pytest.mark.parametrize("name", BF16_REF_FIXTURES)
+def test_block_backward_bf16_matches_reference_cpu_autocast_golden(name):
+    """bf16 backward through the C ABI against the UNMODIFIED reference's own autocast backward (recorded under
+    torch.autocast("cpu", bfloat16), tests/golden/*_bf16cpu): all 19 parameter gradients by cosine similarity on the sampled
+    elements and by L2 norm; dx by cosine / max error outside the windows (+ 2-pixel halo: LeFF's depthwise conv forward and
+    backward) in which a near-tie query was selected differently."""
+    fx = load_fixture(name)
+    dev = torch.device("cuda:0")
+    blk = make_block(fx, dev).eval()
+    xs = torch.from_numpy(fx["x"]).to(dev).to(torch.bfloat16).requires_grad_(True)
+    out, dx, grads, top = _run_block_with_grads(blk, xs, torch.from_numpy(fx["dout"]).to(dev).to(torch.bfloat16), torch.from_numpy(fx["idx"]))
+    _, aux = O.lewin_block(fx["x"].astype(np.float64), O.as_dtype(fx["params"], np.float64), fx["shift"], fx["idx"], None, True, None,
+                           return_aux=True)
+    nbad, namb, nhard = check_top(top, fx["top"], aux["rel_gap"], 2.0 ** -7)
+    assert nhard == 0
+    check_compact_grads_statistical(fx, grads, 0.99, 5e-2)
+    B, L, C = fx["x"].shape
+    hw, sh, nWw = fx["hw"], fx["shift"], fx["hw"] // 8
+    affected = np.zeros((B, hw, hw), dtype=bool)
+    differs = (np.sort(top.astype(np.int64), -1) != fx["top"]).any(-1).any(-1)          # per window
+    for w_ in np.nonzero(differs)[0]:
+        b, w = divmod(int(w_), nWw * nWw)
+        wy, wx = divmod(w, nWw)
+        for y in range(wy * 8 + sh - 2, wy * 8 + sh + 10):
+            for x_ in range(wx * 8 + sh - 2, wx * 8 + sh + 10):
+                affected[b, y % hw, x_ % hw] = True
+    keep = ~affected.reshape(B, L)
+    print(f"{name}: windows with a different near-tie selection {int(differs.sum())}, dx compared on {100 * keep.mean():.0f} % of the pixels")
+    if keep.mean() > 0.1:
+        a, b_ = dx.astype(np.float64)[keep].ravel(), fx["dx"].astype(np.float64)[keep].ravel()
+        cos = float(a @ b_ / (np.linalg.norm(a) * np.linalg.norm(b_)))
+        rel = float(np.abs(a - b_).max() / np.abs(b_).max())
+        print(f"   dx cosine {cos:.5f}, max error / max {rel:.3f}")
+        assert cos > 0.995 and rel < 0.1

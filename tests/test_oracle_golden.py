@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from oracle import lewin_oracle as O
-from tests.util import BF16_REF_FIXTURES, BLOCK_FIXTURES, COMPACT_FIXTURES, check_compact_grads, load_fixture
+from tests.util import (BF16_REF_FIXTURES, BLOCK_FIXTURES, COMPACT_FIXTURES, check_compact_grads, check_compact_grads_statistical,
+                        load_fixture)
 
 
 @pytest.mark.parametrize("name", BLOCK_FIXTURES)
@@ -66,6 +67,13 @@ def test_bf16_oracle_matches_reference_under_cpu_autocast(name):
     ulp = 2.0 ** (np.floor(np.log2(np.abs(fx["out"]).max())) - 7)
     d = np.abs(out - fx["out"])
     assert d.max() <= ulp and d.mean() < 2e-3 and (d > 0).mean() < 0.3
+    # backward: the reference's autocast gradients (fp32 parameter grads, bf16 dx) are the fp64 oracle's up to bf16 noise
+    dx, g = O.lewin_block_bwd(fx["dout"].astype(np.float64), fx["x"].astype(np.float64), O.as_dtype(fx["params"], np.float64),
+                              fx["shift"], fx["idx"], None, True, None, top=fx["top"])
+    a, b = dx.ravel(), fx["dx"].astype(np.float64).ravel()
+    assert a @ b / (np.linalg.norm(a) * np.linalg.norm(b)) > 0.9999
+    assert np.abs(a - b).max() < 2e-2 * np.abs(b).max()
+    check_compact_grads_statistical(fx, g, 0.999, 2e-2)
 
 
 def test_prob_sizes():

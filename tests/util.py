@@ -63,6 +63,22 @@ def check_compact_grads(fx, grads, rtol):
         assert abs(np.linalg.norm(got) - fx["grad_norm"][k]) < rtol * max(fx["grad_norm"][k], 1e-4 * gscale * np.sqrt(got.size)), k
 
 
+def check_compact_grads_statistical(fx, grads, cos_min, norm_rtol):
+    """bf16 gradients against a compact fixture: cosine similarity on the sampled elements and the L2 norm; the key
+    bias, whose gradient is analytically zero, only has to stay at noise level."""
+    nmax = max(fx["grad_norm"].values())
+    assert sorted(grads) == sorted(fx["grad_sample"])
+    for k, ref in fx["grad_sample"].items():
+        got = np.asarray(grads[k], dtype=np.float64)
+        if k.endswith("key_projection.bias"):     # analytically zero (softmax shift invariance): rounding noise on both sides
+            assert np.linalg.norm(got) < 1e-2 * nmax and fx["grad_norm"][k] < 1e-2 * nmax, k
+            continue
+        a, b = got.ravel()[grad_sample_ids(k, got.size, fx["seed"])], ref.astype(np.float64)
+        cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+        assert cos > cos_min, (k, cos)
+        assert abs(np.linalg.norm(got) - fx["grad_norm"][k]) < norm_rtol * fx["grad_norm"][k], (k, np.linalg.norm(got), fx["grad_norm"][k])
+
+
 def make_block(fx, device=None):
     """This package's LeWinTransformerBlock with the fixture's (reference) state_dict, strict load."""
     import torch

@@ -132,6 +132,45 @@ def test_uformer_forward_matches_reference_golden_f32(golden_dir):
     assert abs(p_bf16 - p_ref) < 0.01
 
 
+def test_canvas_mode_matches_reference_golden_f32(golden_dir):
+    """fullres.dehaze_canvas = the reference's test_long_GPU.py:74-93 (wrap-pad, one forward over the whole canvas, crop,
+    clamp) against the unmodified reference's recording for a 200 x 300 image (384^2 canvas, 2304 windows at level 0).  Same
+    bulk criteria as the tile test above (the model is chaotic in near-tie selections); the unclamped crop is compared too
+    because the random-init model saturates most pixels."""
+    import os
+    import lewin_b200 as L
+    from lewin_b200 import fullres
+    from oracle import param_fill
+    z = np.load(os.path.join(golden_dir, "uformer32_canvas_200x300.npz"))
+    dev = torch.device("cuda:0")
+    model = L.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff")
+    param_fill.fill_module(model, int(z["seed"]))
+    model = model.to(dev).eval()
+    img = torch.from_numpy(z["x"]).to(dev)
+    idx = torch.from_numpy(z["idx"].astype(np.int64))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            raw = model(fullres.wrap_pad(img, ps=128), index_samples=idx)[:, :, :200, :300]
+            y = fullres.dehaze_canvas(model, img, ps=128, index_samples=idx)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert torch.equal(y, raw.clamp(0, 1))
+    e = np.abs(raw.cpu().numpy() - z["y_raw"]).ravel()
+    print(f"canvas 200x300: raw max {e.max():.3e} median {np.median(e):.3e} frac>1e-3 {(e > 1e-3).mean():.4f}")
+    # Measured on a B200 (round 1): median 1.1e-5, 7.9 % of the raw values off by > 1e-3 (raw range +-6), max 0.19.  The bulk
+    # agrees to fp32 accuracy; the off pixels are attributed to near-tie top-u flips at the deep levels (one bottleneck token
+    # covers 16 x 16 output pixels and the flip spreads through the 8 decoder blocks) but have NOT yet been localised
+    # (border vs patch pattern) - DESIGN.md section 8 lists that analysis; until then the gate is the measured value + margin.
+    assert np.median(e) < 1e-4
+    assert (e > 1e-3).mean() < 0.15
+    def psnr_to(a, t):
+        return 10 * np.log10(1.0 / float(((a - t) ** 2).mean()))
+    p_ours, p_ref = psnr_to(y.cpu().numpy(), z["x"]), psnr_to(z["y"], z["x"])
+    print(f"canvas PSNR vs target: ours {p_ours:.4f} dB, reference {p_ref:.4f} dB (reported, not gated)")
+
+
 def test_streaming_dehazer_matches_direct_calls():
     """fullres.StreamingDehazer (side-stream H2D / D2H, double-buffered) returns, image for image, exactly what the direct
     dehaze_tiled call returns; 5 different images through 2 slots exercise slot reuse in both directions."""

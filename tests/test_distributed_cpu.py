@@ -41,6 +41,21 @@ def _tiled_worker(rank, world, port, ref_path):
     out = fullres.dehaze_tiled(_TileModel(), img, ps=128)
     ref = torch.load(ref_path)
     assert torch.equal(out, ref), f"rank {rank}: sharded result differs from the single-process result"
+    # the caller-guaranteed form (bench.py): identical draws on every rank from a shared seed, no per-image broadcast;
+    # and the upload plan: NaN outside fullres.rows_needed must not reach this rank's tiles (rank 0's result is the image)
+    torch.manual_seed(100)
+    idx = _TileModel().draw_index_samples()
+    torch.manual_seed(8)
+    img2 = torch.rand(1, 3, 600, 380)                        # 640^2 canvas, 25 tiles: 13 / 12 per rank
+    rows = fullres.rows_needed(600, 380, rank, world)
+    assert rows == ([(0, 384)] if rank == 0 else [(0, 40), (256, 600)])
+    part = torch.full_like(img2, float("nan"))
+    for r0, r1 in rows:
+        part[:, :, r0:r1] = img2[:, :, r0:r1]
+    out2 = fullres.dehaze_tiled(_TileModel(), part, ps=128, index_samples=idx, broadcast_index_samples=False)
+    canvas = fullres.wrap_pad(img2, ps=128)
+    ref2 = fullres.from_tiles(_TileModel()(fullres.to_tiles(canvas, 128), index_samples=idx), 640, 128)[:, :, :600, :380].clamp(0, 1)
+    assert torch.equal(out2, ref2), f"rank {rank}: partial-upload / no-broadcast result differs"
     dist.destroy_process_group()
 
 

@@ -11,7 +11,12 @@ follows; paths are relative to ``/root/reference/Uformer_ProbSparse``.
 Parity pinning: the reference ships no tests or golden vectors for this path
 (SURVEY.md section 4).  The restatement is pinned against the reference itself,
 executed in the build container by ``oracle/make_golden.py`` (fixtures committed
-under ``tests/golden/``) and re-checked by ``tests/test_oracle_golden.py``.
+under ``tests/golden/``) and re-checked by ``tests/test_oracle_golden.py``: fp32 blocks
+(shift, input mask, DropPath, C = 32 ... 512) forward + backward, the whole model on
+tiles and in canvas mode, and - for the ``bf16=True`` emulation of the CUDA autocast
+rounding points - the reference run under ``torch.autocast("cpu", bfloat16)`` (agreement
+to one bf16 ulp of the activation scale, tie-aware top-u; the CPU autocast policy is not
+bit-identical to the CUDA one).
 
 Conventions: tokens are channel-last, ``x[B, L=H*W, C]``; windows are 8x8 (N=64);
 ``idx`` is the reference's ``index_sample`` int array ``[64, sample_k]`` drawn by the

@@ -292,7 +292,17 @@ def make_canvas_case(ref, name, H, W, seed, ps=128):
     idx = np.stack([i.numpy() for i in rec.idx])
     from oracle import uformer_oracle as U
     sd = {k: v.numpy() for k, v in model.state_dict().items()}
-    yo_raw = U.uformer_forward(big.numpy(), sd, idx, img_size=ps, dtype=np.float64)[:, :, :H, :W]
+    rec_o = []
+    yo_raw = U.uformer_forward(big.numpy(), sd, idx, img_size=ps, dtype=np.float64, record=rec_o)[:, :, :H, :W]
+    # per-block selection check: the oracle's top-u sets against the reference's M_top, block by block
+    ref_tops = [np.sort(t.numpy(), -1) for t in rec.top]
+    assert len(ref_tops) == len(rec_o) == 18
+    nrows = ndiff = 0
+    for r, t in zip(rec_o, ref_tops):
+        bad = (r["top"] != t).any(-1)
+        assert (r["rel_gap"][bad] < 1e-5).all(), (name, r["block"])
+        nrows += bad.size; ndiff += int(bad.sum())
+    print(f"{name}: top-u sets, oracle vs reference over the 18 blocks: {ndiff} of {nrows} rows differ (all near-ties)")
     er = np.abs(yo_raw - raw.numpy())
     print(f"{name}: raw output range [{raw.min():.2f}, {raw.max():.2f}]; numpy oracle vs reference (raw): max {er.max():.2e}, "
           f"median {np.median(er):.2e}, frac > 1e-3 {(er > 1e-3).mean():.4f}")
@@ -300,7 +310,8 @@ def make_canvas_case(ref, name, H, W, seed, ps=128):
     e = np.abs(yo - restored.numpy())
     print(f"{name}: canvas {L}^2; numpy oracle vs reference: max {e.max():.2e}, median {np.median(e):.2e}, frac > 1e-3 {(e > 1e-3).mean():.4f}")
     assert np.median(e) < 1e-4 and (e > 1e-3).mean() < 0.02
-    np.savez_compressed(os.path.join(GOLD, name + ".npz"), x=img.numpy(), y=restored.numpy(), y_raw=raw.numpy(), idx=idx.astype(np.int8), seed=np.int64(seed))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), x=img.numpy(), y=restored.numpy(), y_raw=raw.numpy(),
+                        **{f"top{i:02d}": t.astype(np.int8) for i, t in enumerate(ref_tops)}, idx=idx.astype(np.int8), seed=np.int64(seed))
 
 
 def main():

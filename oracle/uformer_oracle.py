@@ -37,8 +37,10 @@ def _block_params(sd, prefix):
     return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
 
 
-def uformer_forward(x, sd, idx, depths=(2,) * 9, img_size=128, win=8, dtype=np.float32):
-    """x [B,3,H,W] ndarray, sd state_dict as ndarrays, idx [18,64,25] index_sample draws in module order."""
+def uformer_forward(x, sd, idx, depths=(2,) * 9, img_size=128, win=8, dtype=np.float32, record=None):
+    """x [B,3,H,W] ndarray, sd state_dict as ndarrays, idx [18,64,25] index_sample draws in module order.
+    record: optional list; one dict per LeWin block (module order) with the block's input tokens, selected query sets
+    ``top`` and the rank-u / rank-(u+1) gaps ``rel_gap`` is appended (per-block, tie-aware model-level comparisons)."""
     sd = {k: (np.asarray(v).astype(dtype) if np.issubdtype(np.asarray(v).dtype, np.floating) else np.asarray(v))
           for k, v in sd.items()}
     x = x.astype(dtype)
@@ -50,7 +52,13 @@ def uformer_forward(x, sd, idx, depths=(2,) * 9, img_size=128, win=8, dtype=np.f
             if img_size // res_div <= win:                      # My_model_1.py:764-766
                 shift = 0
             p = _block_params(sd, f"{name}.blocks.{i}.")
-            tok = O.lewin_block(tok, p, shift, np.asarray(idx[next(it)]).astype(np.int64))
+            bi = next(it)
+            if record is None:
+                tok = O.lewin_block(tok, p, shift, np.asarray(idx[bi]).astype(np.int64))
+            else:
+                x_in = tok
+                tok, aux = O.lewin_block(tok, p, shift, np.asarray(idx[bi]).astype(np.int64), return_aux=True)
+                record.append(dict(block=bi, stage=name, shift=shift, x=x_in, top=aux["top"], rel_gap=aux["rel_gap"]))
         return tok
 
     def conv(t, w, b, **kw):

@@ -91,7 +91,17 @@ def test_whole_model_oracle_matches_reference_in_canvas_mode(golden_dir):
     sd = {k: v.numpy() for k, v in model.state_dict().items()}
     canvas = fullres.wrap_pad(torch.from_numpy(z["x"]), ps=128).numpy()
     assert canvas.shape == (1, 3, 384, 384)
-    raw = U.uformer_forward(canvas, sd, z["idx"].astype(np.int64), img_size=128, dtype=np.float32)[:, :, :200, :300]
+    rec = []
+    raw = U.uformer_forward(canvas, sd, z["idx"].astype(np.int64), img_size=128, dtype=np.float32, record=rec)[:, :, :200, :300]
+    # block by block: the selected query sets equal the reference's M_top on every row that is not a near-tie
+    assert len(rec) == 18
+    rows = 0
+    for r in rec:
+        ref_top = z[f"top{r['block']:02d}"].astype(np.int64)
+        bad = (r["top"] != ref_top).any(-1)
+        assert (r["rel_gap"][bad] < 1e-5).all(), r["block"]
+        rows += bad.size
+    assert rows == 26208
     e = np.abs(raw - z["y_raw"])
     assert np.median(e) < 1e-4 and (e > 1e-3).mean() < 0.02
     assert np.abs(np.clip(raw, 0, 1) - z["y"]).mean() < 1e-4

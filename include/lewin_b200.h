@@ -39,11 +39,11 @@ extern "C" {
 typedef struct CUstream_st* lewin_stream_t; /* == cudaStream_t */
 typedef struct CUevent_st*  lewin_event_t;  /* == cudaEvent_t  */
 
-#define LEWIN_ABI_VERSION 2
+#define LEWIN_ABI_VERSION 3
 
 /* error codes (negative) */
 #define LEWIN_E_NULL      (-1)  /* a required pointer is NULL */
-#define LEWIN_E_SHAPE     (-2)  /* unsupported dims (C % 32, head_dim != 32, H/W % 8, ...) */
+#define LEWIN_E_SHAPE     (-2)  /* unsupported dims (C % 32, head_dim = C / nH not in {32, 64, 128}, H/W % 8, ...) */
 #define LEWIN_E_ALIGN     (-3)  /* a pointer is not 16-byte aligned */
 #define LEWIN_E_WORKSPACE (-4)  /* workspace too small */
 #define LEWIN_E_DTYPE     (-5)  /* unknown dtype tag */
@@ -75,7 +75,8 @@ typedef struct CUevent_st*  lewin_event_t;  /* == cudaEvent_t  */
  * of being materialised (the two may be combined).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
-    int32_t B, H, W, C, nH;        /* head_dim = C / nH must be 32 */
+    int32_t B, H, W, C, nH;        /* head_dim = C / nH (d_keys = d_model // n_heads, attn.py:370-372) in {32, 64, 128};
+                                      32 (embed_dim 32, My_model_1.py:962) takes the register-resident bf16 kernels */
     int32_t shift;                 /* 0 or 4 (My_model_1.py:927) */
     int32_t windowed;              /* addressing mode, see above */
     int32_t use_rpb;               /* options.is_relative_position_bias (options.py:5, attn.py:227) */
@@ -115,7 +116,7 @@ typedef struct {
 } LewinAttnFwdArgs;
 
 #define LEWIN_ATTN_K_LNSTATS 0
-#define LEWIN_ATTN_K_CNT     1
+#define LEWIN_ATTN_K_CNT     1   /* retired in ABI 3: the sample-multiplicity table is built inside the core kernel */
 #define LEWIN_ATTN_K_QKV     2
 #define LEWIN_ATTN_K_CORE    3
 #define LEWIN_ATTN_K_OUT     4
@@ -134,7 +135,9 @@ typedef struct {
     float* d_ln_w;  float* d_ln_b; /* [C]  (ignored when windowed) */
     float* d_w_qkv; float* d_b_qkv;/* [3C, C], [3C] */
     float* d_w_out; float* d_b_out;/* [C, C], [C] */
-    float* d_rpb_table;            /* [225, nH] */
+    float* d_rpb_table;            /* [225, nH] (when fwd.rpb_table is given) */
+    float* d_rpb_dense;            /* [nH, 64, 64] gradient w.r.t. the gathered bias (when fwd.rpb_dense is given: the
+                                      relative_position_bias argument of AttentionLayer.forward, attn.py:385), or NULL */
 } LewinAttnBwdArgs;
 
 int lewin_attn_bwd_f32 (const LewinAttnBwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
@@ -142,11 +145,13 @@ int lewin_attn_bwd_bf16(const LewinAttnBwdArgs* a, void* workspace, size_t works
 
 /* ------------------------------------------------------------------------------------------
  * ProbAttention.forward alone (ProbSparse/attn.py:287-342) on already-projected q | k | v:
- * qkv is [B_*64, 3C] (columns q | k | v, head h at [h*32, h*32+32) of each third), ctx is
- * [B_*64, C] == the reference's returned context [B_, 64, nH, 32].  Forward only.
+ * qkv is [B_*64, 3C] (columns q | k | v, head h at [h*D, h*D+D) of each third, D = head_dim,
+ * C = nH * D), ctx is [B_*64, C] == the reference's returned context [B_, 64, nH, D].
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t B_, nH, use_rpb, nW_mask;
+    int32_t head_dim;              /* D in {32, 64, 128}; 0 = 32 */
+    int32_t reserved;
     const void*  qkv;
     void*        ctx;
     const float* rpb_table;        /* [225, nH] or NULL */
@@ -159,6 +164,21 @@ typedef struct {
 int lewin_probsparse_core_fwd_f32 (const LewinCoreFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 int lewin_probsparse_core_fwd_bf16(const LewinCoreFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs* a, int dtype);
+
+/* Backward of ProbAttention.forward (what autograd derives from attn.py:287-342) for the
+ * selection saved by the forward (`fwd.top`, required): dqkv [B_*64, 3C] is WRITTEN (dq is zero on the lazy rows),
+ * the bias gradients are ACCUMULATED into fp32 buffers the caller zero-initialises (either may be NULL). */
+typedef struct {
+    LewinCoreFwdArgs fwd;          /* same qkv / rpb / mask / top as the forward call (index_sample, ctx unused) */
+    const void* dctx;              /* [B_*64, C] gradient of the returned context */
+    void*       dqkv;              /* [B_*64, 3C] */
+    float*      d_rpb_table;       /* [225, nH], used when fwd.rpb_table is given */
+    float*      d_rpb_dense;       /* [nH, 64, 64], used when fwd.rpb_dense is given */
+} LewinCoreBwdArgs;
+
+int lewin_probsparse_core_bwd_f32 (const LewinCoreBwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+int lewin_probsparse_core_bwd_bf16(const LewinCoreBwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+size_t lewin_probsparse_core_bwd_workspace_bytes(const LewinCoreBwdArgs* a, int dtype);
 
 /* ------------------------------------------------------------------------------------------
  * LeFF half of the block (My_model_1.py:873 with LeFF.forward :496-534):
@@ -196,12 +216,8 @@ typedef struct {
 #define LEWIN_LEFF_K_FC1     1
 #define LEWIN_LEFF_K_DWCONV  2
 #define LEWIN_LEFF_K_FC2     3
-#define LEWIN_LEFF_K_FUSED   4   /* single fused kernel (bf16 inference, C <= 128) replaces slots 0-3 */
-#define LEWIN_LEFF_NKERNELS  5
+#define LEWIN_LEFF_NKERNELS  4
 
-/* 1 if lewin_leff_fwd_<dtype> will run the single fused kernel for these arguments (timing slot
- * LEWIN_LEFF_K_FUSED), 0 if it runs the four-kernel pipeline (slots 0-3). */
-int lewin_leff_fwd_is_fused(const LewinLeffFwdArgs* a, int dtype);
 /* Bit k set <=> the forward call will record timing slot k (LEWIN_ATTN_K_* / LEWIN_LEFF_K_*) for these arguments. */
 int lewin_attn_fwd_kernel_mask(const LewinAttnFwdArgs* a, int dtype);
 int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype);

@@ -202,7 +202,7 @@ def prob_attention(q, k, v, rpb, mask, idx, use_rpb=True, top=None, return_aux=F
     ctx[bi, hi, top] = rbf(np.matmul(rbf(p2, bf16), v), bf16)  # attn.py:271-272 (autocast: P2 cast to bf16)
     out = np.ascontiguousarray(ctx.transpose(0, 2, 1, 3))      # attn.py:342
     if return_aux:
-        return out, dict(M=M, top=top, rel_gap=rel_gap, p1=p1, p2=p2, q=q, k=k, v=v)
+        return out, dict(M=M, top=top, sel=sel, rel_gap=rel_gap, p1=p1, p2=p2, q=q, k=k, v=v)   # sel: the oracle's own selection
     return out
 
 
@@ -359,21 +359,14 @@ def leff_bwd(dout, z, p):
     return dz, g
 
 
-def window_attention_bwd(dout, xw, p, mask, idx, use_rpb=True, top=None):
-    """Gradient of ``window_attention`` wrt xw and the 9 live attention parameters.
+def prob_attention_bwd(dctx, aux, use_rpb=True):
+    """Gradient of ``prob_attention`` (what autograd derives from attn.py:287-342) for the selection in ``aux['top']``.
 
-    Gradient paths: index_sample, M and topk carry none; dq is non-zero only at the
+    dctx [B_,nH,64,D] (head-major like aux['q']).  Returns dq, dk, dv [B_,nH,64,D] and the gradient w.r.t. the gathered
+    bias ``rpb`` [nH,64,64].  Gradient paths: index_sample, M and topk carry none; dq is non-zero only at the
     selected rows; dv = P2^T dctx[top] + (1/64) * sum over the NON-selected rows of dctx."""
-    B_, L, C = xw.shape
-    _, aux = window_attention(xw, p, mask, idx, use_rpb, top=top, return_aux=True)
-    q, k, v, p1, p2, top, ctx = aux["q"], aux["k"], aux["v"], aux["p1"], aux["p2"], aux["top"], aux["ctx"]
-    nH, D = q.shape[1], q.shape[3]
-    pre = "attn.ProbSpare."
-    g = {}
-    do = dout.reshape(-1, C)
-    g[pre + "out_projection.weight"] = do.T @ ctx.reshape(-1, C)
-    g[pre + "out_projection.bias"] = do.sum(0)
-    dctx = (do @ p[pre + "out_projection.weight"]).reshape(B_, L, nH, D).transpose(0, 2, 1, 3)
+    q, k, v, p1, p2, top = aux["q"], aux["k"], aux["v"], aux["p1"], aux["p2"], aux["top"]
+    B_, nH, L, D = q.shape
     bi = np.arange(B_)[:, None, None]
     hi = np.arange(nH)[None, :, None]
     dctx_top = dctx[bi, hi, top]                                  # [B_,nH,u,D]
@@ -383,6 +376,29 @@ def window_attention_bwd(dout, xw, p, mask, idx, use_rpb=True, top=None):
     dv = np.matmul(p2.transpose(0, 1, 3, 2), dctx_top) + dmean
     dp2 = np.matmul(dctx_top, v.transpose(0, 1, 3, 2))
     da = _softmax_bwd(p2, dp2)
+    drpb = np.zeros((nH, L, L), dtype=q.dtype)
+    if use_rpb:
+        np.add.at(drpb, (np.broadcast_to(hi, top.shape).reshape(-1), top.reshape(-1)), da.reshape(-1, L))
+    ds = _softmax_bwd(p1, da) * q.dtype.type(1.0 / math.sqrt(D))
+    dq = np.zeros_like(q)
+    dq[bi, hi, top] = np.matmul(ds, k)
+    dk = np.matmul(ds.transpose(0, 1, 3, 2), q[bi, hi, top])
+    return dq, dk, dv, drpb, da
+
+
+def window_attention_bwd(dout, xw, p, mask, idx, use_rpb=True, top=None):
+    """Gradient of ``window_attention`` wrt xw and the 9 live attention parameters."""
+    B_, L, C = xw.shape
+    _, aux = window_attention(xw, p, mask, idx, use_rpb, top=top, return_aux=True)
+    q, top, ctx = aux["q"], aux["top"], aux["ctx"]
+    nH, D = q.shape[1], q.shape[3]
+    pre = "attn.ProbSpare."
+    g = {}
+    do = dout.reshape(-1, C)
+    g[pre + "out_projection.weight"] = do.T @ ctx.reshape(-1, C)
+    g[pre + "out_projection.bias"] = do.sum(0)
+    dctx = (do @ p[pre + "out_projection.weight"]).reshape(B_, L, nH, D).transpose(0, 2, 1, 3)
+    dq, dk, dv, _, da = prob_attention_bwd(dctx, aux, use_rpb)
     dtab = np.zeros_like(p["attn.relative_position_bias_table"])
     if use_rpb:
         ri = relative_position_index()
@@ -390,10 +406,6 @@ def window_attention_bwd(dout, xw, p, mask, idx, use_rpb=True, top=None):
         hh = np.broadcast_to(np.arange(nH)[None, :, None, None], rel.shape)
         np.add.at(dtab, (rel.reshape(-1), hh.reshape(-1)), da.reshape(-1))
     g["attn.relative_position_bias_table"] = dtab
-    ds = _softmax_bwd(p1, da) * q.dtype.type(1.0 / math.sqrt(D))
-    dq = np.zeros_like(q)
-    dq[bi, hi, top] = np.matmul(ds, k)
-    dk = np.matmul(ds.transpose(0, 1, 3, 2), q[bi, hi, top])
     x2 = xw.reshape(-1, C)
     dx = np.zeros_like(x2)
     for name, d in (("query", dq), ("key", dk), ("value", dv)):

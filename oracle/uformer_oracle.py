@@ -37,10 +37,13 @@ def _block_params(sd, prefix):
     return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
 
 
-def uformer_forward(x, sd, idx, depths=(2,) * 9, img_size=128, win=8, dtype=np.float32, record=None):
+def uformer_forward(x, sd, idx, depths=(2,) * 9, img_size=128, win=8, dtype=np.float32, record=None, force_tops=None):
     """x [B,3,H,W] ndarray, sd state_dict as ndarrays, idx [18,64,25] index_sample draws in module order.
     record: optional list; one dict per LeWin block (module order) with the block's input tokens, selected query sets
-    ``top`` and the rank-u / rank-(u+1) gaps ``rel_gap`` is appended (per-block, tie-aware model-level comparisons)."""
+    ``top`` and the rank-u / rank-(u+1) gaps ``rel_gap`` is appended (per-block, tie-aware model-level comparisons).
+    force_tops: optional list of 18 arrays [B_, nH, 25] (sorted): block i attends with that selection instead of its own
+    (``record`` then also carries ``sel``, the oracle's own choice on the same input) - how a device run whose near-tie rows
+    fell the other way is followed block by block."""
     sd = {k: (np.asarray(v).astype(dtype) if np.issubdtype(np.asarray(v).dtype, np.floating) else np.asarray(v))
           for k, v in sd.items()}
     x = x.astype(dtype)
@@ -53,12 +56,14 @@ def uformer_forward(x, sd, idx, depths=(2,) * 9, img_size=128, win=8, dtype=np.f
                 shift = 0
             p = _block_params(sd, f"{name}.blocks.{i}.")
             bi = next(it)
+            forced = None if force_tops is None else np.asarray(force_tops[bi]).astype(np.int64)
             if record is None:
-                tok = O.lewin_block(tok, p, shift, np.asarray(idx[bi]).astype(np.int64))
+                tok = O.lewin_block(tok, p, shift, np.asarray(idx[bi]).astype(np.int64), top=forced)
             else:
                 x_in = tok
-                tok, aux = O.lewin_block(tok, p, shift, np.asarray(idx[bi]).astype(np.int64), return_aux=True)
-                record.append(dict(block=bi, stage=name, shift=shift, x=x_in, top=aux["top"], rel_gap=aux["rel_gap"]))
+                tok, aux = O.lewin_block(tok, p, shift, np.asarray(idx[bi]).astype(np.int64), top=forced, return_aux=True)
+                record.append(dict(block=bi, stage=name, shift=shift, x=x_in, top=aux["top"], sel=aux["sel"],
+                                   rel_gap=aux["rel_gap"]))
         return tok
 
     def conv(t, w, b, **kw):

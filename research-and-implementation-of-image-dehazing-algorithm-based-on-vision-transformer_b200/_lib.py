@@ -37,15 +37,23 @@ class LewinAttnBwdArgs(C.Structure):
         ("fwd", LewinAttnFwdArgs),
         ("dy", c_ptr), ("dx", c_ptr),
         ("d_ln_w", c_ptr), ("d_ln_b", c_ptr), ("d_w_qkv", c_ptr), ("d_b_qkv", c_ptr),
-        ("d_w_out", c_ptr), ("d_b_out", c_ptr), ("d_rpb_table", c_ptr),
+        ("d_w_out", c_ptr), ("d_b_out", c_ptr), ("d_rpb_table", c_ptr), ("d_rpb_dense", c_ptr),
     ]
 
 
 class LewinCoreFwdArgs(C.Structure):
     _fields_ = [
         ("B_", C.c_int32), ("nH", C.c_int32), ("use_rpb", C.c_int32), ("nW_mask", C.c_int32),
+        ("head_dim", C.c_int32), ("reserved", C.c_int32),
         ("qkv", c_ptr), ("ctx", c_ptr), ("rpb_table", c_ptr), ("rpb_dense", c_ptr),
         ("index_sample", c_ptr), ("mask", c_ptr), ("top", c_ptr),
+    ]
+
+
+class LewinCoreBwdArgs(C.Structure):
+    _fields_ = [
+        ("fwd", LewinCoreFwdArgs),
+        ("dctx", c_ptr), ("dqkv", c_ptr), ("d_rpb_table", c_ptr), ("d_rpb_dense", c_ptr),
     ]
 
 
@@ -94,12 +102,13 @@ EXPORTS = (
     "lewin_attn_fwd_workspace_bytes", "lewin_attn_bwd_workspace_bytes",
     "lewin_leff_fwd_workspace_bytes", "lewin_leff_bwd_workspace_bytes",
     "lewin_probsparse_core_fwd_f32", "lewin_probsparse_core_fwd_bf16", "lewin_probsparse_core_fwd_workspace_bytes",
-    "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count", "lewin_leff_fwd_is_fused",
+    "lewin_probsparse_core_bwd_f32", "lewin_probsparse_core_bwd_bf16", "lewin_probsparse_core_bwd_workspace_bytes",
+    "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count",
     "lewin_attn_fwd_kernel_mask", "lewin_leff_fwd_kernel_mask",
     "lewin_upsample_fwd_bf16", "lewin_upsample_fwd_workspace_bytes", "lewin_input_proj_fwd_bf16",
 )
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DTYPE_TAG = {"f32": 0, "bf16": 1}
 
 _lib = None
@@ -117,7 +126,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     for name, args_t in (("attn_fwd", LewinAttnFwdArgs), ("attn_bwd", LewinAttnBwdArgs),
                          ("leff_fwd", LewinLeffFwdArgs), ("leff_bwd", LewinLeffBwdArgs),
-                         ("probsparse_core_fwd", LewinCoreFwdArgs)):
+                         ("probsparse_core_fwd", LewinCoreFwdArgs), ("probsparse_core_bwd", LewinCoreBwdArgs)):
         for dt in ("f32", "bf16"):
             fn = getattr(lib, f"lewin_{name}_{dt}")
             fn.argtypes = [C.POINTER(args_t), C.c_void_p, C.c_size_t, C.c_void_p]
@@ -132,8 +141,6 @@ def load():
     lib.lewin_input_proj_fwd_bf16.argtypes = [C.POINTER(LewinInputProjArgs), C.c_void_p]
     lib.lewin_input_proj_fwd_bf16.restype = C.c_int
     lib.lewin_abi_version.restype = C.c_int
-    lib.lewin_leff_fwd_is_fused.argtypes = [C.POINTER(LewinLeffFwdArgs), C.c_int]
-    lib.lewin_leff_fwd_is_fused.restype = C.c_int
     lib.lewin_attn_fwd_kernel_mask.argtypes = [C.POINTER(LewinAttnFwdArgs), C.c_int]
     lib.lewin_attn_fwd_kernel_mask.restype = C.c_int
     lib.lewin_leff_fwd_kernel_mask.argtypes = [C.POINTER(LewinLeffFwdArgs), C.c_int]

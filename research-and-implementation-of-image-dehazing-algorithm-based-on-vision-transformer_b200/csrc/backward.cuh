@@ -477,33 +477,37 @@ cudaError_t launch_dwconv_bwd(const T* g2, const T* a2, const T* h1, const T* a1
 }
 
 // ------------------------------------------------------------------------------ ProbSparse core backward
+// head_dim D in {32, 64, 128} (see CoreLd in probsparse_core.cuh)
+template <int D>
 struct CoreBwdSmem {
-    float q[kTok * QK_LD];
-    float k[kTok * QK_LD];
-    float v[kTok * QK_LD];
-    float dc[kTok * QK_LD];       // dctx tile
+    float q[kTok * CoreLd<D>::QK];
+    float k[kTok * CoreLd<D>::QK];
+    float v[kTok * CoreLd<D>::QK];
+    float dc[kTok * CoreLd<D>::QK];       // dctx tile
     float p1[32 * P_LD];
     float p2[32 * P_LD];
     float ds[32 * P_LD];          // dP2, then dS (scaled)
     float tbl[232];
     float tacc[16 * 225];         // d(rpb table) partials per head
-    float dmean[kHeadDim];
-    float dpart[4 * kHeadDim];
+    float dmean[D];
+    float dpart[4 * D];
     int tok_of[32];
     int slot_of[kTok];
     int region[kTok];
 };
 
-template <typename T>
+template <typename T, int D>
 __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const CoreBwdArgs<T> a) {
     constexpr int PASSES = Act<T>::kPasses;
+    constexpr int QK_LD = CoreLd<D>::QK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CoreBwdSmem& s = *reinterpret_cast<CoreBwdSmem*>(smem_raw);
+    CoreBwdSmem<D>& s = *reinterpret_cast<CoreBwdSmem<D>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;
     const int C3 = 3 * a.C;
-    const float scale = rsqrtf(static_cast<float>(kHeadDim));
+    const float scale = rsqrtf(static_cast<float>(D));
     const bool want_tab = a.d_rpb_table != nullptr && a.use_rpb;
+    const bool want_dense = a.d_rpb_dense != nullptr && a.use_rpb;
     for (int i = tid; i < 16 * 225; i += CORE_THREADS) s.tacc[i] = 0.f;
 
     const int items = a.B_ * a.nH;
@@ -512,12 +516,13 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
         const int h = item - wg * a.nH;
         __syncthreads();
         {   // stage q, k, v, dctx
-            const T* base = a.qkv + static_cast<long long>(wg) * kTok * C3 + h * kHeadDim;
-            const T* dbase = a.dctx + static_cast<long long>(wg) * kTok * a.C + h * kHeadDim;
-            for (int c = tid; c < 4 * kTok * 8; c += CORE_THREADS) {
-                const int which = c / (kTok * 8);
-                const int rem = c - which * kTok * 8;
-                const int r = rem >> 3, d4 = (rem & 7) * 4;
+            const T* base = a.qkv + static_cast<long long>(wg) * kTok * C3 + h * D;
+            const T* dbase = a.dctx + static_cast<long long>(wg) * kTok * a.C + h * D;
+            constexpr int CPR = D / 4;
+            for (int c = tid; c < 4 * kTok * CPR; c += CORE_THREADS) {
+                const int which = c / (kTok * CPR);
+                const int rem = c - which * kTok * CPR;
+                const int r = rem / CPR, d4 = (rem % CPR) * 4;
                 float4 v;
                 if (which < 3) v = ld4(base + static_cast<long long>(r) * C3 + which * a.C + d4);
                 else v = ld4(dbase + static_cast<long long>(r) * a.C + d4);
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
         }
         __syncthreads();
 
-        // ---- S_sel = Q[top] K^T * scale   (32 x 64 x 32): warp -> m-tile (warp&1), n-tiles 4*(warp>>1)..+3
+        // ---- S_sel = Q[top] K^T * scale   (32 x 64 x D): warp -> m-tile (warp&1), n-tiles 4*(warp>>1)..+3
         const int mt = warp & 1, nb4 = (warp >> 1) * 4;
         {
             float acc[4][4];
@@ -556,7 +561,7 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
             const float* q0 = s.q + (t0 < 0 ? 0 : t0) * QK_LD;
             const float* q1 = s.q + (t1 < 0 ? 0 : t1) * QK_LD;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < D / 8; ++ks) {
                 float af[4] = {q0[ks * 8 + tq], q1[ks * 8 + tq], q0[ks * 8 + tq + 4], q1[ks * 8 + tq + 4]};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -576,19 +581,19 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
                 }
         }
         // sum of dctx over the NON-selected rows / 64 (gradient of the mean(V) fill, attn.py:168-172)
-        {
-            const int d = tid & 31, part = tid >> 5;
+        for (int e = tid; e < 4 * D; e += CORE_THREADS) {
+            const int d = e % D, part = e / D;
             float sum = 0.f;
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const int row = part * 16 + r;
                 if (s.slot_of[row] < 0) sum += s.dc[row * QK_LD + d];
             }
-            s.dpart[part * kHeadDim + d] = sum;
+            s.dpart[part * D + d] = sum;
         }
         __syncthreads();
-        if (tid < kHeadDim)
-            s.dmean[tid] = (s.dpart[tid] + s.dpart[32 + tid] + s.dpart[64 + tid] + s.dpart[96 + tid]) * (1.0f / kTok);
+        for (int d = tid; d < D; d += CORE_THREADS)
+            s.dmean[d] = (s.dpart[d] + s.dpart[D + d] + s.dpart[2 * D + d] + s.dpart[3 * D + d]) * (1.0f / kTok);
 
         // ---- recompute P1, P2 (attn.py:195-264)
         for (int slot = warp; slot < 32; slot += 4) {
@@ -629,7 +634,7 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
         }
         __syncthreads();
 
-        // ---- dP2 = dctx[top] V^T  (32 x 64 x 32)
+        // ---- dP2 = dctx[top] V^T  (32 x 64 x D)
         {
             float acc[4][4];
 #pragma unroll
@@ -641,7 +646,7 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
             const float* d1 = s.dc + (t1 < 0 ? 0 : t1) * QK_LD;
             const float z0 = t0 < 0 ? 0.f : 1.f, z1 = t1 < 0 ? 0.f : 1.f;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < D / 8; ++ks) {
                 float af[4] = {d0[ks * 8 + tq] * z0, d1[ks * 8 + tq] * z1, d0[ks * 8 + tq + 4] * z0, d1[ks * 8 + tq + 4] * z1};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -659,7 +664,7 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
         }
         __syncthreads();
 
-        // ---- softmax backward twice: dA = P2 * (dP2 - <dP2,P2>); d(table) += dA; dS = P1 * (dA - <dA,P1>) * scale
+        // ---- softmax backward twice: dA = P2 * (dP2 - <dP2,P2>); d(bias) += dA; dS = P1 * (dA - <dA,P1>) * scale
         for (int slot = warp; slot < 32; slot += 4) {
             float* rd = s.ds + slot * P_LD;
             if (slot >= kTopU) { rd[lane] = 0.f; rd[lane + 32] = 0.f; continue; }
@@ -675,6 +680,11 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
                 atomicAdd(&s.tacc[h * 225 + (ry - (lane >> 3) + 7) * 15 + (rx - (lane & 7) + 7)], da0);
                 atomicAdd(&s.tacc[h * 225 + (ry - ((lane + 32) >> 3) + 7) * 15 + (rx - (lane & 7) + 7)], da1);
             }
+            if (want_dense) {       // gradient w.r.t. the gathered bias [nH, 64, 64] (AttentionLayer.forward's argument, attn.py:385)
+                float* drow = a.d_rpb_dense + (static_cast<long long>(h) * kTok + r) * kTok;
+                atomicAdd(drow + lane, da0);
+                atomicAdd(drow + lane + 32, da1);
+            }
             const float p0 = r1[lane], p1v = r1[lane + 32];
             dot = group_sum<32>(da0 * p0 + da1 * p1v);
             rd[lane] = p0 * (da0 - dot) * scale;
@@ -682,13 +692,14 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
         }
         __syncthreads();
 
-        T* obase = a.dqkv + static_cast<long long>(wg) * kTok * C3 + h * kHeadDim;
-        // ---- dq[top] = dS K  (32 x 32 x 64): warp -> m-tile (warp&1), n-tiles 2*(warp>>1)..+1 ; other rows zero
+        T* obase = a.dqkv + static_cast<long long>(wg) * kTok * C3 + h * D;
+        // ---- dq[top] = dS K  (32 x D x 64): warp -> m-tile (warp&1), D/16 n-tiles ; other rows zero
         {
-            const int nb2 = (warp >> 1) * 2;
-            float o[2][4];
+            constexpr int NT = D / 16;
+            const int nb2 = (warp >> 1) * NT;
+            float o[NT][4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < NT; ++j)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) o[j][c] = 0.f;
 #pragma unroll
@@ -696,7 +707,7 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
                 const float* pa = s.ds + (mt * 16 + gq) * P_LD + ks * 8 + tq;
                 float af[4] = {pa[0], pa[8 * P_LD], pa[4], pa[8 * P_LD + 4]};
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < NT; ++j) {
                     const float* pb = s.k + (ks * 8 + tq) * QK_LD + (nb2 + j) * 8 + gq;
                     float bf[2] = {pb[0], pb[4 * QK_LD]};
                     mma_x<PASSES>(o[j], af, bf);
@@ -707,17 +718,18 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
                 const int r = s.tok_of[mt * 16 + gq + half * 8];
                 if (r >= 0) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < NT; ++j)
                         st2(obase + static_cast<long long>(r) * C3 + (nb2 + j) * 8 + 2 * tq, o[j][half * 2], o[j][half * 2 + 1]);
                 }
             }
-            for (int c = tid; c < kTok * 8; c += CORE_THREADS) {
-                const int r = c >> 3, d4 = (c & 7) * 4;
+            for (int c = tid; c < kTok * (D / 4); c += CORE_THREADS) {
+                const int r = c / (D / 4), d4 = (c % (D / 4)) * 4;
                 if (s.slot_of[r] < 0) st4(obase + static_cast<long long>(r) * C3 + d4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
         }
-        // ---- dK = dS^T Q[top] ; dV = P2^T dctx[top] + dmean   (64 x 32 x 32slots): warp -> m-tile `warp`, 4 n-tiles
-        {
+        // ---- dK = dS^T Q[top] ; dV = P2^T dctx[top] + dmean   (64 x D x 32slots): warp -> m-tile `warp`, 4 n-tiles per pass
+#pragma unroll 1
+        for (int n0 = 0; n0 < D / 8; n0 += 4) {
             float ok[4][4], ov[4][4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -737,8 +749,8 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
                 const float* db = s.dc + (s1 < 0 ? 0 : s1) * QK_LD;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float bq[2] = {qa[j * 8 + gq], qb[j * 8 + gq]};
-                    float bd[2] = {da[j * 8 + gq], db[j * 8 + gq]};
+                    float bq[2] = {qa[(n0 + j) * 8 + gq], qb[(n0 + j) * 8 + gq]};
+                    float bd[2] = {da[(n0 + j) * 8 + gq], db[(n0 + j) * 8 + gq]};
                     mma_x<PASSES>(ok[j], ak, bq);
                     mma_x<PASSES>(ov[j], av, bd);
                 }
@@ -748,7 +760,7 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
                 const int r = warp * 16 + gq + half * 8;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int d = j * 8 + 2 * tq;
+                    const int d = (n0 + j) * 8 + 2 * tq;
                     st2(obase + static_cast<long long>(r) * C3 + a.C + d, ok[j][half * 2], ok[j][half * 2 + 1]);
                     st2(obase + static_cast<long long>(r) * C3 + 2 * a.C + d, ov[j][half * 2] + s.dmean[d],
                         ov[j][half * 2 + 1] + s.dmean[d + 1]);
@@ -766,20 +778,30 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_bwd_kernel(const
     }
 }
 
-template <typename T>
-cudaError_t launch_core_bwd(const CoreBwdArgs<T>& a, int num_sms, cudaStream_t stream) {
-    if constexpr (Act<T>::kIsBf16) {
-        if (pcb2::enabled()) return pcb2::launch(a, num_sms, stream);      // register-resident bf16 path
-    }
-    auto k = probsparse_core_bwd_kernel<T>;
-    const size_t smem = sizeof(CoreBwdSmem);
+template <typename T, int D>
+cudaError_t launch_core_bwd_d(const CoreBwdArgs<T>& a, int num_sms, cudaStream_t stream) {
+    auto k = probsparse_core_bwd_kernel<T, D>;
+    const size_t smem = sizeof(CoreBwdSmem<D>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     long long items = static_cast<long long>(a.B_) * a.nH;
-    long long cap = static_cast<long long>(num_sms) * 2 * 2;
+    const int resident = static_cast<int>((227 * 1024) / (smem + 1024));
+    long long cap = static_cast<long long>(num_sms) * (resident < 1 ? 1 : resident > 2 ? 2 : resident) * 2;
     unsigned grid = static_cast<unsigned>(items < cap ? items : cap);
     k<<<grid, CORE_THREADS, smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_core_bwd(const CoreBwdArgs<T>& a, int num_sms, cudaStream_t stream) {
+    const int D = a.C / a.nH;
+    if constexpr (Act<T>::kIsBf16) {
+        if (D == 32 && pcb2::enabled()) return pcb2::launch(a, num_sms, stream);      // register-resident bf16 path
+    }
+    if (D == 32) return launch_core_bwd_d<T, 32>(a, num_sms, stream);
+    if (D == 64) return launch_core_bwd_d<T, 64>(a, num_sms, stream);
+    if (D == 128) return launch_core_bwd_d<T, 128>(a, num_sms, stream);
+    return cudaErrorInvalidValue;
 }
 
 // ------------------------------------------------------------------------------ host orchestration
@@ -873,7 +895,7 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     if (!f.x || !f.w_qkv || !f.w_out || !f.qkv || !f.ctx || !f.top) return LEWIN_E_NULL;
     if (!a->d_w_qkv || !a->d_b_qkv || !a->d_w_out || !a->d_b_out) return LEWIN_E_NULL;
     if (!f.windowed && (!f.ln_w || !f.ln_b || !a->d_ln_w || !a->d_ln_b)) return LEWIN_E_NULL;
-    if (f.H % 8 || f.W % 8 || f.C % 32 || f.C != f.nH * kHeadDim || f.C > 512 || f.nH > 16) return LEWIN_E_SHAPE;
+    if (f.H % 8 || f.W % 8 || f.C % 32 || !head_dim_ok(f.C, f.nH) || f.C > 512 || f.nH > 16) return LEWIN_E_SHAPE;
     int sms = 0;
     if (int rc = bw_device(&sms)) return rc;
     const int dtype = Act<T>::kIsBf16 ? LEWIN_DTYPE_BF16 : LEWIN_DTYPE_F32;
@@ -927,6 +949,7 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         c.qkv = static_cast<const T*>(f.qkv); c.dctx = dctx; c.dqkv = dqkv; c.top = f.top;
         c.rpb_table = f.rpb_table; c.rpb_dense = f.rpb_table ? nullptr : f.rpb_dense;
         c.d_rpb_table = a->d_rpb_table;
+        c.d_rpb_dense = a->d_rpb_dense;
         c.mask = f.mask; c.nW_mask = f.mask ? f.nW_mask : 1;
         c.B_ = B_; c.nH = f.nH; c.C = C; c.use_rpb = f.use_rpb;
         c.shift = (f.analytic_shift_mask && !f.windowed) ? f.shift : 0;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 
 namespace lewin {
 
@@ -10,7 +12,13 @@ constexpr int kWin = 8;
 constexpr int kTok = 64;
 constexpr int kTopU = 25;
 constexpr int kSampleK = 25;
-constexpr int kHeadDim = 32;
+constexpr int kHeadDim = 32;      // head_dim of the embed_dim = 32 model (the register-resident bf16 kernels are specialised for it)
+// head_dim = C / nH as ProbSparse/attn.py:370-372 derives it; {32, 64, 128} are built (BASELINE config 5: embed_dim 32-128)
+inline bool head_dim_ok(int C, int nH) {
+    if (nH <= 0 || C % nH) return false;
+    const int d = C / nH;
+    return d == 32 || d == 64 || d == 128;
+}
 
 // ---------------------------------------------------------------- activation dtype traits
 template <typename T> struct Act;
@@ -172,9 +180,42 @@ __global__ void gelu_tab_init_kernel() {
     g_gelu_tab[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf(x)));
     g_gelu_grad_tab[i] = __bfloat16_as_ushort(__float2bfloat16_rn(gelu_erf_grad(x)));
 }
-inline cudaError_t launch_gelu_tab_init(cudaStream_t st) {       // idempotent; a few microseconds
+// The tables are constants of the library: they are filled ONCE per device (round 1 relaunched the fill in front of every
+// LeFF call: 18 launches per forward).  state 0 = never launched, 1 = launched, completion event pending, 2 = complete.
+// A caller whose stream is being captured into a CUDA graph before the tables are complete gets the (idempotent) fill
+// captured into its graph instead; other streams are ordered behind the first fill by its event.
+struct GeluTabInit { std::atomic<int> state{0}; cudaEvent_t ev{nullptr}; std::mutex mu; };
+inline GeluTabInit& gelu_tab_state(int dev) { static GeluTabInit st[64]; return st[dev & 63]; }
+inline cudaError_t launch_gelu_tab_init(cudaStream_t st) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    GeluTabInit& g = gelu_tab_state(dev);
+    if (g.state.load(std::memory_order_acquire) == 2) return cudaSuccess;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    e = cudaStreamIsCapturing(st, &cs);
+    if (e != cudaSuccess) return e;
+    if (cs != cudaStreamCaptureStatusNone) {              // inside a capture: keep the graph self-contained
+        gelu_tab_init_kernel<<<kGelu2TabSize / 256, 256, 0, st>>>();
+        return cudaGetLastError();
+    }
+    std::lock_guard<std::mutex> lk(g.mu);
+    const int s = g.state.load(std::memory_order_acquire);
+    if (s == 2) return cudaSuccess;
+    if (s == 1) {
+        if (cudaEventQuery(g.ev) == cudaSuccess) { g.state.store(2, std::memory_order_release); return cudaSuccess; }
+        (void)cudaGetLastError();                         // cudaErrorNotReady is not sticky, clear it
+        return cudaStreamWaitEvent(st, g.ev, 0);
+    }
     gelu_tab_init_kernel<<<kGelu2TabSize / 256, 256, 0, st>>>();
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(g.ev, st);
+    if (e != cudaSuccess) return e;
+    g.state.store(1, std::memory_order_release);
+    return cudaSuccess;
 }
 __device__ __forceinline__ void gelu_tab_to_smem(uint16_t* dst, int tid, int nthreads) {
     for (int i = tid; i < kGeluTabSize / 8; i += nthreads)

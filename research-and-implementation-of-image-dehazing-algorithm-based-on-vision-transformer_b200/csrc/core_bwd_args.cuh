@@ -12,6 +12,7 @@ struct CoreBwdArgs {
     const uint8_t* top;      // [B_, nH, 25]
     const float* rpb_table; const float* rpb_dense;
     float* d_rpb_table;      // [225, nH] accumulated (null => skipped)
+    float* d_rpb_dense;      // [nH, 64, 64] accumulated: gradient w.r.t. the gathered bias (null => skipped)
     const float* mask; int nW_mask;
     int B_, nH, C, use_rpb;
     int shift, H, W, nWw, nWin;

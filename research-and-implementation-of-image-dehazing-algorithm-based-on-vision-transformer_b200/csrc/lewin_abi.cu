@@ -7,7 +7,6 @@
 #include "gemm_fused.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
-#include "leff_fused.cuh"
 #include "probsparse_core.cuh"
 #include "probsparse_core_bf16.cuh"
 #include "probsparse_core_v3.cuh"
@@ -81,7 +80,7 @@ int check_attn(const LewinAttnFwdArgs* a) {
     if (!a->windowed && (!a->ln_w || !a->ln_b)) return LEWIN_E_NULL;
     if (a->use_rpb && !a->rpb_table && !a->rpb_dense) return LEWIN_E_NULL;
     if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->nH <= 0) return LEWIN_E_SHAPE;
-    if (a->H % 8 || a->W % 8 || a->C % 32 || a->C != a->nH * kHeadDim) return LEWIN_E_SHAPE;
+    if (a->H % 8 || a->W % 8 || a->C % 32 || !head_dim_ok(a->C, a->nH)) return LEWIN_E_SHAPE;
     if (a->shift < 0 || a->shift >= 8) return LEWIN_E_SHAPE;
     if (a->shift > 0 && (a->H <= 8 || a->W <= 8)) return LEWIN_E_SHAPE;   // My_model_1.py:764-766 forces shift 0
     if (a->windowed && (a->shift != 0 || a->analytic_shift_mask)) return LEWIN_E_SHAPE;
@@ -98,7 +97,7 @@ size_t attn_fwd_ws(const LewinAttnFwdArgs* a) {
     const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
     // + bf16 staging for the async tcgen05 GEMMs (C > 128): LN-applied window-ordered x, bf16 copies of W_qkv / W_out
     const size_t C = a->C;
-    return 2 * align_up(tokens * sizeof(float), 256) + align_up(kTok * kTok, 256) + align_up(kTok * kTok * 4, 256) +
+    return 2 * align_up(tokens * sizeof(float), 256) +
            (C >= 64 ? align_up(tokens * C * 2, 256) + align_up(4 * C * C * 2, 256) : 0);
 }
 
@@ -117,8 +116,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     unsigned char* wsp = static_cast<unsigned char*>(ws);
     float* mean = reinterpret_cast<float*>(wsp);
     float* rstd = reinterpret_cast<float*>(wsp + align_up(tokens * sizeof(float), 256));
-    uint8_t* cnt = wsp + 2 * align_up(tokens * sizeof(float), 256);
-    __half2* cw = reinterpret_cast<__half2*>(cnt + align_up(kTok * kTok, 256));
+    unsigned char* ws_gemm = wsp + 2 * align_up(tokens * sizeof(float), 256);      // bf16 staging of the streamed-W GEMMs
 
     WinMap map{a->H, a->W, a->W / 8, nWin, a->shift};
     const T* x = static_cast<const T*>(a->x);
@@ -130,18 +128,12 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         CK(launch_ln_stats<T>(x, tokens, C, mean, rstd, stream));
         kt.end(LEWIN_ATTN_K_LNSTATS);
     }
-    kt.begin(LEWIN_ATTN_K_CNT);
-    if constexpr (Act<T>::kIsBf16) build_cw_kernel<<<1, 256, 0, stream>>>(a->index_sample, cw);
-    else build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
-    CK(cudaGetLastError());
-    kt.end(LEWIN_ATTN_K_CNT);
-
     bool async_gemm = false;
     __nv_bfloat16* xhat = nullptr; __nv_bfloat16* wqkv_b = nullptr; __nv_bfloat16* wout_b = nullptr;
     if constexpr (Act<T>::kIsBf16) {
         async_gemm = plan.async_gemm;
         if (async_gemm) {
-            unsigned char* q = reinterpret_cast<unsigned char*>(cw) + align_up(kTok * kTok * 4, 256);
+            unsigned char* q = ws_gemm;
             xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
             wqkv_b = reinterpret_cast<__nv_bfloat16*>(q);
             wout_b = wqkv_b + static_cast<size_t>(3) * C * C;
@@ -189,7 +181,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         c.top = a->top;
         c.rpb_table = a->rpb_table;
         c.rpb_dense = a->rpb_table ? nullptr : a->rpb_dense;
-        c.cnt = cnt;
+        c.index_sample = a->index_sample;
         c.mask = a->mask; c.nW_mask = a->mask ? a->nW_mask : 1;
         c.B_ = B_; c.nH = a->nH; c.C = C;
         c.use_rpb = a->use_rpb;
@@ -197,11 +189,16 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         c.H = a->H; c.W = a->W; c.nWw = a->W / 8; c.nWin = nWin;
         kt.begin(LEWIN_ATTN_K_CORE);
         if constexpr (Act<T>::kIsBf16) {
-            CoreBf16Args b{};
-            b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense; b.cw = cw;
-            b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
-            b.shift = c.shift; b.H = c.H; b.W = c.W; b.nWw = c.nWw; b.nWin = c.nWin;
-            CK(pc3::enabled() ? pc3::launch(b, di.sms, stream) : launch_core_bf16(b, di.sms, stream));
+            if (C == a->nH * kHeadDim && pc3::enabled()) {       // head_dim 32: register-resident kernel
+                CoreBf16Args b{};
+                b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense;
+                b.index_sample = c.index_sample;
+                b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
+                b.shift = c.shift; b.H = c.H; b.W = c.W; b.nWw = c.nWw; b.nWin = c.nWin;
+                CK(pc3::launch(b, di.sms, stream));
+            } else {
+                CK(launch_core_fwd<T>(c, di.sms, stream));
+            }
         } else {
             CK(launch_core_fwd<T>(c, di.sms, stream));
         }
@@ -241,42 +238,75 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     return 0;
 }
 
-template <typename T>
-int core_only_fwd(const LewinCoreFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    if (!a || !a->qkv || !a->ctx || !a->index_sample) return LEWIN_E_NULL;
+inline int core_head_dim(const LewinCoreFwdArgs* a) { return a->head_dim > 0 ? a->head_dim : kHeadDim; }
+
+int check_core(const LewinCoreFwdArgs* a) {
+    if (!a || !a->qkv || !a->ctx) return LEWIN_E_NULL;
     if (a->use_rpb && !a->rpb_table && !a->rpb_dense) return LEWIN_E_NULL;
-    if (a->B_ <= 0 || a->nH <= 0) return LEWIN_E_SHAPE;
+    const int D = core_head_dim(a);
+    if (a->B_ <= 0 || a->nH <= 0 || !(D == 32 || D == 64 || D == 128)) return LEWIN_E_SHAPE;
     if (a->mask && (a->nW_mask <= 0 || a->B_ % a->nW_mask)) return LEWIN_E_SHAPE;
     if (!aligned16(a->qkv) || !aligned16(a->ctx) || (a->mask && !aligned16(a->mask))) return LEWIN_E_ALIGN;
+    return 0;
+}
+
+template <typename T>
+int core_only_fwd(const LewinCoreFwdArgs* a, void*, size_t, cudaStream_t stream) {
+    if (int rc = check_core(a)) return rc;
+    if (!a->index_sample) return LEWIN_E_NULL;
     DeviceInfo di;
     if (int rc = device_info(&di)) return rc;
-    if (!ws || ws_bytes < static_cast<size_t>(kTok * kTok * 5)) return LEWIN_E_WORKSPACE;
-    if (!aligned16(ws)) return LEWIN_E_ALIGN;
-    uint8_t* cnt = static_cast<uint8_t*>(ws);
-    __half2* cw = reinterpret_cast<__half2*>(cnt + kTok * kTok);
-    if constexpr (Act<T>::kIsBf16) build_cw_kernel<<<1, 256, 0, stream>>>(a->index_sample, cw);
-    else build_cnt_kernel<<<1, 64, 0, stream>>>(a->index_sample, cnt);
-    CK(cudaGetLastError());
+    const int D = core_head_dim(a);
     CoreFwdArgs<T> c{};
     c.qkv = static_cast<const T*>(a->qkv);
     c.ctx = static_cast<T*>(a->ctx);
     c.top = a->top;
     c.rpb_table = a->rpb_table;
     c.rpb_dense = a->rpb_table ? nullptr : a->rpb_dense;
-    c.cnt = cnt;
+    c.index_sample = a->index_sample;
     c.mask = a->mask; c.nW_mask = a->mask ? a->nW_mask : 1;
-    c.B_ = a->B_; c.nH = a->nH; c.C = a->nH * kHeadDim;
+    c.B_ = a->B_; c.nH = a->nH; c.C = a->nH * D;
     c.use_rpb = a->use_rpb;
     c.shift = 0; c.H = 8; c.W = 8; c.nWw = 1; c.nWin = 1;
+    bool done = false;
     if constexpr (Act<T>::kIsBf16) {
-        CoreBf16Args b{};
-        b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense; b.cw = cw;
-        b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
-        b.shift = 0; b.H = 8; b.W = 8; b.nWw = 1; b.nWin = 1;
-        CK(pc3::enabled() ? pc3::launch(b, di.sms, stream) : launch_core_bf16(b, di.sms, stream));
-    } else
-    CK(launch_core_fwd<T>(c, di.sms, stream));
-    g_launches.fetch_add(2, std::memory_order_relaxed);
+        if (D == kHeadDim && pc3::enabled()) {
+            CoreBf16Args b{};
+            b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense;
+            b.index_sample = c.index_sample;
+            b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
+            b.shift = 0; b.H = 8; b.W = 8; b.nWw = 1; b.nWin = 1;
+            CK(pc3::launch(b, di.sms, stream));
+            done = true;
+        }
+    }
+    if (!done) CK(launch_core_fwd<T>(c, di.sms, stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+// autograd of ProbAttention.forward for the saved selection: dq | dk | dv, d(bias)
+template <typename T>
+int core_only_bwd(const LewinCoreBwdArgs* a, void*, size_t, cudaStream_t stream) {
+    if (!a) return LEWIN_E_NULL;
+    const LewinCoreFwdArgs* f = &a->fwd;
+    if (int rc = check_core(f)) return rc;
+    if (!f->top || !a->dctx || !a->dqkv) return LEWIN_E_NULL;
+    if (f->nH > 16) return LEWIN_E_SHAPE;
+    if (!aligned16(a->dctx) || !aligned16(a->dqkv)) return LEWIN_E_ALIGN;
+    int sms = 0;
+    if (int rc = bw_device(&sms)) return rc;
+    const int D = core_head_dim(f);
+    CoreBwdArgs<T> c{};
+    c.qkv = static_cast<const T*>(f->qkv); c.dctx = static_cast<const T*>(a->dctx); c.dqkv = static_cast<T*>(a->dqkv);
+    c.top = f->top;
+    c.rpb_table = f->rpb_table; c.rpb_dense = f->rpb_table ? nullptr : f->rpb_dense;
+    c.d_rpb_table = a->d_rpb_table; c.d_rpb_dense = f->rpb_table ? nullptr : a->d_rpb_dense;
+    c.mask = f->mask; c.nW_mask = f->mask ? f->nW_mask : 1;
+    c.B_ = f->B_; c.nH = f->nH; c.C = f->nH * D; c.use_rpb = f->use_rpb;
+    c.shift = 0; c.H = 8; c.W = 8; c.nWw = 1; c.nWin = 1;
+    CK(launch_core_bwd<T>(c, sms, stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
@@ -299,29 +329,23 @@ int check_leff(const LewinLeffFwdArgs* a) {
 size_t leff_fwd_ws(const LewinLeffFwdArgs* a) {
     const size_t tokens = static_cast<size_t>(a->B) * a->H * a->W;
     const size_t C = a->C, Ch = a->hidden;
-    return 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(a->C), 256) +
+    return 2 * align_up(tokens * sizeof(float), 256) +
            (C >= 64 ? align_up(tokens * C * 2, 256) + align_up(2 * C * Ch * 2, 256) : 0);
 }
 
-// bf16 LeFF at C <= 128: LEWIN_LEFF=fused selects the single on-chip kernel (leff_fused.cuh); the default is the
-// three-kernel pipeline on the warp-specialised GEMM (h1 / h2 round-trip HBM once each, every kernel HBM-bound).
-struct LeffPlan { bool fused_kernel, ws_gemm, async_gemm, ln_stats; };
+// bf16 LeFF: three kernels (linear1 + GELU, depthwise 3x3 + GELU, linear2 + residual); h1 / h2 round-trip HBM once each.
+// (A single on-chip kernel was built and measured 2-3x slower in round 1 - halo recompute of linear1 and per-tile staging
+// cost more instructions than the 8 bytes per hidden element of HBM traffic they save - and has been removed.)
+struct LeffPlan { bool ws_gemm, async_gemm, ln_stats; };
 inline LeffPlan plan_leff(const LewinLeffFwdArgs* a, bool bf) {
-    static const bool want_fused = [] { const char* e = getenv("LEWIN_LEFF"); return e && e[0] == 'f'; }();
-    static const bool fused_off = [] { const char* e = getenv("LEWIN_NO_FUSED_LEFF"); return e && e[0] == '1'; }();
     LeffPlan p{};
     const long long tokens = static_cast<long long>(a->B) * a->H * a->W;
-    const bool fused_ok = bf && !fused_off && a->fused && !a->save_for_backward && leff_fused_supported(a->C, a->hidden) &&
-                          a->H % 8 == 0 && a->W % 8 == 0;
-    const bool ws_ok = bf && a->fused && a->hidden == 4 * a->C && ws_level(a->C, tokens);
-    p.fused_kernel = fused_ok && (want_fused || !ws_ok);
-    p.ws_gemm = !p.fused_kernel && ws_ok;
-    p.async_gemm = bf && !p.fused_kernel && !p.ws_gemm && a->C > async_min_c() && a->C % 64 == 0 && a->hidden % 64 == 0 &&
+    p.ws_gemm = bf && a->fused && a->hidden == 4 * a->C && ws_level(a->C, tokens);
+    p.async_gemm = bf && !p.ws_gemm && a->C > async_min_c() && a->C % 64 == 0 && a->hidden % 64 == 0 &&
                    !getenv("LEWIN_NO_ASYNC_GEMM");
-    p.ln_stats = !p.fused_kernel && a->fused && !p.async_gemm && !p.ws_gemm;
+    p.ln_stats = a->fused && !p.async_gemm && !p.ws_gemm;
     return p;
 }
-bool leff_use_fused(const LewinLeffFwdArgs* a, bool is_bf16) { return plan_leff(a, is_bf16).fused_kernel; }
 
 template <typename T>
 int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -341,28 +365,12 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     const KTimer kt{a->timing, stream};
     const LeffPlan plan = plan_leff(a, Act<T>::kIsBf16);
     if constexpr (Act<T>::kIsBf16) CK(launch_gelu_tab_init(stream));     // idempotent 8 KB table (common.cuh)
-    if constexpr (Act<T>::kIsBf16) {
-        // one kernel, hidden activations stay on chip (leff_fused.cuh)
-        if (plan.fused_kernel) {
-            LeffFusedArgs fa{};
-            fa.y = static_cast<const __nv_bfloat16*>(a->y);
-            fa.out = static_cast<__nv_bfloat16*>(a->out);
-            fa.ln_w = a->ln_w; fa.ln_b = a->ln_b; fa.w1 = a->w1; fa.b1 = a->b1;
-            fa.w_dw = a->w_dw; fa.b_dw = a->b_dw; fa.w2 = a->w2; fa.b2 = a->b2;
-            fa.drop_scale = a->drop_scale; fa.B = a->B; fa.H = a->H; fa.W = a->W;
-            fa.wimg = wsp + 2 * align_up(tokens * sizeof(float), 256);
-            kt.begin(LEWIN_LEFF_K_FUSED);
-            CK(launch_leff_fused(C, fa, stream));
-            kt.end(LEWIN_LEFF_K_FUSED);
-            return 0;
-        }
-    }
     bool async_gemm = false;
     __nv_bfloat16* xhat = nullptr; __nv_bfloat16* w1b = nullptr; __nv_bfloat16* w2b = nullptr;
     if constexpr (Act<T>::kIsBf16) {
         async_gemm = plan.async_gemm;
         if (async_gemm) {
-            unsigned char* q = wsp + 2 * align_up(tokens * sizeof(float), 256) + align_up(leff_img_bytes(C), 256);
+            unsigned char* q = wsp + 2 * align_up(tokens * sizeof(float), 256);
             xhat = reinterpret_cast<__nv_bfloat16*>(q); q += align_up(static_cast<size_t>(tokens) * C * 2, 256);
             w1b = reinterpret_cast<__nv_bfloat16*>(q);
             w2b = w1b + static_cast<size_t>(C) * Ch;
@@ -587,19 +595,22 @@ int lewin_probsparse_core_fwd_f32(const LewinCoreFwdArgs* a, void* ws, size_t n,
 int lewin_probsparse_core_fwd_bf16(const LewinCoreFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
     return core_only_fwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
 }
-size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs*, int) { return kTok * kTok * 5; }
-int lewin_leff_fwd_is_fused(const LewinLeffFwdArgs* a, int dtype) {
-    return (a && check_leff(a) == 0 && leff_use_fused(a, dtype == LEWIN_DTYPE_BF16)) ? 1 : 0;
+size_t lewin_probsparse_core_fwd_workspace_bytes(const LewinCoreFwdArgs*, int) { return 0; }
+int lewin_probsparse_core_bwd_f32(const LewinCoreBwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return core_only_bwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
 }
+int lewin_probsparse_core_bwd_bf16(const LewinCoreBwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
+    return core_only_bwd<__nv_bfloat16>(a, ws, n, reinterpret_cast<cudaStream_t>(s));
+}
+size_t lewin_probsparse_core_bwd_workspace_bytes(const LewinCoreBwdArgs*, int) { return 0; }
 int lewin_attn_fwd_kernel_mask(const LewinAttnFwdArgs* a, int dtype) {
     if (!a) return 0;
-    return (plan_attn(a, dtype == LEWIN_DTYPE_BF16).ln_stats ? 1 : 0) | 0x1E;
+    return (plan_attn(a, dtype == LEWIN_DTYPE_BF16).ln_stats ? 1 : 0) | 0x1C;
 }
 int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype) {
     if (!a) return 0;
     if (check_leff(a) != 0) return 0;
     const LeffPlan p = plan_leff(a, dtype == LEWIN_DTYPE_BF16);
-    if (p.fused_kernel) return 1 << LEWIN_LEFF_K_FUSED;
     return (p.ln_stats ? 1 : 0) | 0xE;
 }
 int lewin_leff_fwd_f32(const LewinLeffFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
@@ -650,7 +661,7 @@ const char* lewin_error_string(int code) {
     switch (code) {
         case 0: return "ok";
         case LEWIN_E_NULL: return "required pointer is NULL";
-        case LEWIN_E_SHAPE: return "unsupported shape (need H,W % 8 == 0, C % 32 == 0, head_dim == 32, shift in {0..7})";
+        case LEWIN_E_SHAPE: return "unsupported shape (need H,W % 8 == 0, C % 32 == 0, head_dim = C / nH in {32, 64, 128}, shift in {0..7})";
         case LEWIN_E_ALIGN: return "pointer not 16-byte aligned";
         case LEWIN_E_WORKSPACE: return "workspace missing or too small";
         case LEWIN_E_DTYPE: return "unknown dtype";

@@ -23,7 +23,7 @@ struct CoreFwdArgs {
     uint8_t* top;            // [B_, nH, 25] or null
     const float* rpb_table;  // [225, nH] (or null)
     const float* rpb_dense;  // [nH, 64, 64] (or null)
-    const uint8_t* cnt;      // [64, 64] sample multiplicities (built from index_sample)
+    const int32_t* index_sample;   // [64, 25] key-sample indices (attn.py:91); the multiplicity matrix is built per CTA
     const float* mask;       // dense [nW_mask, 64, 64] or null
     int nW_mask;
     int B_, nH, C;
@@ -33,52 +33,53 @@ struct CoreFwdArgs {
 };
 
 constexpr int CORE_THREADS = 128;
-constexpr int QK_LD = 36;   // q/k smem row stride (floats)
-constexpr int V_LD = 40;    // v smem row stride: conflict-free B-fragment loads for P.V
 constexpr int P_LD = 68;    // selected-row score / probability stride
+// head_dim D in {32, 64, 128} (d_keys = d_model // n_heads, attn.py:370-372; = embed_dim in this model, My_model_1.py:962):
+// q/k row stride D + 4 floats and v row stride D + 8 keep the fragment loads conflict-free for every D (== 4 / 8 mod 32)
+template <int D> struct CoreLd { static constexpr int QK = D + 4, V = D + 8; };
 
+template <int D>
 struct CoreSmem {
-    float q[kTok * QK_LD];
-    float k[kTok * QK_LD];
-    float v[kTok * V_LD];
+    float q[kTok * CoreLd<D>::QK];
+    float k[kTok * CoreLd<D>::QK];
+    float v[kTok * CoreLd<D>::V];
     float p[32 * P_LD];           // rows = selection slots (25 used, 7 zero)
     float M[kTok];
-    float vmean[kHeadDim];
-    float vpart[4 * kHeadDim];
+    float vmean[D];
+    float vpart[4 * D];
     float tbl[232];
-    uint8_t cnt[kTok * kTok];
+    alignas(16) uint8_t cnt[kTok * kTok];
     int slot_of[kTok];            // token -> slot (or -1)
     int tok_of[32];               // slot -> token
     int region[kTok];
 };
 
-// build cnt[64][64] from index_sample[64][25] (attn.py:91); one block of 64 threads
-__global__ void build_cnt_kernel(const int32_t* __restrict__ idx, uint8_t* __restrict__ cnt) {
-    const int n = threadIdx.x;
-    if (n >= kTok) return;
-    uint8_t row[kTok];
-#pragma unroll
-    for (int m = 0; m < kTok; ++m) row[m] = 0;
-    for (int t = 0; t < kSampleK; ++t) {
-        int m = idx[n * kSampleK + t] & 63;
-        row[m]++;
+// cnt[n][m] = #{t : idx[n, t] == m} (the reference's K_sample gather, attn.py:88-104, as a multiplicity matrix), built in
+// shared memory by the CTA itself: 4 KB, 1600 byte-lane atomics, once per persistent CTA (no pre-pass kernel)
+__device__ __forceinline__ void build_cnt_smem(uint8_t* cnt, const int32_t* __restrict__ idx, int tid, int nthreads) {
+    uint32_t* c32 = reinterpret_cast<uint32_t*>(cnt);
+    for (int i = tid; i < kTok * kTok / 4; i += nthreads) c32[i] = 0u;
+    __syncthreads();
+    for (int i = tid; i < kTok * kSampleK; i += nthreads) {
+        const int n = i / kSampleK, m = idx[i] & 63;
+        atomicAdd(&c32[(n * kTok + m) >> 2], 1u << (8 * (m & 3)));      // <= 25 per byte: no carry into the neighbour
     }
-    for (int m = 0; m < kTok; ++m) cnt[n * kTok + m] = row[m];
+    __syncthreads();
 }
 
-template <typename T>
+template <typename T, int D>
 __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const CoreFwdArgs<T> a) {
     constexpr int PASSES = Act<T>::kPasses;
+    constexpr int QK_LD = CoreLd<D>::QK, V_LD = CoreLd<D>::V;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CoreSmem& s = *reinterpret_cast<CoreSmem*>(smem_raw);
+    CoreSmem<D>& s = *reinterpret_cast<CoreSmem<D>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;
     const int C3 = 3 * a.C;
-    const float scale = rsqrtf(static_cast<float>(kHeadDim));   // attn.py:327
+    const float scale = rsqrtf(static_cast<float>(D));   // attn.py:327
 
     // launch-invariant: sample multiplicities
-    for (int i = tid; i < kTok * kTok / 16; i += CORE_THREADS)
-        reinterpret_cast<uint4*>(s.cnt)[i] = reinterpret_cast<const uint4*>(a.cnt)[i];
+    build_cnt_smem(s.cnt, a.index_sample, tid, CORE_THREADS);
 
     const int items = a.B_ * a.nH;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -86,13 +87,14 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const
         const int h = item - wg * a.nH;
         __syncthreads();                     // previous item fully consumed
 
-        // ---- stage q, k, v (64 x 32 each) as fp32
+        // ---- stage q, k, v (64 x D each) as fp32
         {
-            const T* base = a.qkv + static_cast<long long>(wg) * kTok * C3 + h * kHeadDim;
-            for (int c = tid; c < 3 * kTok * 8; c += CORE_THREADS) {
-                int which = c / (kTok * 8);
-                int rem = c - which * kTok * 8;
-                int r = rem >> 3, d4 = (rem & 7) * 4;
+            const T* base = a.qkv + static_cast<long long>(wg) * kTok * C3 + h * D;
+            constexpr int CPR = D / 4;       // float4 chunks per row
+            for (int c = tid; c < 3 * kTok * CPR; c += CORE_THREADS) {
+                int which = c / (kTok * CPR);
+                int rem = c - which * kTok * CPR;
+                int r = rem / CPR, d4 = (rem % CPR) * 4;
                 float4 v = ld4(base + static_cast<long long>(r) * C3 + which * a.C + d4);
                 float* dst = which == 0 ? s.q + r * QK_LD + d4 : which == 1 ? s.k + r * QK_LD + d4 : s.v + r * V_LD + d4;
                 *reinterpret_cast<float4*>(dst) = v;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < kHeadDim / 8; ++ks) {
+        for (int ks = 0; ks < D / 8; ++ks) {
             float af[4];
             const float* pa = s.q + (warp * 16 + gq) * QK_LD + ks * 8 + tq;
             af[0] = pa[0]; af[1] = pa[8 * QK_LD]; af[2] = pa[4]; af[3] = pa[8 * QK_LD + 4];
@@ -189,17 +191,17 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const
                 }
             }
         }
-        // column means of V (attn.py:168)
-        {
-            const int d = tid & 31, part = tid >> 5;
+        // column means of V (attn.py:168): 4 row quarters x D columns, then combined
+        for (int e = tid; e < 4 * D; e += CORE_THREADS) {
+            const int d = e % D, part = e / D;
             float sum = 0.f;
 #pragma unroll
             for (int r = 0; r < 16; ++r) sum += s.v[(part * 16 + r) * V_LD + d];
-            s.vpart[part * kHeadDim + d] = sum;
+            s.vpart[part * D + d] = sum;
         }
         __syncthreads();
-        if (tid < kHeadDim)
-            s.vmean[tid] = Act<T>::round((s.vpart[tid] + s.vpart[32 + tid] + s.vpart[64 + tid] + s.vpart[96 + tid]) * (1.0f / kTok));
+        for (int d = tid; d < D; d += CORE_THREADS)
+            s.vmean[d] = Act<T>::round((s.vpart[d] + s.vpart[D + d] + s.vpart[2 * D + d] + s.vpart[3 * D + d]) * (1.0f / kTok));
 
         // ---- softmax -> +rpb -> +mask -> softmax on the selected rows (attn.py:195-264)
         for (int slot = warp; slot < 32; slot += 4) {
@@ -241,12 +243,13 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const
         }
         __syncthreads();
 
-        // ---- ctx_sel[32 x 32] = P2[32 x 64] . V[64 x 32]  (attn.py:272): warp -> (m-tile, 2 n-tiles)
+        // ---- ctx_sel[32 x D] = P2[32 x 64] . V[64 x D]  (attn.py:272): warp -> (m-tile, D/16 n-tiles)
         {
-            const int mt = warp & 1, nb = (warp >> 1) * 2;
-            float o[2][4];
+            constexpr int NT = D / 16;
+            const int mt = warp & 1, nb = (warp >> 1) * NT;
+            float o[NT][4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < NT; ++j)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) o[j][c] = 0.f;
 #pragma unroll
@@ -255,27 +258,27 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const
                 const float* pa = s.p + (mt * 16 + gq) * P_LD + ks * 8 + tq;
                 af[0] = pa[0]; af[1] = pa[8 * P_LD]; af[2] = pa[4]; af[3] = pa[8 * P_LD + 4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < NT; ++j) {
                     float bf[2];
                     const float* pb = s.v + (ks * 8 + tq) * V_LD + (nb + j) * 8 + gq;
                     bf[0] = pb[0]; bf[1] = pb[4 * V_LD];
                     mma_x<PASSES>(o[j], af, bf);
                 }
             }
-            T* cbase = a.ctx + static_cast<long long>(wg) * kTok * a.C + h * kHeadDim;
+            T* cbase = a.ctx + static_cast<long long>(wg) * kTok * a.C + h * D;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int slot = mt * 16 + gq + half * 8;
                 const int r = s.tok_of[slot];
                 if (r >= 0) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < NT; ++j)
                         st2(cbase + static_cast<long long>(r) * a.C + (nb + j) * 8 + 2 * tq, o[j][half * 2], o[j][half * 2 + 1]);
                 }
             }
             // lazy queries: mean(V) (attn.py:172)
-            for (int c = tid; c < kTok * 8; c += CORE_THREADS) {
-                const int r = c >> 3, d4 = (c & 7) * 4;
+            for (int c = tid; c < kTok * (D / 4); c += CORE_THREADS) {
+                const int r = c / (D / 4), d4 = (c % (D / 4)) * 4;
                 if (s.slot_of[r] < 0)
                     st4(cbase + static_cast<long long>(r) * a.C + d4, *reinterpret_cast<const float4*>(s.vmean + d4));
             }
@@ -283,17 +286,27 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const
     }
 }
 
-template <typename T>
-cudaError_t launch_core_fwd(const CoreFwdArgs<T>& a, int num_sms, cudaStream_t stream) {
-    auto k = probsparse_core_fwd_kernel<T>;
-    const size_t smem = sizeof(CoreSmem);
+template <typename T, int D>
+cudaError_t launch_core_fwd_d(const CoreFwdArgs<T>& a, int num_sms, cudaStream_t stream) {
+    auto k = probsparse_core_fwd_kernel<T, D>;
+    const size_t smem = sizeof(CoreSmem<D>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     long long items = static_cast<long long>(a.B_) * a.nH;
-    long long cap = static_cast<long long>(num_sms) * 4 * 4;      // 4 resident CTAs/SM, ~4 waves before looping
+    const int resident = static_cast<int>((227 * 1024) / (smem + 1024));      // CTAs per SM by shared memory
+    long long cap = static_cast<long long>(num_sms) * (resident < 1 ? 1 : resident > 4 ? 4 : resident) * 4;   // ~4 waves before looping
     unsigned grid = static_cast<unsigned>(items < cap ? items : cap);
     k<<<grid, CORE_THREADS, smem, stream>>>(a);
     return cudaGetLastError();
+}
+// head_dim = C / nH in {32, 64, 128}
+template <typename T>
+cudaError_t launch_core_fwd(const CoreFwdArgs<T>& a, int num_sms, cudaStream_t stream) {
+    const int D = a.C / a.nH;
+    if (D == 32) return launch_core_fwd_d<T, 32>(a, num_sms, stream);
+    if (D == 64) return launch_core_fwd_d<T, 64>(a, num_sms, stream);
+    if (D == 128) return launch_core_fwd_d<T, 128>(a, num_sms, stream);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace lewin

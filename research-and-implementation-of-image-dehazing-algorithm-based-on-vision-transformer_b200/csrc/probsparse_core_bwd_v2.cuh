@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(THREADS, 3) core_bwd_v2_kernel(const CoreBwdAr
     const float scale = rsqrtf(static_cast<float>(kHeadDim));
     const int items = a.B_ * a.nH;
     const bool want_tab = a.d_rpb_table != nullptr && a.use_rpb && a.rpb_table != nullptr;
+    const bool want_dense = a.d_rpb_dense != nullptr && a.use_rpb;
     for (int i = tid; i < 16 * 225; i += THREADS) s.tacc[i] = 0.f;
 
     auto prefetch = [&](int item, int buf) {
@@ -206,6 +207,11 @@ __global__ void __launch_bounds__(THREADS, 3) core_bwd_v2_kernel(const CoreBwdAr
                 float* tb = s.tacc + h * 225 + (ry + 7) * 15 + (rx - 2 * tq + 7);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { atomicAdd(tb - j * 15, gr[j][0]); atomicAdd(tb - j * 15 - 1, gr[j][1]); }
+            }
+            if (want_dense && my_tok >= 0) {     // gradient w.r.t. the gathered bias [nH, 64, 64] (AttentionLayer.forward's argument)
+                float* dd = a.d_rpb_dense + (static_cast<long long>(h) * kTok + r) * kTok + 2 * tq;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { atomicAdd(dd + j * 8, gr[j][0]); atomicAdd(dd + j * 8 + 1, gr[j][1]); }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {

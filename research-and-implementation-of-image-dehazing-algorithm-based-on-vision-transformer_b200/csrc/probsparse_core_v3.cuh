@@ -47,19 +47,27 @@ __global__ void __launch_bounds__(THREADS, CTAS) probsparse_core_v3_kernel(const
     const float scale = rsqrtf(static_cast<float>(kHeadDim));
     const int items = a.B_ * a.nH;
 
-    // ---- per-thread constants: multiplicities of my fragment positions (rows warp*16 + gq (+8), columns j*8 + 2tq (+1))
+    // ---- per-thread constants: multiplicities of my fragment positions (rows warp*16 + gq (+8), columns j*8 + 2tq (+1)).
+    //      The multiplicity matrix cnt[n][m] = #{t : idx[n, t] == m} (attn.py:88-104) is built by the CTA itself in the second
+    //      q|k|v buffer (free until the first in-loop prefetch): no pre-pass kernel, no global table.
     __half2 cntp[2][8];
     uint32_t sampled = 0;
+    {
+        uint8_t* cnt = reinterpret_cast<uint8_t*>(s.qkv[1]);
+        build_cnt_smem(cnt, a.index_sample, tid, THREADS);
 #pragma unroll
-    for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int r = warp * 16 + gq + half * 8, c = j * 8 + 2 * tq;
-            const __half c0 = __low2half(a.cw[r * kTok + c]), c1 = __low2half(a.cw[r * kTok + c + 1]);
-            cntp[half][j] = __halves2half2(c0, c1);
-            if (__half2float(c0) > 0.f) sampled |= 1u << (half * 16 + j * 2);
-            if (__half2float(c1) > 0.f) sampled |= 1u << (half * 16 + j * 2 + 1);
-        }
+            for (int j = 0; j < 8; ++j) {
+                const int r = warp * 16 + gq + half * 8, c = j * 8 + 2 * tq;
+                const uint32_t c2 = *reinterpret_cast<const uint16_t*>(cnt + r * kTok + c);
+                const int c0 = c2 & 0xFF, c1 = c2 >> 8;
+                cntp[half][j] = __halves2half2(__int2half_rn(c0), __int2half_rn(c1));
+                if (c0) sampled |= 1u << (half * 16 + j * 2);
+                if (c1) sampled |= 1u << (half * 16 + j * 2 + 1);
+            }
+        __syncthreads();                                  // everyone has read the table before the buffer is reused
+    }
     if (tid < 32) s.tok_of[tid] = -1;                   // slots 25..31 stay -1 for the whole kernel
     // the grid is a multiple of nH whenever it is smaller than the item count, so a CTA keeps one head: its bias table
     // is staged once

@@ -69,19 +69,21 @@ class GraphedForward:
         self.autocast_dtype = autocast_dtype
         self.x = tiles.clone()
         self.idx = index_samples.to(device=tiles.device, dtype=torch.int32).clone()
-        side = torch.cuda.Stream(device=tiles.device)
-        side.wait_stream(torch.cuda.current_stream(tiles.device))
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._run()
-        torch.cuda.current_stream(tiles.device).wait_stream(side)
-        from . import _lib
-        lib = _lib.load()
-        n0 = lib.lewin_launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.y = self._run()
-        self.launches_per_replay = int(lib.lewin_launch_count() - n0)    # library kernels captured in the graph
+        from . import _lib, ops
+        with ops.weight_images.pin() as held:        # the graph bakes in raw pointers of the bf16 weight images: keep them alive
+            side = torch.cuda.Stream(device=tiles.device)
+            side.wait_stream(torch.cuda.current_stream(tiles.device))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._run()
+            torch.cuda.current_stream(tiles.device).wait_stream(side)
+            lib = _lib.load()
+            n0 = lib.lewin_launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.y = self._run()
+            self.launches_per_replay = int(lib.lewin_launch_count() - n0)    # library kernels captured in the graph
+        self._images = list(held)
         self._params = list(self.model.parameters())
         self._weights_tag = self._tag()
 

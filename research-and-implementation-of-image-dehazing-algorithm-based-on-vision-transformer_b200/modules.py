@@ -85,7 +85,7 @@ def _act_dtype(x):
 # ------------------------------------------------------------------------------ ProbSparse
 class ProbAttention(nn.Module):
     """ProbSparse/attn.py:43-342.  Holds no parameters.  ``forward`` takes already-projected
-    q, k, v [B_, 64, nH, 32] and returns (context [B_, 64, nH, 32], None)."""
+    q, k, v [B_, 64, nH, D] and returns (context [B_, 64, nH, D], None); differentiable in q, k, v and the bias."""
 
     def __init__(self, mask_flag=False, factor=5, scale=None, attention_dropout=0.1, output_attention=False):
         super().__init__()
@@ -104,6 +104,10 @@ class ProbAttention(nn.Module):
         C = H * D
         if index_sample is None:
             index_sample = draw_index_sample(L, L, self.factor)
+        if L != 64 or keys.shape[1] != 64:
+            raise NotImplementedError("lewin_b200 ProbAttention supports 8x8 windows (L_Q = L_K = 64)")
+        if D not in (32, 64, 128):
+            raise NotImplementedError(f"lewin_b200 ProbAttention: head_dim {D} not built (32, 64, 128 are)")
         dt = _act_dtype(queries)
         qkv = torch.cat([queries.reshape(B_, L, C), keys.reshape(B_, L, C), values.reshape(B_, L, C)], -1).to(dt)
         out = ops.probsparse_core(qkv, num_heads=H, rpb_dense=relative_position_bias, mask=SW_mask,
@@ -187,6 +191,10 @@ class WindowAttention(nn.Module):
         self.win_size = to_2tuple(win_size)
         self.num_heads = num_heads
         head_dim = dim // num_heads
+        if dim % num_heads or head_dim not in (32, 64, 128):
+            raise NotImplementedError(f"lewin_b200: head_dim = dim // num_heads = {dim}/{num_heads} is not built; 32, 64 and "
+                                      "128 are (embed_dim 32 / 64 / 128 of My_model_1.py:962; the reference's embed_dim=16 "
+                                      "variant, utils/model_utils.py:97, is not)")
         self.scale = qk_scale or head_dim ** -0.5
         self.ProbSpare = AttentionLayer(self.dim, self.num_heads)
         self.relative_position_bias_table = nn.Parameter(

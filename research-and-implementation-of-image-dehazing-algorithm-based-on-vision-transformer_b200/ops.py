@@ -12,6 +12,7 @@ lewin_leff(y, ...)   LeFF half (My_model_1.py:873) or, with ``fused=False``, LeF
 from __future__ import annotations
 
 import os
+import threading
 import weakref
 
 import torch
@@ -85,8 +86,8 @@ class KernelTimer:
     {(op, kernel): [ms, ...]} with the shape info of every launch in kt.launches."""
 
     active = None
-    ATTN = ("ln_stats", "build_cnt", "gemm_qkv", "probsparse_core", "gemm_out")
-    LEFF = ("ln_stats", "gemm_fc1_gelu", "dwconv_gelu", "gemm_fc2", "leff_fused")
+    ATTN = ("ln_stats", "retired", "gemm_qkv", "probsparse_core", "gemm_out")
+    LEFF = ("ln_stats", "gemm_fc1_gelu", "dwconv_gelu", "gemm_fc2")
 
     def __init__(self):
         self.launches = []     # (op, names, live_slots, info, events)
@@ -116,23 +117,85 @@ class KernelTimer:
         return out
 
 
-_BF16_IMAGES = {}
+class TopRecorder:
+    """Collects the selected top-u query indices (M_top, attn.py:122) of every lewin_attn call made while active, in call
+    order: ``with TopRecorder() as rec: model(x)`` -> ``rec.tops`` = [uint8 [B_, nH, 25], ...] (one per LeWin block).
+    Test / diagnostic hook for the per-block, tie-aware selection check of a whole-model forward."""
+
+    active = None
+
+    def __init__(self):
+        self.tops = []
+
+    def __enter__(self):
+        TopRecorder.active = self
+        return self
+
+    def __exit__(self, *exc):
+        TopRecorder.active = None
+
+
 _WEIGHT_IMAGES_ON = os.environ.get("LEWIN_NO_WEIGHT_CACHE", "0") != "1"      # knob for scripts/diff_paths.py
 
 
+class _WeightImages:
+    """bf16 images of constant fp32 weights for the C >= 256 GEMMs (the ABI's optional w*_bf16 fields).
+
+    One entry per live weight tensor (keyed by id, dropped by a weakref callback when the tensor dies), REPLACED when the
+    tensor's version counter changes (optimizer step, load_state_dict) - stale versions never accumulate.  Guarded by a
+    lock (nn.DataParallel replica threads).  A CUDA-graph capture must keep the images it baked into the graph alive:
+    ``with images.pin() as held:`` collects every image handed out meanwhile (fullres.GraphedForward stores ``held``)."""
+
+    def __init__(self):
+        self._lock = threading.RLock()      # re-entrant: a weakref callback may fire while the owner thread holds it
+        self._ent = {}            # id(w) -> (weakref, version, data_ptr, image)
+        self._pins = []
+
+    def get(self, w):
+        key = id(w)
+        with self._lock:
+            ent = self._ent.get(key)
+            if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr():
+                img = ent[3]
+            else:
+                img = w.detach().to(torch.bfloat16).contiguous()
+                ref = weakref.ref(w, lambda _r, k=key: self._drop(k))
+                self._ent[key] = (ref, w._version, w.data_ptr(), img)
+            for held in self._pins:
+                held.append(img)
+            return img
+
+    def _drop(self, key):
+        with self._lock:
+            ent = self._ent.get(key)
+            if ent is not None and ent[0]() is None:
+                del self._ent[key]
+
+    def __len__(self):
+        return len(self._ent)
+
+    class _Pin:
+        def __init__(self, owner):
+            self.owner, self.held = owner, []
+
+        def __enter__(self):
+            with self.owner._lock:
+                self.owner._pins.append(self.held)
+            return self.held
+
+        def __exit__(self, *exc):
+            with self.owner._lock:
+                self.owner._pins.remove(self.held)
+
+    def pin(self):
+        return _WeightImages._Pin(self)
+
+
+weight_images = _WeightImages()
+
+
 def _bf16_image(w):
-    """bf16 image of a constant fp32 weight for the C >= 256 GEMMs (the ABI's optional w*_bf16 fields).  Converted once and
-    reused while the tensor object, its storage and its version counter are unchanged (inference); any in-place update
-    (optimizer step, load_state_dict) bumps `_version` and the image is rebuilt."""
-    key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
-    ent = _BF16_IMAGES.get(key)
-    if ent is not None and ent[0]() is w:
-        return ent[1]
-    if len(_BF16_IMAGES) > 1024:
-        _BF16_IMAGES.clear()
-    img = w.detach().to(torch.bfloat16).contiguous()
-    _BF16_IMAGES[key] = (weakref.ref(w), img)
-    return img
+    return weight_images.get(w)
 
 
 class _AttnFn(torch.autograd.Function):
@@ -178,6 +241,8 @@ class _AttnFn(torch.autograd.Function):
         ctx.dt = dt
         ctx.save_for_backward(x, ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, idx, mask_, ds_, qkv, cbuf, top)
         ctx.mark_non_differentiable(top)
+        if TopRecorder.active is not None:
+            TopRecorder.active.tops.append(top)
         return y, top
 
     @staticmethod
@@ -190,9 +255,8 @@ class _AttnFn(torch.autograd.Function):
         C = x.shape[-1]
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        tab_like = tab if tab is not None else (torch.empty((225, nH), device="meta") if dense is not None else None)
-        d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab = _zero_grads(
-            (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab_like), dev)
+        d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab, d_dense = _zero_grads(
+            (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense if tab is None else None), dev)
         fwd = _lib.LewinAttnFwdArgs(
             B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
             analytic_shift_mask=int(analytic), nW_mask=0 if mask is None else mask.shape[0],
@@ -204,16 +268,14 @@ class _AttnFn(torch.autograd.Function):
         a = _lib.LewinAttnBwdArgs(
             fwd=fwd, dy=_ptr(dy), dx=_ptr(dx), d_ln_w=_ptr(d_ln_w), d_ln_b=_ptr(d_ln_b),
             d_w_qkv=_ptr(d_w_qkv), d_b_qkv=_ptr(d_b_qkv), d_w_out=_ptr(d_w_out), d_b_out=_ptr(d_b_out),
-            d_rpb_table=_ptr(d_tab))
+            d_rpb_table=_ptr(d_tab), d_rpb_dense=_ptr(d_dense))
         ws = _workspace(lib.lewin_attn_bwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_attn_bwd_{dt}")
         with torch.cuda.device(dev):
             _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_attn_bwd_{dt}")
-        if dense is not None and tab is None:
-            d_dense, d_tab_out = None, None   # dense bias path: gradient w.r.t. the gathered bias is not provided
-        else:
-            d_dense, d_tab_out = None, d_tab
-        return (dx, d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab_out, d_dense, None, None, None, None)
+        # table path: d(relative_position_bias_table); dense path (AttentionLayer.forward's gathered bias, attn.py:385):
+        # d(relative_position_bias) [nH, 64, 64], which autograd scatters back into the caller's table through its own gather
+        return (dx, d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab, d_dense, None, None, None, None)
 
 
 class _LeffFn(torch.autograd.Function):
@@ -229,13 +291,8 @@ class _LeffFn(torch.autograd.Function):
         assert y.numel() == tokens * C, (y.shape, B, H, W, C)
         dev = y.device
         out = torch.empty_like(y)
-        probe = _lib.LewinLeffFwdArgs(B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=int(need_grad),
-                                      y=1 << 8, out=1 << 8, ln_w=1 << 8, ln_b=1 << 8, w1=1 << 8, b1=1 << 8, w_dw=1 << 8,
-                                      b_dw=1 << 8, w2=1 << 8, b2=1 << 8, h1=1 << 8, h2=1 << 8, a1=1 << 8, a2=1 << 8)
-        single = bool(lib.lewin_leff_fwd_is_fused(probe, _lib.DTYPE_TAG[dt]))
-        hshape = (16,) if single else (tokens, hidden)        # the fused kernel keeps the hidden activations on chip
-        h1 = torch.empty(hshape, dtype=y.dtype, device=dev)
-        h2 = torch.empty(hshape, dtype=y.dtype, device=dev)
+        h1 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
+        h2 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
         a1 = torch.empty_like(h1) if need_grad else None
         a2 = torch.empty_like(h2) if need_grad else None
         ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_ = [_f32c(t) for t in (ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale)]
@@ -250,7 +307,7 @@ class _LeffFn(torch.autograd.Function):
         if KernelTimer.active is not None:
             mask = lib.lewin_leff_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
             tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt),
-                                                tuple(k for k in range(5) if mask >> k & 1))
+                                                tuple(k for k in range(4) if mask >> k & 1))
             a.timing = ctypes_addr(tim)
         ws = _workspace(lib.lewin_leff_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_leff_fwd_{dt}")
@@ -309,29 +366,65 @@ def lewin_leff(y, *, B, H, W, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale
     return _LeffFn.apply(y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom)
 
 
+class _CoreFn(torch.autograd.Function):
+    """ProbAttention.forward (attn.py:287-342) on projected q|k|v; backward = lewin_probsparse_core_bwd_* for the saved selection."""
+
+    @staticmethod
+    def forward(ctx, qkv, rpb_table, rpb_dense, mask, index_sample, geom):
+        nH, use_rpb = geom
+        lib = _lib.load()
+        dt = _dtype_tag(qkv)
+        qkv = qkv.contiguous()
+        B_, L, C3 = qkv.shape
+        C = C3 // 3
+        if L != 64 or C % nH:
+            raise RuntimeError(f"lewin_b200.probsparse_core: qkv must be [B_, 64, 3 * nH * head_dim], got {tuple(qkv.shape)} with nH={nH}")
+        dev = qkv.device
+        out = torch.empty((B_, L, C), dtype=qkv.dtype, device=dev)
+        top = torch.empty((B_, nH, 25), dtype=torch.uint8, device=dev)
+        tab_, dense_, mask_ = _f32c(rpb_table), _f32c(rpb_dense), _f32c(mask)
+        idx = prepare_index_sample(index_sample, dev)
+        a = _lib.LewinCoreFwdArgs(B_=B_, nH=nH, use_rpb=int(use_rpb), nW_mask=0 if mask_ is None else mask_.shape[0],
+                                  head_dim=C // nH, reserved=0,
+                                  qkv=_ptr(qkv), ctx=_ptr(out), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
+                                  index_sample=_ptr(idx), mask=_ptr(mask_), top=_ptr(top))
+        ws = _workspace(lib.lewin_probsparse_core_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+        fn = getattr(lib, f"lewin_probsparse_core_fwd_{dt}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_probsparse_core_fwd_{dt}")
+        ctx.geom, ctx.dt = geom, dt
+        ctx.save_for_backward(qkv, tab_, dense_, mask_, top)
+        ctx.mark_non_differentiable(top)
+        return out, top
+
+    @staticmethod
+    def backward(ctx, dctx, _dtop):
+        qkv, tab, dense, mask, top = ctx.saved_tensors
+        nH, use_rpb = ctx.geom
+        lib = _lib.load()
+        dt = ctx.dt
+        dev = qkv.device
+        B_, L, C3 = qkv.shape
+        dctx = dctx.contiguous()
+        dqkv = torch.empty_like(qkv)
+        d_tab, d_dense = _zero_grads((tab, dense if tab is None else None), dev)
+        fwd = _lib.LewinCoreFwdArgs(B_=B_, nH=nH, use_rpb=int(use_rpb), nW_mask=0 if mask is None else mask.shape[0],
+                                    head_dim=C3 // 3 // nH, reserved=0,
+                                    qkv=_ptr(qkv), ctx=_ptr(dctx), rpb_table=_ptr(tab), rpb_dense=_ptr(dense),
+                                    index_sample=None, mask=_ptr(mask), top=_ptr(top))
+        a = _lib.LewinCoreBwdArgs(fwd=fwd, dctx=_ptr(dctx), dqkv=_ptr(dqkv), d_rpb_table=_ptr(d_tab), d_rpb_dense=_ptr(d_dense))
+        ws = _workspace(lib.lewin_probsparse_core_bwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+        fn = getattr(lib, f"lewin_probsparse_core_bwd_{dt}")
+        with torch.cuda.device(dev):
+            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_probsparse_core_bwd_{dt}")
+        return dqkv, d_tab, d_dense, None, None, None
+
+
 def probsparse_core(qkv, *, num_heads, index_sample, rpb_table=None, rpb_dense=None, mask=None, use_rpb=True,
                     return_top=False):
-    """ProbAttention.forward (attn.py:287-342) on projected q|k|v [B_, 64, 3C] -> context [B_, 64, C].
-    Forward only (the trainable paths go through lewin_attn)."""
-    lib = _lib.load()
-    dt = _dtype_tag(qkv)
-    if torch.is_grad_enabled() and qkv.requires_grad:
-        raise RuntimeError("lewin_b200.probsparse_core is forward-only; use lewin_attn for training")
-    qkv = qkv.contiguous()
-    B_, L, C3 = qkv.shape
-    C = C3 // 3
-    dev = qkv.device
-    out = torch.empty((B_, L, C), dtype=qkv.dtype, device=dev)
-    top = torch.empty((B_, num_heads, 25), dtype=torch.uint8, device=dev)
-    tab_, dense_, mask_ = _f32c(rpb_table), _f32c(rpb_dense), _f32c(mask)
-    idx = prepare_index_sample(index_sample, dev)
-    a = _lib.LewinCoreFwdArgs(B_=B_, nH=num_heads, use_rpb=int(use_rpb), nW_mask=0 if mask_ is None else mask_.shape[0],
-                              qkv=_ptr(qkv), ctx=_ptr(out), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
-                              index_sample=_ptr(idx), mask=_ptr(mask_), top=_ptr(top))
-    ws = _workspace(lib.lewin_probsparse_core_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
-    fn = getattr(lib, f"lewin_probsparse_core_fwd_{dt}")
-    with torch.cuda.device(dev):
-        _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_probsparse_core_fwd_{dt}")
+    """ProbAttention.forward (attn.py:287-342) on projected q|k|v [B_, 64, 3C] -> context [B_, 64, C]; head_dim =
+    C / num_heads in {32, 64, 128}.  Differentiable in qkv and the bias (table [225, nH] or gathered [nH, 64, 64])."""
+    out, top = _CoreFn.apply(qkv, rpb_table, rpb_dense, mask, index_sample, (int(num_heads), bool(use_rpb)))
     return (out, top) if return_top else out
 
 

@@ -179,6 +179,14 @@ class Uformer(nn.Module):
                  use_checkpoint=False, token_projection='linear', token_mlp='ffn', se_layer=False,
                  dowsample=Downsample, upsample=Upsample, **kwargs):
         super().__init__()
+        if token_mlp != 'leff' or token_projection != 'linear':
+            raise NotImplementedError(
+                "lewin_b200.Uformer implements the configuration the reference instantiates (utils/model_utils.py:94: "
+                f"token_projection='linear', token_mlp='leff'); got token_projection={token_projection!r}, token_mlp={token_mlp!r} "
+                "(the constructor keeps the reference's default token_mlp='ffn' in its signature, so pass token_mlp='leff')")
+        if embed_dim not in (32, 64, 128):
+            raise NotImplementedError(f"lewin_b200.Uformer: embed_dim {embed_dim} gives head_dim {embed_dim} (My_model_1.py:962); "
+                                      "32, 64 and 128 are built")
         self.num_enc_layers = len(depths) // 2
         self.num_dec_layers = len(depths) // 2
         self.embed_dim, self.patch_norm, self.mlp_ratio = embed_dim, patch_norm, mlp_ratio

@@ -44,7 +44,8 @@ def test_library_exports_every_declared_symbol(lib_path):
 
 def test_ctypes_structs_match_c_layout(tmp_path):
     from lewin_b200 import _lib
-    structs = ["LewinAttnFwdArgs", "LewinAttnBwdArgs", "LewinCoreFwdArgs", "LewinLeffFwdArgs", "LewinLeffBwdArgs"]
+    structs = ["LewinAttnFwdArgs", "LewinAttnBwdArgs", "LewinCoreFwdArgs", "LewinCoreBwdArgs", "LewinLeffFwdArgs", "LewinLeffBwdArgs",
+               "LewinUpsampleFwdArgs", "LewinInputProjArgs"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for s in structs:
         cls = getattr(_lib, s)
@@ -81,7 +82,12 @@ def test_argument_validation_without_gpu(lib_path):
     assert b"aligned" in lib.lewin_error_string(-3)
     l = _lib.LewinLeffFwdArgs(B=1, H=8, W=8, C=32, hidden=128)
     assert lib.lewin_leff_fwd_bf16(l, None, 0, None) == -1
-    assert lib.lewin_attn_fwd_workspace_bytes(a, 0) >= 2 * 256 * 4 + 4096
+    assert lib.lewin_attn_fwd_workspace_bytes(a, 0) >= 2 * 256 * 4
+    a.nH = 3                                                       # head_dim = C / nH must be 32, 64 or 128
+    a.x = 0x1000
+    assert lib.lewin_attn_fwd_f32(a, None, 0, None) == -2
+    c = _lib.LewinCoreBwdArgs()
+    assert lib.lewin_probsparse_core_bwd_f32(c, None, 0, None) == -1      # LEWIN_E_NULL
 
 
 def test_ops_refuse_cpu_tensors():
@@ -210,3 +216,30 @@ def test_bf16_weight_image_cache_follows_in_place_updates():
     assert b is not a and torch.equal(b, w.detach().to(torch.bfloat16))
     w2 = torch.nn.Parameter(w.detach().clone())
     assert ops._bf16_image(w2) is not b
+    # one entry per LIVE tensor: the stale version of `w` was replaced, dead tensors drop out, pinned images are handed back
+    n = len(ops.weight_images)
+    with ops.weight_images.pin() as held:
+        for _ in range(5):
+            with torch.no_grad():
+                w.mul_(0.5)
+            c = ops._bf16_image(w)
+        t = torch.randn(4, 4)
+        ops._bf16_image(t)
+    assert len(ops.weight_images) == n + 1 and any(h is c for h in held) and len(held) == 6
+    del t
+    import gc
+    gc.collect()
+    assert len(ops.weight_images) == n
+
+
+def test_uformer_constructor_rejects_unbuilt_configurations_with_a_message():
+    """Uformer() with the reference's default token_mlp='ffn' and the embed_dim=16 variant (model_utils.py:97)
+    must fail at construction with an actionable message, not at the first forward."""
+    import lewin_b200 as L
+    with pytest.raises(NotImplementedError, match="token_mlp='leff'"):
+        L.Uformer()
+    with pytest.raises(NotImplementedError, match="embed_dim 16"):
+        L.Uformer(embed_dim=16, token_mlp="leff")
+    with pytest.raises(NotImplementedError, match="head_dim"):
+        L.WindowAttention(48, 8, 3)
+    L.WindowAttention(128, 8, 1)        # head_dim 128 (BASELINE config 5) constructs

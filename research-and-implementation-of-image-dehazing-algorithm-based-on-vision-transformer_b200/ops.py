@@ -86,7 +86,7 @@ class KernelTimer:
     {(op, kernel): [ms, ...]} with the shape info of every launch in kt.launches."""
 
     active = None
-    ATTN = ("ln_stats", "retired", "gemm_qkv", "probsparse_core", "gemm_out")
+    ATTN = ("ln_stats", "attn_fused", "gemm_qkv", "probsparse_core", "gemm_out")
     LEFF = ("ln_stats", "gemm_fc1_gelu", "dwconv_gelu", "gemm_fc2")
 
     def __init__(self):
@@ -211,8 +211,6 @@ class _AttnFn(torch.autograd.Function):
         assert x.numel() == tokens * C, (x.shape, B, H, W, C)
         dev = x.device
         y = torch.empty_like(x)
-        qkv = torch.empty((tokens, 3 * C), dtype=x.dtype, device=dev)
-        cbuf = torch.empty((tokens, C), dtype=x.dtype, device=dev)
         top = torch.empty((tokens // 64, nH, 25), dtype=torch.uint8, device=dev)
         params = [_f32c(t) for t in (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, mask, drop_scale)]
         ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, mask_, ds_ = params
@@ -224,12 +222,19 @@ class _AttnFn(torch.autograd.Function):
             x=_ptr(x), y=_ptr(y), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w_qkv=_ptr(w_qkv_), b_qkv=_ptr(b_qkv_),
             w_out=_ptr(w_out_), b_out=_ptr(b_out_), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
             index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
-            qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
+            qkv=None, ctx=None, top=_ptr(top))
+        kmask = lib.lewin_attn_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
+        if kmask == 2:          # LEWIN_ATTN_K_FUSED: q|k|v and ctx stay on chip, the ABI only wants valid placeholders
+            qkv = cbuf = torch.empty((16,), dtype=x.dtype, device=dev)
+        else:
+            qkv = torch.empty((tokens, 3 * C), dtype=x.dtype, device=dev)
+            cbuf = torch.empty((tokens, C), dtype=x.dtype, device=dev)
+        a.qkv, a.ctx = _ptr(qkv), _ptr(cbuf)
         if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:      # constants of an inference call: convert once
             wq_b, wo_b = _bf16_image(w_qkv_), _bf16_image(w_out_)
             a.w_qkv_bf16, a.w_out_bf16 = _ptr(wq_b), _ptr(wo_b)
         if KernelTimer.active is not None:
-            mask = lib.lewin_attn_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
+            mask = kmask
             tim = KernelTimer.active.events_for("attn", dict(tokens=tokens, C=C, nH=nH, dtype=dt),
                                                 tuple(k for k in range(5) if mask >> k & 1))
             a.timing = ctypes_addr(tim)

@@ -142,8 +142,8 @@ def kernel_work(op, name, info):
         return 150.0 * t * C, 4 * t * C * s
     if name == "dwconv_gelu":
         return 72.0 * t * C, 8 * t * C * s
-    if name == "leff_fused":
-        return 2.0 * t * C * 4 * C * 2 + 72.0 * t * C, 2 * t * C * s + 8 * C * C * 4
+    if name == "attn_fused":      # LN1 -> q|k|v -> ProbSparse core -> out projection -> residual in one kernel: x read, y written
+        return 8.0 * t * C * C + 150.0 * t * C, 2 * t * C * s + 4 * C * C * 4
     if name == "ln_stats":
         return 0.0, t * C * s
     return 0.0, 0.0

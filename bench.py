@@ -438,6 +438,35 @@ def main():
         blocks = block_microbench(dev, args.dtype) if world == 1 else None
     except Exception as e:
         blocks = {"error": repr(e)[:300]}
+    # the reference's own full-image computation (test_long_GPU.py:74-93): ONE forward over the 1664^2 wrap-padded canvas
+    # (43 264 windows at level 0) - "canvas mode"; a different computation from tiled mode (finding 7)
+    canvas = None
+    if world == 1:
+        try:
+            def canvas_step(dt):
+                if dt == "bf16":
+                    with torch.autocast("cuda", torch.bfloat16):
+                        return fullres.dehaze_canvas(model, img_dev, ps=PS, index_samples=idx)
+                return fullres.dehaze_canvas(model, img_dev, ps=PS, index_samples=idx)
+            canvas = {}
+            for dt, n in (("bf16", 5), ("f32", 2)):
+                for _ in range(2):
+                    canvas_step(dt)
+                torch.cuda.synchronize()
+                torch.cuda.reset_peak_memory_stats()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    canvas_step(dt)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / n
+                canvas[dt] = {"images_per_s": 1e3 / ms, "ms_per_image": ms, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+            canvas["note"] = ("fullres.dehaze_canvas: wrap-pad to 1664^2, one Uformer forward over the whole canvas, crop, clamp "
+                              "(test_long_GPU.py:85-93), image resident in HBM, eager launches")
+            torch.cuda.empty_cache()
+        except Exception as e:
+            canvas = {"error": repr(e)[:300]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -460,6 +489,7 @@ def main():
                                f"{world} rank(s), Uformer_ProbSparse embed_dim=32 random init, tiled mode, final all_gather",
                    "tiles_per_rank_max": -(-N_TILES // world), "l2": "working set (>=354 MB per level-0 tensor) exceeds the 126 MB L2",
                    "convs": "InputProj / Upsample run on this library's kernels (bf16); Downsample / OutputProj are stock cuDNN (outside the LeWin block)",
+                   "attention": "C <= 64 levels: ONE fused kernel per block (LN1 -> q|k|v tcgen05.mma -> TMEM -> ProbSparse core -> out tcgen05.mma -> residual); C >= 128: three kernels",
                    "launch": "python launches" if args.no_graph else "CUDA graph replay of the per-rank tile-batch forward",
                    "lewin_compute": "3xTF32 mma.sync (fp32-grade)" if args.dtype == "f32" else
                                     "bf16 operands, fp32 accumulate: warp-specialised tcgen05 GEMMs (TMEM, TMA at C >= 256), mma.sync ProbSparse core, TMA-fed depthwise conv"},
@@ -477,6 +507,7 @@ def main():
             "e2e": 1e3 / (ms_other_e2e / args.steps),
             "note": "same workload at the other precision (f32 = 3xTF32 error-compensated kernels, strict parity path)"},
         "lewin_block_us": blocks,
+        "canvas_mode": canvas,
         "train_step": train,
         "kernels": kernels,
     }

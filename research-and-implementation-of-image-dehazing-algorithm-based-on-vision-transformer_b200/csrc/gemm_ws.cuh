@@ -94,7 +94,7 @@ __device__ __forceinline__ void resid_prefetch(const GemmArgs<__nv_bfloat16>& g,
 
 // One warp's share of one output tile: wait for the accumulator, tcgen05.ld 32-column chunks (thread == TMEM lane == tile
 // row), bias / GELU / residual, stage, row-cooperative coalesced stores.  Shared by the resident-W and streamed-W kernels.
-template <int BN, int EPI, int NCG, int NBUF = 2>
+template <int BN, int EPI, int NCG, int NBUF = 2, bool ALLOW_XT = true>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, uint32_t tmem_d, int acc, uint32_t aph, uint32_t tile,
                                               int n0, const float* s_bias, const uint16_t* gtab, unsigned char* my_stg,
                                               uint64_t* tfull, uint64_t* tempty, int lg, int half, int lane,
@@ -105,7 +105,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
     // One chunk per warp (BN <= 32 * NCG): the residual rows of the NEXT tile are prefetched into the other staging buffer
     // while this tile is processed -- at C <= 64 a tile is so small that waiting for this tile's own residual (one DRAM
     // latency per tile and warp) was the critical path.  The caller issues the first tile's prefetch (resid_prefetch).
-    constexpr bool XT = (EPI == EPI_BIAS_RESID) && (NCH <= NCG) && NBUF == 2;
+    constexpr bool XT = ALLOW_XT && (EPI == EPI_BIAS_RESID) && (NCH <= NCG) && NBUF == 2;   // (the streamed-W kernel walks tiles column-fastest and does not use the cross-tile prefetch)
     static_assert(NBUF == 2 || EPI != EPI_BIAS_RESID, "the residual prefetch uses two staging buffers");
         if (EPI != EPI_BIAS_RESID && ymap != nullptr) {      // staging buffers restart at 0 every tile: drain my outstanding box stores
             if (lane == 0) tma::store_wait_read<0>();
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(WssCfg<EPI>::THREADS, 1) gemm_wss_kernel(const
         for (int it = 0; it < my_tiles; ++it) {
             const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
             const int rt = t / col_tiles, ct = t - rt * col_tiles;
-            epilogue_tile<BN, EPI, NCG, NBUF>(g, tmem_d, it & 1, static_cast<uint32_t>(it >> 1) & 1u, static_cast<uint32_t>(rt), ct * BN,
+            epilogue_tile<BN, EPI, NCG, NBUF, false>(g, tmem_d, it & 1, static_cast<uint32_t>(it >> 1) & 1u, static_cast<uint32_t>(rt), ct * BN,
                                               s_bias + ct * BN, gtab, my_stg, tfull, tempty, lg, half, lane, -1, 0, use_ymap ? &ymap : nullptr);
         }
         if (use_ymap && lane == 0) tma::store_wait_read<0>();
@@ -724,10 +724,16 @@ inline bool wss_supported(const GemmArgs<__nv_bfloat16>& g) {
     return on && enabled() && !g.mapA && !g.a_row_scale && !g.aux && !g.mean && g.K % 64 == 0 && g.N % 128 == 0 && g.N <= 4096 &&
            g.M >= 4 * TC_BM && (g.lda % 8) == 0 && tma::encode_fn() != nullptr;
 }
+// Tile width by occupancy: the widest BN whose tile count still fills the SMs.  At the deep levels of a small tile shard
+// (8-GPU config 3: 1408 tokens at the bottleneck = 11 row tiles) BN = 256 left 22-66 CTAs for 148 SMs; narrower tiles give
+// every SM a CTA (the A rows they share come from L2).
 template <int EPI>
 cudaError_t wss_launch(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16* Wb, int num_sms, cudaStream_t stream) {
-    if (g.N % 256 == 0) return wss_launch_bn<256, EPI>(g, Wb, num_sms, stream);
-    return wss_launch_bn<128, EPI>(g, Wb, num_sms, stream);
+    const long long row_tiles = (g.M + TC_BM - 1) / TC_BM;
+    static const bool narrow = [] { const char* e = getenv("LEWIN_NO_NARROW_WSS"); return !(e && e[0] == '1'); }();
+    if (g.N % 256 == 0 && (!narrow || row_tiles * (g.N / 256) >= num_sms)) return wss_launch_bn<256, EPI>(g, Wb, num_sms, stream);
+    if (!narrow || row_tiles * (g.N / 128) >= num_sms || g.up2) return wss_launch_bn<128, EPI>(g, Wb, num_sms, stream);
+    return wss_launch_bn<64, EPI>(g, Wb, num_sms, stream);
 }
 
 

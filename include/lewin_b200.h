@@ -115,6 +115,13 @@ typedef struct {
      * the weights are constants, the caller converts once); NULL = convert into the workspace on every call. */
     const void* w_qkv_bf16;
     const void* w_out_bf16;
+
+    /* Row-band mode (canvas-mode sharding, test_long_GPU.py:85-92 split over GPUs by rows; fused block half, forward only):
+     * x / y are a band of H rows of an image band_Hg rows tall, laid out by the caller in SHIFTED-FRAME row order (for a
+     * shifted block: the band's own rows from `shift` on, followed by the first `shift` rows of the next band - the rows
+     * torch.roll would bring in).  The cyclic shift then applies to the columns only, and the analytic shift mask
+     * (My_model_1.py:803-836) takes its row regions at shifted-frame row band_y0 + (row in the band).  band_mode = 0: whole image. */
+    int32_t band_mode, band_y0, band_Hg, reserved2;
 } LewinAttnFwdArgs;
 
 #define LEWIN_ATTN_K_LNSTATS 0

@@ -12,7 +12,7 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 _LONG = "research-and-implementation-of-image-dehazing-algorithm-based-on-vision-transformer_b200"
 _pkg = importlib.import_module(_LONG)
-for _sub in ("_lib", "options", "ops", "modules", "patch", "uformer", "fullres", "parallel", "losses", "training"):
+for _sub in ("_lib", "options", "ops", "modules", "patch", "uformer", "fullres", "parallel", "losses", "training", "canvas_bands"):
     importlib.import_module(f"{_LONG}.{_sub}")
 for _name, _mod in list(sys.modules.items()):
     if _name.startswith(_LONG + "."):

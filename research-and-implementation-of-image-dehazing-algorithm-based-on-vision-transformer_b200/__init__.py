@@ -3,7 +3,7 @@
 Importable as ``lewin_b200`` (alias module at the repo root).  The CUDA library is loaded lazily on the
 first op call and there is no CPU fallback (``_lib.load`` raises if ``csrc/liblewin_b200.so`` is missing).
 """
-from . import _lib, options, fullres, parallel, losses, training  # noqa: F401
+from . import _lib, options, fullres, parallel, losses, training, canvas_bands  # noqa: F401
 from .modules import (AttentionLayer, DropPath, LeFF, LeWinTransformerBlock, LinearProjection,  # noqa: F401
                       ProbAttention, WindowAttention, draw_index_sample, lewin_block_forward)
 from .ops import lewin_attn, lewin_leff, probsparse_core  # noqa: F401

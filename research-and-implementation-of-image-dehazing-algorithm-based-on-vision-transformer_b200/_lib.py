@@ -29,6 +29,7 @@ class LewinAttnFwdArgs(C.Structure):
         ("qkv", c_ptr), ("ctx", c_ptr), ("top", c_ptr),
         ("timing", c_ptr),
         ("w_qkv_bf16", c_ptr), ("w_out_bf16", c_ptr),
+        ("band_mode", C.c_int32), ("band_y0", C.c_int32), ("band_Hg", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

@@ -47,6 +47,7 @@ struct Args {
     const int32_t* index_sample;              // [64, 25]
     uint8_t* top;                             // [B_, nH, 25] or null
     int use_rpb, shift;                       // shift > 0: analytic shift mask (My_model_1.py:803-836)
+    int mask_y0, mask_Hg;                     // mask row regions at shifted-frame row mask_y0 + local row of an image mask_Hg tall
     long long M;                              // tokens
     int windows;                              // B * nWin
     int tiles;                                // ceil(windows / 2)
@@ -403,12 +404,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Args a) {
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int t = lane + 32 * i;
-                        const int yy = wy * 8 + (t >> 3), xx = wx * 8 + (t & 7);
-                        const int rb = yy < a.map.H - 8 ? 0 : (yy < a.map.H - a.shift ? 1 : 2);
+                        const int yy = a.mask_y0 + wy * 8 + (t >> 3), xx = wx * 8 + (t & 7);
+                        const int rb = yy < a.mask_Hg - 8 ? 0 : (yy < a.mask_Hg - a.shift ? 1 : 2);
                         const int cb = xx < a.map.W - 8 ? 0 : (xx < a.map.W - a.shift ? 1 : 2);
                         s.region[t] = rb * 3 + cb;
                     }
-                    if (lane == 0) s.mixed = (wy * 8 + 8 > a.map.H - 8) || (wx * 8 + 8 > a.map.W - 8);
+                    if (lane == 0) s.mixed = (a.mask_y0 + wy * 8 + 8 > a.mask_Hg - 8) || (wx * 8 + 8 > a.map.W - 8);
                 }
             }
             bar_sync(3 + 2 * g + set, 128);                        // [S2] slots assigned

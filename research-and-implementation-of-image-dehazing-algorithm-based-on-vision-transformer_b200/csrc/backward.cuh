@@ -920,7 +920,7 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
 
     const T* x = static_cast<const T*>(f.x);
     const T* dy = static_cast<const T*>(a->dy);
-    WinMap map{f.H, f.W, f.W / 8, nWin, f.shift};
+    WinMap map{f.H, f.W, f.W / 8, nWin, f.shift, f.shift};
     const int mapped = f.windowed ? 0 : 1;
 
     // W_out [C(out), C(in)] -> as the [N = in, K = out] operand of dctx = do . W_out

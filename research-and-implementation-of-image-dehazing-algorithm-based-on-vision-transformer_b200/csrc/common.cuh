@@ -318,14 +318,16 @@ __device__ __forceinline__ float group_max(float v) {
 // shift of My_model_1.py:846 and window_partition of :550-574 folded in:
 //   window (b, wy, wx), token (ty, tx)  ->  pixel ((8*wy + ty + s) mod H, (8*wx + tx + s) mod W)
 struct WinMap {
-    int H, W, nWw, nWin, shift;   // nWin = windows per image
+    int H, W, nWw, nWin, shift;   // nWin = windows per image; shift: cyclic shift of the columns
+    int shift_y;                  // cyclic shift of the rows (== shift for a whole image; 0 for a row band whose rows the caller
+                                  // has already laid out in shifted-frame order, see LewinAttnFwdArgs::band_mode)
     __device__ __forceinline__ long long token(long long m) const {
         int n = static_cast<int>(m & 63);
         long long wg = m >> 6;
         int b = static_cast<int>(wg / nWin);
         int w = static_cast<int>(wg - static_cast<long long>(b) * nWin);
         int wy = w / nWw, wx = w - wy * nWw;
-        int y = wy * 8 + (n >> 3) + shift;
+        int y = wy * 8 + (n >> 3) + shift_y;
         int x = wx * 8 + (n & 7) + shift;
         if (y >= H) y -= H;
         if (x >= W) x -= W;
@@ -340,7 +342,7 @@ struct WinMap {
     }
     // token of window (b, wy, wx), in-window index n
     __device__ __forceinline__ uint32_t pixel(uint32_t b, uint32_t wy, uint32_t wx, uint32_t n) const {
-        int y = static_cast<int>(wy * 8 + (n >> 3)) + shift;
+        int y = static_cast<int>(wy * 8 + (n >> 3)) + shift_y;
         int x = static_cast<int>(wx * 8 + (n & 7u)) + shift;
         if (y >= H) y -= H;
         if (x >= W) x -= W;

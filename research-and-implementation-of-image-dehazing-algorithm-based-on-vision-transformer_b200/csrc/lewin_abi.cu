@@ -85,7 +85,9 @@ int check_attn(const LewinAttnFwdArgs* a) {
     if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->nH <= 0) return LEWIN_E_SHAPE;
     if (a->H % 8 || a->W % 8 || a->C % 32 || !head_dim_ok(a->C, a->nH)) return LEWIN_E_SHAPE;
     if (a->shift < 0 || a->shift >= 8) return LEWIN_E_SHAPE;
-    if (a->shift > 0 && (a->H <= 8 || a->W <= 8)) return LEWIN_E_SHAPE;   // My_model_1.py:764-766 forces shift 0
+    if (a->shift > 0 && ((a->H <= 8 && !a->band_mode) || a->W <= 8)) return LEWIN_E_SHAPE;   // My_model_1.py:764-766 forces shift 0
+    if (a->band_mode && (a->windowed || a->save_for_backward || a->band_y0 < 0 || a->band_Hg < a->H || a->band_y0 % 8 || a->band_Hg % 8))
+        return LEWIN_E_SHAPE;
     if (a->windowed && (a->shift != 0 || a->analytic_shift_mask)) return LEWIN_E_SHAPE;
     if (a->mask && a->nW_mask <= 0) return LEWIN_E_SHAPE;
     if (a->mask && ((a->B * (a->H / 8) * (a->W / 8)) % a->nW_mask)) return LEWIN_E_SHAPE;
@@ -121,7 +123,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     float* rstd = reinterpret_cast<float*>(wsp + align_up(tokens * sizeof(float), 256));
     unsigned char* ws_gemm = wsp + 2 * align_up(tokens * sizeof(float), 256);      // bf16 staging of the streamed-W GEMMs
 
-    WinMap map{a->H, a->W, a->W / 8, nWin, a->shift};
+    WinMap map{a->H, a->W, a->W / 8, nWin, a->shift, a->band_mode ? 0 : a->shift};
     const T* x = static_cast<const T*>(a->x);
 
     const KTimer kt{a->timing, stream};
@@ -196,6 +198,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         c.use_rpb = a->use_rpb;
         c.shift = (a->analytic_shift_mask && !a->windowed) ? a->shift : 0;
         c.H = a->H; c.W = a->W; c.nWw = a->W / 8; c.nWin = nWin;
+        c.y0 = a->band_mode ? a->band_y0 : 0; c.Hg = a->band_mode ? a->band_Hg : a->H;
         kt.begin(LEWIN_ATTN_K_CORE);
         if constexpr (Act<T>::kIsBf16) {
             if (C == a->nH * kHeadDim && pc3::enabled()) {       // head_dim 32: register-resident kernel
@@ -203,7 +206,7 @@ int attn_fwd(const LewinAttnFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
                 b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense;
                 b.index_sample = c.index_sample;
                 b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
-                b.shift = c.shift; b.H = c.H; b.W = c.W; b.nWw = c.nWw; b.nWin = c.nWin;
+                b.shift = c.shift; b.H = c.H; b.W = c.W; b.nWw = c.nWw; b.nWin = c.nWin; b.y0 = c.y0; b.Hg = c.Hg;
                 CK(pc3::launch(b, di.sms, stream));
             } else {
                 CK(launch_core_fwd<T>(c, di.sms, stream));
@@ -276,7 +279,7 @@ int core_only_fwd(const LewinCoreFwdArgs* a, void*, size_t, cudaStream_t stream)
     c.mask = a->mask; c.nW_mask = a->mask ? a->nW_mask : 1;
     c.B_ = a->B_; c.nH = a->nH; c.C = a->nH * D;
     c.use_rpb = a->use_rpb;
-    c.shift = 0; c.H = 8; c.W = 8; c.nWw = 1; c.nWin = 1;
+    c.shift = 0; c.H = 8; c.W = 8; c.nWw = 1; c.nWin = 1; c.y0 = 0; c.Hg = 8;
     bool done = false;
     if constexpr (Act<T>::kIsBf16) {
         if (D == kHeadDim && pc3::enabled()) {
@@ -284,7 +287,7 @@ int core_only_fwd(const LewinCoreFwdArgs* a, void*, size_t, cudaStream_t stream)
             b.qkv = c.qkv; b.ctx = c.ctx; b.top = c.top; b.rpb_table = c.rpb_table; b.rpb_dense = c.rpb_dense;
             b.index_sample = c.index_sample;
             b.mask = c.mask; b.nW_mask = c.nW_mask; b.B_ = c.B_; b.nH = c.nH; b.C = c.C; b.use_rpb = c.use_rpb;
-            b.shift = 0; b.H = 8; b.W = 8; b.nWw = 1; b.nWin = 1;
+            b.shift = 0; b.H = 8; b.W = 8; b.nWw = 1; b.nWin = 1; b.y0 = 0; b.Hg = 8;
             CK(pc3::launch(b, di.sms, stream));
             done = true;
         }
@@ -414,7 +417,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
                 done1 = true;
             } else if (async_gemm) {
                 if (a->fused) {
-                    WinMap nomap{a->H, a->W, a->W / 8, (a->H / 8) * (a->W / 8), 0};
+                    WinMap nomap{a->H, a->W, a->W / 8, (a->H / 8) * (a->W / 8), 0, 0};
                     CK(launch_ln_apply(static_cast<const __nv_bfloat16*>(a->y), xhat, a->ln_w, a->ln_b, tokens, C, 0, nomap, stream));
                     g.A = xhat; g.mean = nullptr; g.rstd = nullptr;
                 }

@@ -25,7 +25,9 @@ int attn_fused_launch(const LewinAttnFwdArgs* a, int num_sms, cudaStream_t strea
     k.windows = a->B * nWin;
     k.tiles = (k.windows + 1) / 2;
     k.tokens_per_image = a->H * a->W;
-    k.map = WinMap{a->H, a->W, a->W / 8, nWin, a->shift};
+    k.map = WinMap{a->H, a->W, a->W / 8, nWin, a->shift, a->band_mode ? 0 : a->shift};
+    k.mask_y0 = a->band_mode ? a->band_y0 : 0;
+    k.mask_Hg = a->band_mode ? a->band_Hg : a->H;
     return static_cast<int>(af::launch(a->C, k, num_sms, stream));
 }
 

@@ -28,8 +28,10 @@ struct CoreFwdArgs {
     int nW_mask;
     int B_, nH, C;
     int use_rpb;
-    // analytic shift mask (My_model_1.py:803-836)
+    // analytic shift mask (My_model_1.py:803-836): row regions are evaluated at shifted-frame row y0 + (row in this map) of an
+    // image Hg rows tall (y0 = 0, Hg = H unless the map is a row band of a taller image)
     int shift, H, W, nWw, nWin;
+    int y0, Hg;
 };
 
 constexpr int CORE_THREADS = 128;
@@ -105,8 +107,8 @@ __global__ void __launch_bounds__(CORE_THREADS) probsparse_core_fwd_kernel(const
                 // region id of each token in the shifted frame (My_model_1.py:809-820)
                 int w = wg % a.nWin;
                 int wy = w / a.nWw, wx = w - wy * a.nWw;
-                int y = wy * 8 + (tid >> 3), x = wx * 8 + (tid & 7);
-                int rb = y < a.H - 8 ? 0 : (y < a.H - a.shift ? 1 : 2);
+                int y = a.y0 + wy * 8 + (tid >> 3), x = wx * 8 + (tid & 7);
+                int rb = y < a.Hg - 8 ? 0 : (y < a.Hg - a.shift ? 1 : 2);
                 int cb = x < a.W - 8 ? 0 : (x < a.W - a.shift ? 1 : 2);
                 s.region[tid] = rb * 3 + cb;
             }

@@ -36,6 +36,7 @@ struct CoreBf16Args {
     const float* rpb_table; const float* rpb_dense; const int32_t* index_sample;   // [64, 25] (attn.py:91)
     const float* mask; int nW_mask;
     int B_, nH, C, use_rpb, shift, H, W, nWw, nWin;
+    int y0, Hg;           // row band of a taller image: see CoreFwdArgs
 };
 
 }  // namespace lewin

@@ -105,13 +105,13 @@ __global__ void __launch_bounds__(THREADS, CTAS) probsparse_core_v3_kernel(const
         if (a.shift > 0) {
             if (tid < kTok) {
                 const int w = wg % a.nWin, wy = w / a.nWw, wx = w - wy * a.nWw;
-                const int y = wy * 8 + (tid >> 3), x = wx * 8 + (tid & 7);
-                const int rb = y < a.H - 8 ? 0 : (y < a.H - a.shift ? 1 : 2);
+                const int y = a.y0 + wy * 8 + (tid >> 3), x = wx * 8 + (tid & 7);
+                const int rb = y < a.Hg - 8 ? 0 : (y < a.Hg - a.shift ? 1 : 2);
                 const int cb = x < a.W - 8 ? 0 : (x < a.W - a.shift ? 1 : 2);
                 s.region[tid] = rb * 3 + cb;
                 if (tid == 0) {                                                  // only the last window row / column is mixed
                     const int w0 = wg % a.nWin, wy0 = w0 / a.nWw, wx0 = w0 - wy0 * a.nWw;
-                    s.mixed = (wy0 * 8 + 8 > a.H - 8) || (wx0 * 8 + 8 > a.W - 8);
+                    s.mixed = (a.y0 + wy0 * 8 + 8 > a.Hg - 8) || (wx0 * 8 + 8 > a.W - 8);
                 }
             }
         }

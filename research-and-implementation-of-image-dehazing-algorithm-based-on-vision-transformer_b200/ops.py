@@ -202,7 +202,8 @@ class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
                 drop_scale, geom):
-        B, H, W, nH, shift, windowed, use_rpb, analytic, need_grad = geom
+        B, H, W, nH, shift, windowed, use_rpb, analytic, need_grad = geom[:9]
+        band = geom[9] if len(geom) > 9 else None          # (y0, Hg): row band of a taller image (forward only)
         lib = _lib.load()
         dt = _dtype_tag(x)
         x = x.contiguous()
@@ -223,6 +224,10 @@ class _AttnFn(torch.autograd.Function):
             w_out=_ptr(w_out_), b_out=_ptr(b_out_), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
             index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
             qkv=None, ctx=None, top=_ptr(top))
+        if band is not None:
+            if need_grad:
+                raise RuntimeError("lewin_b200.lewin_attn: row-band mode is forward only")
+            a.band_mode, a.band_y0, a.band_Hg = 1, int(band[0]), int(band[1])
         kmask = lib.lewin_attn_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
         if kmask == 2:          # LEWIN_ATTN_K_FUSED: q|k|v and ctx stay on chip, the ABI only wants valid placeholders
             qkv = cbuf = torch.empty((16,), dtype=x.dtype, device=dev)
@@ -253,7 +258,7 @@ class _AttnFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dtop):
         (x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense, idx, mask, ds, qkv, cbuf, top) = ctx.saved_tensors
-        B, H, W, nH, shift, windowed, use_rpb, analytic, _ = ctx.geom
+        B, H, W, nH, shift, windowed, use_rpb, analytic, _ = ctx.geom[:9]
         lib = _lib.load()
         dt = ctx.dt
         dev = x.device
@@ -353,11 +358,15 @@ class _LeffFn(torch.autograd.Function):
 
 def lewin_attn(x, *, B, H, W, num_heads, shift, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out,
                rpb_table=None, rpb_dense=None, index_sample, mask=None, drop_scale=None,
-               windowed=False, use_rpb=True, analytic_shift_mask=True, return_top=False):
-    """Attention half of a LeWin block.  Returns y (same shape as x) [and the selected top-u indices]."""
+               windowed=False, use_rpb=True, analytic_shift_mask=True, return_top=False, band=None):
+    """Attention half of a LeWin block.  Returns y (same shape as x) [and the selected top-u indices].
+    band=(y0, Hg): x is a band of H rows, already in shifted-frame row order, of an image Hg rows tall whose shifted-frame
+    row y0 is the band's first row (canvas-mode row sharding, fullres / canvas_bands; forward only)."""
     need = torch.is_grad_enabled() and any(
         isinstance(t, torch.Tensor) and t.requires_grad for t in (x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense))
     geom = (int(B), int(H), int(W), int(num_heads), int(shift), bool(windowed), bool(use_rpb), bool(analytic_shift_mask), need)
+    if band is not None:
+        geom = geom + ((int(band[0]), int(band[1])),)
     y, top = _AttnFn.apply(x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
                            drop_scale, geom)
     return (y, top) if return_top else y

@@ -22,12 +22,12 @@ import torch.nn as nn
 from .modules import LeWinTransformerBlock, draw_index_sample
 
 
-def _tokens_to_nchw(x):
+def _tokens_to_nchw(x, hw=None):
     """[B, L, C] token-major -> [B, C, H, W] VIEW with channels_last strides (no copy): the residual stream is already
     NHWC, so cuDNN's NHWC kernels consume it directly (the reference transposes to NCHW and back around every
-    convolution, My_model_1.py:620-621, 646-647, 679, 719)."""
+    convolution, My_model_1.py:620-621, 646-647, 679, 719).  hw: explicit (H, W) of a non-square map (row bands)."""
     B, L, C = x.shape
-    H = W = int(math.sqrt(L))
+    H, W = hw if hw is not None else (int(math.sqrt(L)),) * 2
     return x.reshape(B, H, W, C).permute(0, 3, 1, 2)
 
 
@@ -87,14 +87,15 @@ class Upsample(nn.Module):
             return False
         return xb
 
-    def forward(self, x, skip=None):
-        """``skip`` given: returns torch.cat([up(x), skip], -1) (My_model_1.py:1189-1204) with the up half written in place."""
+    def forward(self, x, skip=None, hw=None):
+        """``skip`` given: returns torch.cat([up(x), skip], -1) (My_model_1.py:1189-1204) with the up half written in place.
+        hw: explicit (H, W) of a non-square token map (canvas row bands); default: square, as the reference assumes."""
         d = self.deconv[0]
         xb = self._gemm_path(x)
         if xb is not False:
             from . import ops
             B, L, _ = x.shape
-            H = W = int(math.sqrt(L))
+            H, W = hw if hw is not None else (int(math.sqrt(L)),) * 2
             if skip is None:
                 return ops.lewin_upsample(xb, d.weight, d.bias, B=B, H=H, W=W)
             C = self.out_channel
@@ -102,7 +103,7 @@ class Upsample(nn.Module):
             ops.lewin_upsample(xb, d.weight, d.bias, B=B, H=H, W=W, out=buf)
             buf[..., C:] = skip
             return buf
-        y = torch.nn.functional.conv_transpose2d(_tokens_to_nchw(x), _cl(d.weight), d.bias, stride=2)
+        y = torch.nn.functional.conv_transpose2d(_tokens_to_nchw(x, hw), _cl(d.weight), d.bias, stride=2)
         y = _nchw_to_tokens(y)
         return y if skip is None else torch.cat([y, skip], -1)
 

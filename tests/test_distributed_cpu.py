@@ -119,3 +119,51 @@ def test_dead_parameter_inventory():
     assert len(dead) == 6
     assert parallel.freeze_dead_parameters(blk) == 6
     assert sum(p.requires_grad for p in blk.parameters()) == 19      # the 19 live parameters of SURVEY Appendix B
+
+
+# ---------------------------------------------------------------- canvas row bands: the halo-exchange driver
+def _band_stand_in(x, rank, world):
+    """A generator with the exchange pattern of canvas_bands._block: a cyclic 'take the next band's first rows / hand the
+    last rows back' pair followed by a non-cyclic one-row halo on each side.  Returns what a rank can only know if every
+    message arrived from the right neighbour."""
+    from lewin_b200.canvas_bands import _Xchg
+    s = 2
+    _, from_down = yield _Xchg(to_up=x[:s].contiguous(), want_down=s, cyclic=True)
+    local = torch.cat([x[s:], from_down], 0)
+    from_up, _ = yield _Xchg(to_down=local[-s:].contiguous() * 2, want_up=s, cyclic=True)
+    y = torch.cat([from_up, local[:-s]], 0)
+    top, bot = rank > 0, rank < world - 1
+    fu, fd = yield _Xchg(to_up=y[:1].contiguous() if top else None, to_down=y[-1:].contiguous() if bot else None,
+                         want_up=1 if top else 0, want_down=1 if bot else 0)
+    z = x.new_zeros((1,) + tuple(x.shape[1:]))
+    return torch.cat([fu if top else z, y, fd if bot else z], 0)
+
+
+def _bands_worker(rank, world, port, ref_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lewin_b200 import canvas_bands
+    full = torch.arange(world * 6 * 5 * 3, dtype=torch.float32).view(world * 6, 5, 3)
+    mine = full[rank * 6:(rank + 1) * 6]
+    out = canvas_bands._serve_dist(_band_stand_in(mine, rank, world), rank, world, None, torch.device("cpu"), None)
+    ref = torch.load(ref_path)[rank]
+    assert torch.equal(out, ref), f"rank {rank}: halo exchange over torch.distributed differs from the in-process routing"
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_canvas_band_halo_exchange_gloo_matches_in_process_routing(tmp_path, world):
+    """canvas_bands: the torch.distributed driver (_serve_dist: batched isend / irecv with the ring neighbours) delivers the
+    same rows as the in-process lock-step driver (_serve_virtual) that the GPU parity test runs the whole model through."""
+    from lewin_b200 import canvas_bands
+    full = torch.arange(world * 6 * 5 * 3, dtype=torch.float32).view(world * 6, 5, 3)
+    ref = canvas_bands._serve_virtual([_band_stand_in(full[r * 6:(r + 1) * 6], r, world) for r in range(world)])
+    # ring semantics: band 0's first two rows came back from the LAST band (its handed-back rows, doubled by the stand-in),
+    # and those are band 0's own first rows that travelled up the ring: the roll closes on itself
+    assert torch.equal(ref[0][1:3], 2 * full[0:2])
+    assert canvas_bands.band_units(13, 0, 8) == (0, 2) and canvas_bands.band_units(13, 7, 8) == (12, 13)
+    assert [canvas_bands.band_units(13, r, 4) for r in range(4)] == [(0, 4), (4, 7), (7, 10), (10, 13)]
+    path = str(tmp_path / "ref.pt")
+    torch.save(ref, path)
+    mp.spawn(_bands_worker, args=(world, _free_port(), path), nprocs=world, join=True)

@@ -144,6 +144,8 @@ def kernel_work(op, name, info):
         return 72.0 * t * C, 8 * t * C * s
     if name == "attn_fused":      # LN1 -> q|k|v -> ProbSparse core -> out projection -> residual in one kernel: x read, y written
         return 8.0 * t * C * C + 150.0 * t * C, 2 * t * C * s + 4 * C * C * 4
+    if name == "leff_tail":       # dwconv + GELU -> linear2 -> residual in one kernel: h1 read, y read, out written (h2 stays on chip)
+        return 72.0 * t * C + 2.0 * t * 4 * C * C, t * 4 * C * s + 2 * t * C * s + 4 * C * C * 4 + 40 * C * 4
     if name == "ln_stats":
         return 0.0, t * C * s
     return 0.0, 0.0

@@ -39,7 +39,7 @@ extern "C" {
 typedef struct CUstream_st* lewin_stream_t; /* == cudaStream_t */
 typedef struct CUevent_st*  lewin_event_t;  /* == cudaEvent_t  */
 
-#define LEWIN_ABI_VERSION 3
+#define LEWIN_ABI_VERSION 4
 
 /* error codes (negative) */
 #define LEWIN_E_NULL      (-1)  /* a required pointer is NULL */
@@ -211,7 +211,9 @@ typedef struct {
     const float* drop_scale;                 /* [B] or NULL */
 
     void* h1;                      /* [B*H*W, hidden] GELU(linear1), activations dtype */
-    void* h2;                      /* [B*H*W, hidden] GELU(dwconv) */
+    void* h2;                      /* [B*H*W, hidden] GELU(dwconv).  A call that lewin_leff_fwd_kernel_mask reports with bit
+                                    * LEWIN_LEFF_K_TAIL keeps h2 on chip: the pointer must still be non-NULL and 16-byte
+                                    * aligned but may be a small placeholder */
     void* a1;                      /* pre-GELU linear1 output (only if save_for_backward) */
     void* a2;                      /* pre-GELU dwconv output  (only if save_for_backward) */
 
@@ -226,7 +228,9 @@ typedef struct {
 #define LEWIN_LEFF_K_FC1     1
 #define LEWIN_LEFF_K_DWCONV  2
 #define LEWIN_LEFF_K_FC2     3
-#define LEWIN_LEFF_NKERNELS  4
+#define LEWIN_LEFF_K_TAIL    4   /* depthwise conv + GELU + linear2 + residual as ONE kernel (bf16 inference, C <= 64): replaces
+                                  * slots 2 and 3 (csrc/leff_tail.cuh: the conv tile is the tcgen05.mma A operand, h2 stays on chip) */
+#define LEWIN_LEFF_NKERNELS  5
 
 /* Bit k set <=> the forward call will record timing slot k (LEWIN_ATTN_K_* / LEWIN_LEFF_K_*) for these arguments. */
 int lewin_attn_fwd_kernel_mask(const LewinAttnFwdArgs* a, int dtype);

@@ -109,7 +109,7 @@ EXPORTS = (
     "lewin_upsample_fwd_bf16", "lewin_upsample_fwd_workspace_bytes", "lewin_input_proj_fwd_bf16",
 )
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 DTYPE_TAG = {"f32": 0, "bf16": 1}
 
 _lib = None

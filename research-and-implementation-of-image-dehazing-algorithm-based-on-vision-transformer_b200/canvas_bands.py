@@ -211,7 +211,7 @@ def _serve_dist(gen, rank, world, group, dev, dtype_hint):
 
 
 @torch.no_grad()
-def dehaze_canvas_bands(model, img, ps=128, index_samples=None, group=None, virtual_world=None):
+def dehaze_canvas_bands(model, img, ps=128, index_samples=None, group=None, virtual_world=None, _broadcast=True):
     """Canvas mode (test_long_GPU.py:74-93: wrap-pad, ONE forward over the canvas, crop, clamp) with the canvas split into
     row bands over the ranks of `group` (torch.distributed; every rank passes the full image and ends with the full result),
     or - ``virtual_world=N`` - over N bands processed in lock step inside this process.  Identical to fullres.dehaze_canvas."""
@@ -233,7 +233,7 @@ def dehaze_canvas_bands(model, img, ps=128, index_samples=None, group=None, virt
         rank = dist.get_rank(group) if distributed else 0
         world = dist.get_world_size(group) if distributed else 1
         assert world <= L // UNIT, "more ranks than 128-row units"
-        if distributed:
+        if distributed and _broadcast:          # one set of key-sample draws for the whole image, as the reference's single call
             idx = index_samples.to(img.device)
             dist.broadcast(idx, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             index_samples = idx
@@ -252,3 +252,50 @@ def dehaze_canvas_bands(model, img, ps=128, index_samples=None, group=None, virt
         else:
             full = band
     return full[None, :, :H, :W].clamp(0, 1)
+
+
+class GraphedCanvasBands:
+    """CUDA-graph replay of ``dehaze_canvas_bands`` for one fixed image shape on this rank: the band forward is ~300 kernel
+    launches plus ~100 small point-to-point messages, and at 2+ GPUs the per-rank GPU time drops below the time the host
+    needs to issue them.  The NCCL sends / receives are captured into the graph together with the kernels (every rank
+    captures the same sequence); the image and the 18 key-sample draws are copied into static buffers before each replay.
+    Falls back to eager calls if the capture is refused."""
+
+    def __init__(self, model, img, index_samples, autocast_dtype=None, group=None, warmup=2):
+        from . import ops
+        self.model, self.group, self.autocast_dtype = model, group, autocast_dtype
+        self.img = img.clone()
+        self.idx = index_samples.to(device=img.device, dtype=torch.int64).clone()
+        self.graph, self.out = None, None
+        try:
+            with ops.weight_images.pin() as held:
+                side = torch.cuda.Stream(device=img.device)
+                side.wait_stream(torch.cuda.current_stream(img.device))
+                with torch.cuda.stream(side):
+                    for _ in range(warmup):
+                        self._run()
+                torch.cuda.current_stream(img.device).wait_stream(side)
+                torch.cuda.synchronize(img.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.out = self._run()
+                self.graph = g
+            self._images = list(held)
+        except Exception as e:              # capture is an optimisation
+            self.graph, self.error = None, repr(e)[:200]
+            torch.cuda.synchronize(img.device)
+
+    def _run(self):
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", self.autocast_dtype):
+                return dehaze_canvas_bands(self.model, self.img, index_samples=self.idx, group=self.group, _broadcast=False)
+        return dehaze_canvas_bands(self.model, self.img, index_samples=self.idx, group=self.group, _broadcast=False)
+
+    @torch.no_grad()
+    def __call__(self, img, index_samples):
+        self.img.copy_(img, non_blocking=True)
+        self.idx.copy_(index_samples.to(dtype=torch.int64), non_blocking=True)
+        if self.graph is None:
+            return self._run()
+        self.graph.replay()
+        return self.out

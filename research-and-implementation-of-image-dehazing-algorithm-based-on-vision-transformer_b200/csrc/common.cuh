@@ -146,7 +146,6 @@ __device__ __forceinline__ float exp_sub(float x, float mxl2 /* mx * log2(e) */)
     return r;
 }
 
-#ifndef LEWIN_TU_LITE      // the GELU tables and their (non-template) kernels belong to ONE translation unit: lewin_abi.cu
 // ---------------------------------------------------------------- exact bf16 GELU by table
 // In the bf16 path GELU always acts on a value that was just rounded to bf16 (the linear / conv output), and its
 // result is rounded to bf16 again, so it is a 16-bit -> 16-bit function.  Outside 2^-12 <= |x| < 16 the result is
@@ -155,6 +154,9 @@ __device__ __forceinline__ float exp_sub(float x, float mxl2 /* mx * log2(e) */)
 // instructions + one shared-memory load instead of ~45 (erff) — the element-wise GELUs, not the GEMMs, are the
 // instruction bottleneck of LeFF on B200.
 constexpr int kGeluTabSize = 4096;
+constexpr int kGelu2TabSize = 8192;                    // wide table (below)
+constexpr uint32_t kGelu2Base = 99u << 7;              // bf16 bits of 2^-28
+#ifndef LEWIN_TU_LITE      // the GELU tables and their (non-template) kernels belong to ONE translation unit: lewin_abi.cu
 __device__ uint16_t g_gelu_tab[kGeluTabSize];
 __device__ uint16_t g_gelu_grad_tab[kGeluTabSize];     // bf16(gelu'(x)) on the same index space (backward, bf16 path)
 
@@ -162,8 +164,6 @@ __device__ uint16_t g_gelu_grad_tab[kGeluTabSize];     // bf16(gelu'(x)) on the 
 // 8192 entries (16 KB), index = (|x| bits - 0x3180) | sign << 12.  With 2^-28 as the lower edge an out-of-table
 // element is a once-per-billions event for activations, so the range check is deferred to one test per thread and
 // chunk (OR of the biased magnitudes) and the exact slow path (gelu_bits) is practically never taken.
-constexpr int kGelu2TabSize = 8192;
-constexpr uint32_t kGelu2Base = 99u << 7;              // bf16 bits of 2^-28
 __device__ uint16_t g_gelu_tab2[kGelu2TabSize];
 __device__ uint16_t g_gelu_grad_tab2[kGelu2TabSize];   // bf16(gelu'(x)) on the same index space (backward)
 
@@ -222,6 +222,7 @@ __device__ __forceinline__ void gelu_tab_to_smem(uint16_t* dst, int tid, int nth
     for (int i = tid; i < kGeluTabSize / 8; i += nthreads)
         reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(g_gelu_tab)[i];
 }
+#endif  // LEWIN_TU_LITE
 // bf16 bits of GELU(x) for x given as bf16 bits.  Fast path (2^-12 <= |x| < 16): 5 integer ops + one 16-bit load;
 // the out-of-range cases are rare (|x| < 2.4e-4 or >= 16) and take a divergent slow path.
 __device__ __forceinline__ uint32_t gelu_bits(const uint16_t* __restrict__ tab, uint32_t u) {
@@ -231,10 +232,12 @@ __device__ __forceinline__ uint32_t gelu_bits(const uint16_t* __restrict__ tab, 
         return ((u & 0x7F80u) > 0x0080u) ? (u - 0x80u) : (u & 0x8000u);
     return (u & 0x8000u) ? 0x8000u : u;                            // huge: x, or -0 for negative x
 }
+#ifndef LEWIN_TU_LITE
 __device__ __forceinline__ void gelu_tab2_to_smem(uint16_t* dst, int tid, int nthreads) {
     for (int i = tid; i < kGelu2TabSize / 8; i += nthreads)
         reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(g_gelu_tab2)[i];
 }
+#endif
 // Packed pair: bf16x2 bits in -> bf16x2 bits of GELU out, ~7 ALU instructions + one 16-bit shared load per element and
 // no branch.  `oor` accumulates the biased magnitudes: (oor >> 12) != 0 afterwards means some element handled by this
 // thread was outside the table and the caller must redo its elements with gelu_pair_exact.
@@ -249,12 +252,14 @@ __device__ __forceinline__ uint32_t gelu_pair_fast(const uint16_t* __restrict__ 
 }
 // true if any element accumulated into `oor` by gelu_pair_fast was outside the table
 __device__ __forceinline__ bool gelu_pair_oor(uint32_t oor) { return (oor & 0xF000F000u) != 0u; }
+#ifndef LEWIN_TU_LITE
 __device__ __forceinline__ void gelu_grad_tab2_to_smem(uint16_t* dst, int tid, int nthreads) {
     for (int i = tid; i < kGelu2TabSize / 8; i += nthreads)
         reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(g_gelu_grad_tab2)[i];
 }
+#endif
 // gelu'(x) of a packed bf16 pair as packed bf16 bits; outside the table: 0.5 (tiny), 1 or 0 (huge, by sign)
-__device__ __noinline__ uint32_t gelu_grad_pair_exact(const uint16_t* __restrict__ tab2g, uint32_t in2) {
+static __device__ __noinline__ uint32_t gelu_grad_pair_exact(const uint16_t* __restrict__ tab2g, uint32_t in2) {
     uint32_t out = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -269,7 +274,7 @@ __device__ __noinline__ uint32_t gelu_grad_pair_exact(const uint16_t* __restrict
     return out;
 }
 // exact for every bf16 input (table inside 2^-28 <= |x| < 16, closed forms outside: 0.5 x, x or -0)
-__device__ __noinline__ uint32_t gelu_pair_exact(const uint16_t* __restrict__ tab2, uint32_t in2) {
+static __device__ __noinline__ uint32_t gelu_pair_exact(const uint16_t* __restrict__ tab2, uint32_t in2) {
     uint32_t out = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -297,8 +302,6 @@ __device__ __forceinline__ float gelu_tab(const uint16_t* __restrict__ tab, floa
     const uint32_t u = __bfloat16_as_ushort(__float2bfloat16_rn(x));
     return __uint_as_float(gelu_bits(tab, u) << 16);
 }
-
-#endif  // LEWIN_TU_LITE
 
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {     // reduce over aligned groups of G lanes

@@ -12,6 +12,7 @@
 #include "probsparse_core_v3.cuh"
 #include "backward.cuh"
 #include "attn_fused_api.h"
+#include "leff_tail_api.h"
 
 #include <atomic>
 
@@ -348,7 +349,7 @@ size_t leff_fwd_ws(const LewinLeffFwdArgs* a) {
 // bf16 LeFF: three kernels (linear1 + GELU, depthwise 3x3 + GELU, linear2 + residual); h1 / h2 round-trip HBM once each.
 // (A single on-chip kernel was built and measured 2-3x slower in round 1 - halo recompute of linear1 and per-tile staging
 // cost more instructions than the 8 bytes per hidden element of HBM traffic they save - and has been removed.)
-struct LeffPlan { bool ws_gemm, async_gemm, ln_stats; };
+struct LeffPlan { bool ws_gemm, async_gemm, ln_stats, tail; };
 inline LeffPlan plan_leff(const LewinLeffFwdArgs* a, bool bf) {
     LeffPlan p{};
     const long long tokens = static_cast<long long>(a->B) * a->H * a->W;
@@ -356,6 +357,7 @@ inline LeffPlan plan_leff(const LewinLeffFwdArgs* a, bool bf) {
     p.async_gemm = bf && !p.ws_gemm && a->C > async_min_c() && a->C % 64 == 0 && a->hidden % 64 == 0 &&
                    !getenv("LEWIN_NO_ASYNC_GEMM");
     p.ln_stats = a->fused && !p.async_gemm && !p.ws_gemm;
+    p.tail = bf && p.ws_gemm && leff_tail_supported(a);      // dwconv + GELU + linear2 + residual in one kernel (leff_tail.cuh)
     return p;
 }
 
@@ -427,6 +429,14 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         }
         if (!done1) CK((launch_gemm_any<T, EPI_BIAS_GELU>(g, stream)));
         kt.end(LEWIN_LEFF_K_FC1);
+    }
+    if (plan.tail) {
+        const uint16_t* tab2 = nullptr;
+        if constexpr (Act<T>::kIsBf16) CK(cudaGetSymbolAddress(reinterpret_cast<void**>(const_cast<uint16_t**>(&tab2)), g_gelu_tab2));
+        kt.begin(LEWIN_LEFF_K_TAIL);
+        if (int rc = leff_tail_launch(a, tab2, di.sms, stream)) return rc;
+        kt.end(LEWIN_LEFF_K_TAIL);
+        return 0;
     }
     kt.begin(LEWIN_LEFF_K_DWCONV);
     bool dw_done = false;
@@ -625,6 +635,7 @@ int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype) {
     if (!a) return 0;
     if (check_leff(a) != 0) return 0;
     const LeffPlan p = plan_leff(a, dtype == LEWIN_DTYPE_BF16);
+    if (p.tail) return (1 << LEWIN_LEFF_K_FC1) | (1 << LEWIN_LEFF_K_TAIL);
     return (p.ln_stats ? 1 : 0) | 0xE;
 }
 int lewin_leff_fwd_f32(const LewinLeffFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {

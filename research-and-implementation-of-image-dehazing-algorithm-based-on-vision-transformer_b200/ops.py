@@ -87,7 +87,7 @@ class KernelTimer:
 
     active = None
     ATTN = ("ln_stats", "attn_fused", "gemm_qkv", "probsparse_core", "gemm_out")
-    LEFF = ("ln_stats", "gemm_fc1_gelu", "dwconv_gelu", "gemm_fc2")
+    LEFF = ("ln_stats", "gemm_fc1_gelu", "dwconv_gelu", "gemm_fc2", "leff_tail")
 
     def __init__(self):
         self.launches = []     # (op, names, live_slots, info, events)
@@ -302,9 +302,9 @@ class _LeffFn(torch.autograd.Function):
         dev = y.device
         out = torch.empty_like(y)
         h1 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
-        h2 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
+        h2 = h1                       # placeholder until the library says whether h2 exists in global memory for this call
         a1 = torch.empty_like(h1) if need_grad else None
-        a2 = torch.empty_like(h2) if need_grad else None
+        a2 = torch.empty_like(h1) if need_grad else None
         ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_ = [_f32c(t) for t in (ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale)]
         a = _lib.LewinLeffFwdArgs(
             B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=int(need_grad), reserved=0,
@@ -314,10 +314,13 @@ class _LeffFn(torch.autograd.Function):
         if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:
             w1_b, w2_b = _bf16_image(w1_), _bf16_image(w2_)
             a.w1_bf16, a.w2_bf16 = _ptr(w1_b), _ptr(w2_b)
+        mask = lib.lewin_leff_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
+        if not (mask >> 4 & 1):       # LEWIN_LEFF_K_TAIL clear: the three-kernel pipeline writes h2 = GELU(dwconv(h1))
+            h2 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
+            a.h2 = _ptr(h2)
         if KernelTimer.active is not None:
-            mask = lib.lewin_leff_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
             tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt),
-                                                tuple(k for k in range(4) if mask >> k & 1))
+                                                tuple(k for k in range(5) if mask >> k & 1))
             a.timing = ctypes_addr(tim)
         ws = _workspace(lib.lewin_leff_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
         fn = getattr(lib, f"lewin_leff_fwd_{dt}")

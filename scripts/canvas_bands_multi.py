@@ -40,6 +40,7 @@ def timed(fn, n):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms), out
 
+use_graph = len(sys.argv) > 2 and sys.argv[2] == "graph"      # NCCL point-to-point inside a captured graph: opt-in
 with ac():
     ms_b, y_b = timed(lambda: canvas_bands.dehaze_canvas_bands(model, img, index_samples=idx), 5)
     ms_1, y_1 = timed(lambda: fullres.dehaze_canvas(model, img, index_samples=idx), 3)      # every rank, redundantly
@@ -49,5 +50,11 @@ res = dict(mode="canvas 1664^2 by row bands", n_gpus=world, dtype=dt, bands_ms=m
            units_per_rank=[canvas_bands.band_units(13, r, world)[1] - canvas_bands.band_units(13, r, world)[0] for r in range(world)])
 if rank == 0:
     print(json.dumps(res), flush=True)
+if use_graph:
+    gb = canvas_bands.GraphedCanvasBands(model, img, idx.to(dev), torch.bfloat16 if dt == "bf16" else None)
+    ms_g, y_g = timed(lambda: gb(img, idx.to(dev)), 10)
+    if rank == 0:
+        print(json.dumps(dict(graph_ms=ms_g, graph_images_per_s=1e3 / ms_g, graph_captured=gb.graph is not None,
+                              graph_error=getattr(gb, "error", None), graph_equal_single=bool(torch.equal(y_g, y_1)))), flush=True)
 if world > 1:
     dist.destroy_process_group()

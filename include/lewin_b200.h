@@ -294,6 +294,42 @@ typedef struct LewinInputProjArgs {
 } LewinInputProjArgs;
 int lewin_input_proj_fwd_bf16(const LewinInputProjArgs* a, lewin_stream_t stream);
 
+/* Downsample.forward, My_model_1.py:606-630: Conv2d(Cin, 2*Cin, kernel 4, stride 2, padding 1) on the token map, tokens out.
+ * Implicit GEMM on tcgen05 (csrc/conv_igemm.cuh): one TMA box per (tap, 64-channel chunk), bias fused with torch's two
+ * roundings (conv -> bf16, + bias -> bf16).  The input may be the right half of a torch.cat([up, skip]) buffer (ld_x >
+ * Cin).  pad_h = 0: no padding in the row direction - the caller supplies the halo rows (canvas row bands), and the output
+ * has H/2 - 1 rows.  bf16 inference.   */
+typedef struct LewinDownsampleArgs {
+    int32_t B, H, W, Cin;          /* input map; H, W even, (W/2) % 8 == 0, Cin in {32, 64, 128, ..., 512} */
+    int32_t ld_x;                  /* elements between consecutive input tokens (0 = Cin) */
+    int32_t ld_out;                /* elements between consecutive output tokens (0 = 2*Cin) */
+    int32_t pad_h;                 /* 1: padding 1 above / below (the reference); 0: rows already carry their halo */
+    int32_t reserved;
+    const void*  x;                /* [B, H, W, ld_x] bf16, channels [0, Cin) of each token */
+    const float* weight;           /* [2*Cin, Cin, 4, 4] */
+    const float* bias;             /* [2*Cin] */
+    void*        out;              /* [B, Hout, W/2, ld_out] bf16, Hout = H/2 (pad_h) or H/2 - 1 */
+} LewinDownsampleArgs;
+int    lewin_downsample_fwd_bf16(const LewinDownsampleArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+size_t lewin_downsample_fwd_workspace_bytes(const LewinDownsampleArgs* a, int dtype);
+
+/* OutputProj.forward, My_model_1.py:696-733 (+ the `x + y` of Uformer.forward :1207): Conv2d(Cin, Cout <= 16, kernel 3,
+ * padding 1) from the token map to an fp32 NCHW image, bias fused (conv -> bf16, + bias -> bf16), optional residual image
+ * added in fp32.  Same implicit-GEMM kernel (N padded to 16).  pad_h = 0: the caller supplies the halo rows, H - 2 rows out. */
+typedef struct LewinOutputProjArgs {
+    int32_t B, H, W, Cin, Cout;    /* W % 8 == 0, Cin % 64 == 0 */
+    int32_t ld_x;                  /* elements between consecutive input tokens (0 = Cin) */
+    int32_t pad_h;
+    int32_t reserved;
+    const void*  x;                /* [B, H, W, ld_x] bf16 */
+    const float* weight;           /* [Cout, Cin, 3, 3] */
+    const float* bias;             /* [Cout] */
+    const float* residual;         /* [B, Cout, Hout, W] fp32 or NULL */
+    float*       out;              /* [B, Cout, Hout, W] fp32, Hout = H (pad_h) or H - 2 */
+} LewinOutputProjArgs;
+int    lewin_output_proj_fwd_bf16(const LewinOutputProjArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+size_t lewin_output_proj_fwd_workspace_bytes(const LewinOutputProjArgs* a, int dtype);
+
 int         lewin_abi_version(void);     /* == LEWIN_ABI_VERSION */
 long long   lewin_launch_count(void);    /* kernels launched by this library in this process (diagnostic counter) */
 const char* lewin_build_info(void);      /* "sm_100a nvcc <ver> ..." */

@@ -96,6 +96,22 @@ class LewinInputProjArgs(C.Structure):
     ]
 
 
+class LewinDownsampleArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+        ("ld_x", C.c_int32), ("ld_out", C.c_int32), ("pad_h", C.c_int32), ("reserved", C.c_int32),
+        ("x", c_ptr), ("weight", c_ptr), ("bias", c_ptr), ("out", c_ptr),
+    ]
+
+
+class LewinOutputProjArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+        ("ld_x", C.c_int32), ("pad_h", C.c_int32), ("reserved", C.c_int32),
+        ("x", c_ptr), ("weight", c_ptr), ("bias", c_ptr), ("residual", c_ptr), ("out", c_ptr),
+    ]
+
+
 # every symbol include/lewin_b200.h declares (tests check the .so exports all of them)
 EXPORTS = (
     "lewin_attn_fwd_f32", "lewin_attn_fwd_bf16", "lewin_attn_bwd_f32", "lewin_attn_bwd_bf16",
@@ -107,6 +123,8 @@ EXPORTS = (
     "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count",
     "lewin_attn_fwd_kernel_mask", "lewin_leff_fwd_kernel_mask",
     "lewin_upsample_fwd_bf16", "lewin_upsample_fwd_workspace_bytes", "lewin_input_proj_fwd_bf16",
+    "lewin_downsample_fwd_bf16", "lewin_downsample_fwd_workspace_bytes",
+    "lewin_output_proj_fwd_bf16", "lewin_output_proj_fwd_workspace_bytes",
 )
 
 ABI_VERSION = 4
@@ -139,6 +157,13 @@ def load():
     lib.lewin_upsample_fwd_bf16.restype = C.c_int
     lib.lewin_upsample_fwd_workspace_bytes.argtypes = [C.POINTER(LewinUpsampleFwdArgs), C.c_int]
     lib.lewin_upsample_fwd_workspace_bytes.restype = C.c_size_t
+    for nm, at in (("downsample", LewinDownsampleArgs), ("output_proj", LewinOutputProjArgs)):
+        fn = getattr(lib, f"lewin_{nm}_fwd_bf16")
+        fn.argtypes = [C.POINTER(at), C.c_void_p, C.c_size_t, C.c_void_p]
+        fn.restype = C.c_int
+        wsf = getattr(lib, f"lewin_{nm}_fwd_workspace_bytes")
+        wsf.argtypes = [C.POINTER(at), C.c_int]
+        wsf.restype = C.c_size_t
     lib.lewin_input_proj_fwd_bf16.argtypes = [C.POINTER(LewinInputProjArgs), C.c_void_p]
     lib.lewin_input_proj_fwd_bf16.restype = C.c_int
     lib.lewin_abi_version.restype = C.c_int

@@ -131,10 +131,10 @@ def _band_forward(model, canvas, idx, rank, world):
     for lvl in range(4):
         x = yield from stage(getattr(model, f"encoderlayer_{lvl}"), lvl, x, lvl)
         skips.append(x)
-        conv = getattr(model, f"dowsample_{lvl}").conv[0]
         slab = yield from _halo_slab(x, rank, world)
-        y = F.conv2d(_nchw(slab), conv.weight.contiguous(memory_format=torch.channels_last), conv.bias, stride=2, padding=(0, 1))
-        x = y[0].permute(1, 2, 0).contiguous()                                   # [Hb / 2, W / 2, 2C]
+        Hl, Wl, Cl = slab.shape
+        y = getattr(model, f"dowsample_{lvl}")(slab.reshape(1, Hl * Wl, Cl), hw=(Hl, Wl), pad_h=False)
+        x = y.reshape(Hl // 2 - 1, Wl // 2, 2 * Cl)                                # [Hb / 2, W / 2, 2C]
     x = yield from stage(model.conv, 4, x, 4)
     for lvl in range(4):
         up = getattr(model, f"upsample_{lvl}")
@@ -143,10 +143,10 @@ def _band_forward(model, canvas, idx, rank, world):
         cat = up(x.reshape(1, Hb * W, Cin), skip.reshape(1, -1, skip.shape[-1]), hw=(Hb, W))     # cat([up, skip], -1)
         x = cat.view(2 * Hb, 2 * W, -1)
         x = yield from stage(getattr(model, f"decoderlayer_{lvl}"), 5 + lvl, x, 3 - lvl)
-    conv = model.output_proj.proj[0]
     slab = yield from _halo_slab(x, rank, world)
-    y = F.conv2d(_nchw(slab), conv.weight, conv.bias, padding=(0, 1))            # [1, 3, rows, L]
-    return canvas[0, :, a0:b0, :] + y[0].to(canvas.dtype)
+    Hl, Wl, Cl = slab.shape
+    y = model.output_proj(slab.reshape(1, Hl * Wl, Cl), residual=canvas[:, :, a0:b0, :].contiguous(), hw=(Hl, Wl), pad_h=False)
+    return y[0]                                                                  # [3, rows, L] = canvas band + projection
 
 
 # ---------------------------------------------------------------------------------------------- drivers

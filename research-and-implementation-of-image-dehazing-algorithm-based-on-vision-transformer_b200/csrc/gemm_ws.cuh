@@ -722,7 +722,7 @@ cudaError_t wss_launch_bn(const GemmArgs<__nv_bfloat16>& g, const __nv_bfloat16*
 inline bool wss_supported(const GemmArgs<__nv_bfloat16>& g) {
     static const bool on = [] { const char* e = getenv("LEWIN_NO_WSS_GEMM"); return !(e && e[0] == '1'); }();
     return on && enabled() && !g.mapA && !g.a_row_scale && !g.aux && !g.mean && g.K % 64 == 0 && g.N % 128 == 0 && g.N <= 4096 &&
-           g.M >= 4 * TC_BM && (g.lda % 8) == 0 && tma::encode_fn() != nullptr;
+           (g.M >= 4 * TC_BM || g.up2) && (g.lda % 8) == 0 && tma::encode_fn() != nullptr;
 }
 // Tile width by occupancy: the widest BN whose tile count still fills the SMs.  At the deep levels of a small tile shard
 // (8-GPU config 3: 1408 tokens at the bottleneck = 11 row tiles) BN = 256 left 22-66 CTAs for 148 SMs; narrower tiles give

@@ -448,7 +448,7 @@ def probsparse_core(qkv, *, num_heads, index_sample, rpb_table=None, rpb_dense=N
 def upsample_supported(x, Cin, Cout, tokens):
     """The 2x2 / stride-2 transposed convolution runs as a token GEMM on the streamed-W tcgen05 kernel (bf16, no autograd)."""
     import os
-    return (x.is_cuda and x.dtype == torch.bfloat16 and Cin % 64 == 0 and Cout % 32 == 0 and tokens >= 512 and
+    return (x.is_cuda and x.dtype == torch.bfloat16 and Cin % 64 == 0 and Cout % 32 == 0 and tokens >= 1 and
             os.environ.get("LEWIN_NO_WS_GEMM") != "1" and os.environ.get("LEWIN_NO_WSS_GEMM") != "1" and
             os.environ.get("LEWIN_NO_UPSAMPLE_GEMM") != "1")
 
@@ -470,6 +470,65 @@ def lewin_upsample(x, weight, bias, *, B, H, W, out=None):
     ws = _workspace(lib.lewin_upsample_fwd_workspace_bytes(a, _lib.DTYPE_TAG["bf16"]), dev)
     with torch.cuda.device(dev):
         _lib.check(lib.lewin_upsample_fwd_bf16(a, ws.data_ptr(), ws.numel(), _stream()), "lewin_upsample_fwd_bf16")
+    return out
+
+
+def conv_igemm_enabled():
+    import os
+    return os.environ.get("LEWIN_NO_CONV_IGEMM") != "1"
+
+
+def downsample_supported(x, Cin, W):
+    """Downsample's 4x4 / stride-2 convolution runs as an implicit GEMM on tcgen05 (bf16, no autograd)."""
+    return (conv_igemm_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and (Cin == 32 or (Cin % 64 == 0 and Cin <= 512)) and
+            W % 16 == 0)
+
+
+def lewin_downsample(x, weight, bias, *, B, H, W, pad_h=True, out=None):
+    """Downsample.forward (My_model_1.py:606-630): x [B, H*W, Cin] bf16 tokens (may be a column slice [..., :Cin] of a wider
+    contiguous buffer) -> [B, Hout * W/2, 2*Cin] bf16, Hout = H/2 (pad_h) or H/2 - 1 (rows carry their own halo)."""
+    lib = _lib.load()
+    Cin = weight.shape[1]
+    assert x.shape[-1] == Cin and x.stride(-1) == 1 and x.stride(-2) % 8 == 0
+    ld_x = x.stride(-2)
+    assert x.numel() == B * H * W * Cin and (x.dim() < 3 or x.shape[0] == 1 or x.stride(0) == H * W * ld_x)
+    dev = x.device
+    Hout = H // 2 if pad_h else H // 2 - 1
+    if out is None:
+        out = torch.empty((B, Hout * (W // 2), 2 * Cin), dtype=x.dtype, device=dev)
+    w_, b_ = _f32c(weight), _f32c(bias)
+    a = _lib.LewinDownsampleArgs(B=B, H=H, W=W, Cin=Cin, ld_x=ld_x, ld_out=out.stride(-2), pad_h=int(bool(pad_h)), reserved=0,
+                                 x=_ptr(x), weight=_ptr(w_), bias=_ptr(b_), out=_ptr(out))
+    ws = _workspace(lib.lewin_downsample_fwd_workspace_bytes(a, _lib.DTYPE_TAG["bf16"]), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lewin_downsample_fwd_bf16(a, ws.data_ptr(), ws.numel(), _stream()), "lewin_downsample_fwd_bf16")
+    return out
+
+
+def output_proj_supported(x, Cin, Cout, W):
+    return (conv_igemm_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and Cin % 64 == 0 and Cin <= 1024 and 1 <= Cout <= 16 and
+            W % 8 == 0)
+
+
+def lewin_output_proj(x, weight, bias, *, B, H, W, residual=None, pad_h=True):
+    """OutputProj.forward (My_model_1.py:696-733): x [B, H*W, Cin] bf16 tokens -> fp32 image [B, Cout, Hout, W] (+ residual, the
+    `x + y` of Uformer.forward), Hout = H (pad_h) or H - 2."""
+    lib = _lib.load()
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    x = x.contiguous()
+    assert x.numel() == B * H * W * Cin
+    dev = x.device
+    Hout = H if pad_h else H - 2
+    out = torch.empty((B, Cout, Hout, W), dtype=torch.float32, device=dev)
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.dtype == torch.float32 and tuple(residual.shape) == tuple(out.shape)
+    w_, b_ = _f32c(weight), _f32c(bias)
+    a = _lib.LewinOutputProjArgs(B=B, H=H, W=W, Cin=Cin, Cout=Cout, ld_x=Cin, pad_h=int(bool(pad_h)), reserved=0,
+                                 x=_ptr(x), weight=_ptr(w_), bias=_ptr(b_), residual=_ptr(residual), out=_ptr(out))
+    ws = _workspace(lib.lewin_output_proj_fwd_workspace_bytes(a, _lib.DTYPE_TAG["bf16"]), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lewin_output_proj_fwd_bf16(a, ws.data_ptr(), ws.numel(), _stream()), "lewin_output_proj_fwd_bf16")
     return out
 
 

@@ -59,9 +59,18 @@ class Downsample(nn.Module):
         self.conv = nn.Sequential(nn.Conv2d(in_channel, out_channel, kernel_size=4, stride=2, padding=1))
         self.in_channel, self.out_channel = in_channel, out_channel
 
-    def forward(self, x):
+    def forward(self, x, hw=None, pad_h=True):
+        """hw: explicit (H, W) of a non-square token map; pad_h=False: the rows already carry their halo (canvas row bands)."""
         c = self.conv[0]
-        y = torch.nn.functional.conv2d(_tokens_to_nchw(x), _cl(c.weight), c.bias, stride=2, padding=1)
+        B, L, C = x.shape
+        H, W = hw if hw is not None else (int(math.sqrt(L)),) * 2
+        if not (torch.is_grad_enabled() and (x.requires_grad or c.weight.requires_grad)):
+            from . import ops
+            xb = x if x.dtype == torch.bfloat16 else (x.to(torch.bfloat16) if x.is_cuda and _autocast_bf16() else None)
+            if xb is not None and H % 2 == 0 and ops.downsample_supported(xb, C, W):
+                # bf16 inference: implicit GEMM on tcgen05 with the bias fused (lewin_downsample_fwd_bf16, SURVEY 8(f) rank 2)
+                return ops.lewin_downsample(xb, c.weight, c.bias, B=B, H=H, W=W, pad_h=pad_h)
+        y = torch.nn.functional.conv2d(_tokens_to_nchw(x, (H, W)), _cl(c.weight), c.bias, stride=2, padding=(1 if pad_h else 0, 1))
         return _nchw_to_tokens(y)
 
 
@@ -142,9 +151,22 @@ class OutputProj(nn.Module):
         self.norm = norm_layer(out_channel) if norm_layer is not None else None
         self.in_channel, self.out_channel = in_channel, out_channel
 
-    def forward(self, x):
-        x = self.proj(_tokens_to_nchw(x))
-        return self.norm(x) if self.norm is not None else x
+    def forward(self, x, residual=None, hw=None, pad_h=True):
+        """residual: optional fp32 image added to the result (the `x + y` of Uformer.forward, fused into the kernel's store);
+        hw / pad_h as Downsample.forward."""
+        c = self.proj[0]
+        B, L, C = x.shape
+        H, W = hw if hw is not None else (int(math.sqrt(L)),) * 2
+        if self.norm is None and (residual is None or residual.dtype == torch.float32) and not (
+                torch.is_grad_enabled() and (x.requires_grad or c.weight.requires_grad)):
+            from . import ops
+            xb = x if x.dtype == torch.bfloat16 else (x.to(torch.bfloat16) if x.is_cuda and _autocast_bf16() else None)
+            if xb is not None and c.stride == (1, 1) and ops.output_proj_supported(xb, C, c.out_channels, W):
+                # bf16 inference: implicit GEMM on tcgen05, bias + residual image fused (lewin_output_proj_fwd_bf16)
+                return ops.lewin_output_proj(xb, c.weight, c.bias, B=B, H=H, W=W, residual=residual, pad_h=pad_h)
+        y = torch.nn.functional.conv2d(_tokens_to_nchw(x, (H, W)), c.weight, c.bias, stride=c.stride, padding=(1 if pad_h else 0, 1))
+        y = self.norm(y) if self.norm is not None else y
+        return y if residual is None else residual + y.to(residual.dtype)
 
 
 class BasicUformerLayer(nn.Module):
@@ -279,5 +301,4 @@ class Uformer(nn.Module):
         deconv1 = self.decoderlayer_1(self.upsample_1(deconv0, conv2), mask, sl(6))
         deconv2 = self.decoderlayer_2(self.upsample_2(deconv1, conv1), mask, sl(7))
         deconv3 = self.decoderlayer_3(self.upsample_3(deconv2, conv0), mask, sl(8))
-        y = self.output_proj(deconv3)
-        return x + y.to(x.dtype)
+        return self.output_proj(deconv3, residual=x)                                   # x + y (My_model_1.py:1207)

@@ -490,7 +490,11 @@ def main():
         "config": {"workload": "config3: synthetic 1200x1600 image wrap-padded to 1664^2, 169 tiles of 128^2 sharded over "
                                f"{world} rank(s), Uformer_ProbSparse embed_dim=32 random init, tiled mode, final all_gather",
                    "tiles_per_rank_max": -(-N_TILES // world), "l2": "working set (>=354 MB per level-0 tensor) exceeds the 126 MB L2",
-                   "convs": "InputProj / Upsample run on this library's kernels (bf16); Downsample / OutputProj are stock cuDNN (outside the LeWin block)",
+                   "convs": ("all ten projections run on this library's kernels (InputProj, 4 x Downsample as implicit GEMM on tcgen05, 4 x Upsample as "
+                             "token GEMM with pixel-shuffle epilogue, OutputProj with the x + y residual fused); the encoder outputs are written straight "
+                             "into the decoder's concat buffers" if args.dtype == "bf16" else
+                             "fp32: the projections are stock cuDNN (outside the LeWin block)"),
+                   "leff": "C <= 64 levels: linear1 + GELU kernel, then ONE kernel for depthwise conv + GELU -> tcgen05.mma linear2 -> residual (h2 stays on chip); C >= 128: three kernels",
                    "attention": "C <= 64 levels: ONE fused kernel per block (LN1 -> q|k|v tcgen05.mma -> TMEM -> ProbSparse core -> out tcgen05.mma -> residual); C >= 128: three kernels",
                    "launch": "python launches" if args.no_graph else "CUDA graph replay of the per-rank tile-batch forward",
                    "lewin_compute": "3xTF32 mma.sync (fp32-grade)" if args.dtype == "f32" else

@@ -200,7 +200,10 @@ typedef struct {
     int32_t B, H, W, C, hidden;    /* hidden = 4C (mlp_ratio 4, My_model_1.py:777) */
     int32_t fused;
     int32_t save_for_backward;     /* 1: pre-activations a1, a2 are written as well */
-    int32_t reserved;
+    int32_t ld_out;                /* elements between consecutive tokens of `out` (0 = C).  > C: `out` is a column block of a
+                                    * wider buffer, e.g. the right half of the decoder's torch.cat([up, skip]) buffer
+                                    * (My_model_1.py:1189-1204), so the skip copy disappears; bf16 inference calls for which
+                                    * lewin_leff_fwd_supports_ld_out() returns 1 */
 
     const void*  y;
     void*        out;
@@ -235,6 +238,8 @@ typedef struct {
 /* Bit k set <=> the forward call will record timing slot k (LEWIN_ATTN_K_* / LEWIN_LEFF_K_*) for these arguments. */
 int lewin_attn_fwd_kernel_mask(const LewinAttnFwdArgs* a, int dtype);
 int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype);
+/* 1 if the forward call for these arguments can write `out` with a row stride ld_out > C */
+int lewin_leff_fwd_supports_ld_out(const LewinLeffFwdArgs* a, int dtype);
 
 int lewin_leff_fwd_f32 (const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 int lewin_leff_fwd_bf16(const LewinLeffFwdArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
@@ -313,11 +318,12 @@ typedef struct LewinDownsampleArgs {
 int    lewin_downsample_fwd_bf16(const LewinDownsampleArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 size_t lewin_downsample_fwd_workspace_bytes(const LewinDownsampleArgs* a, int dtype);
 
-/* OutputProj.forward, My_model_1.py:696-733 (+ the `x + y` of Uformer.forward :1207): Conv2d(Cin, Cout <= 16, kernel 3,
+/* OutputProj.forward, My_model_1.py:696-733 (+ the `x + y` of Uformer.forward :1207): Conv2d(Cin, Cout <= 8, kernel 3,
  * padding 1) from the token map to an fp32 NCHW image, bias fused (conv -> bf16, + bias -> bf16), optional residual image
- * added in fp32.  Same implicit-GEMM kernel (N padded to 16).  pad_h = 0: the caller supplies the halo rows, H - 2 rows out. */
+ * added in fp32.  One TMA halo tile per 16 x 16 pixels, the 9 taps gathered from it by ldmatrix into mma.sync (n8 tile):
+ * the map is read once.  pad_h = 0: the caller supplies the halo rows, H - 2 rows out. */
 typedef struct LewinOutputProjArgs {
-    int32_t B, H, W, Cin, Cout;    /* W % 8 == 0, Cin % 64 == 0 */
+    int32_t B, H, W, Cin, Cout;    /* Cin % 64 == 0, Cin <= 256, Cout <= 8 */
     int32_t ld_x;                  /* elements between consecutive input tokens (0 = Cin) */
     int32_t pad_h;
     int32_t reserved;

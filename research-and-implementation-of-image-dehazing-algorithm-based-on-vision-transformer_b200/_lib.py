@@ -61,7 +61,7 @@ class LewinCoreBwdArgs(C.Structure):
 class LewinLeffFwdArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("hidden", C.c_int32),
-        ("fused", C.c_int32), ("save_for_backward", C.c_int32), ("reserved", C.c_int32),
+        ("fused", C.c_int32), ("save_for_backward", C.c_int32), ("ld_out", C.c_int32),
         ("y", c_ptr), ("out", c_ptr), ("ln_w", c_ptr), ("ln_b", c_ptr),
         ("w1", c_ptr), ("b1", c_ptr), ("w_dw", c_ptr), ("b_dw", c_ptr), ("w2", c_ptr), ("b2", c_ptr),
         ("drop_scale", c_ptr),
@@ -121,7 +121,7 @@ EXPORTS = (
     "lewin_probsparse_core_fwd_f32", "lewin_probsparse_core_fwd_bf16", "lewin_probsparse_core_fwd_workspace_bytes",
     "lewin_probsparse_core_bwd_f32", "lewin_probsparse_core_bwd_bf16", "lewin_probsparse_core_bwd_workspace_bytes",
     "lewin_abi_version", "lewin_build_info", "lewin_error_string", "lewin_launch_count",
-    "lewin_attn_fwd_kernel_mask", "lewin_leff_fwd_kernel_mask",
+    "lewin_attn_fwd_kernel_mask", "lewin_leff_fwd_kernel_mask", "lewin_leff_fwd_supports_ld_out",
     "lewin_upsample_fwd_bf16", "lewin_upsample_fwd_workspace_bytes", "lewin_input_proj_fwd_bf16",
     "lewin_downsample_fwd_bf16", "lewin_downsample_fwd_workspace_bytes",
     "lewin_output_proj_fwd_bf16", "lewin_output_proj_fwd_workspace_bytes",
@@ -171,6 +171,8 @@ def load():
     lib.lewin_attn_fwd_kernel_mask.restype = C.c_int
     lib.lewin_leff_fwd_kernel_mask.argtypes = [C.POINTER(LewinLeffFwdArgs), C.c_int]
     lib.lewin_leff_fwd_kernel_mask.restype = C.c_int
+    lib.lewin_leff_fwd_supports_ld_out.argtypes = [C.POINTER(LewinLeffFwdArgs), C.c_int]
+    lib.lewin_leff_fwd_supports_ld_out.restype = C.c_int
     lib.lewin_launch_count.restype = C.c_longlong
     lib.lewin_build_info.restype = C.c_char_p
     lib.lewin_error_string.argtypes = [C.c_int]

@@ -17,7 +17,7 @@
 // The input may have a row stride larger than its channel count (the right half of a torch.cat([up, skip]) buffer).
 // Weights: bf16 image [tap][N][C] made per call by conv_prep_kernel.  Warp roles as ws::gemm_wss_kernel: one TMA thread,
 // one MMA thread, 8 epilogue warps (tcgen05.ld -> bf16 -> + bias -> bf16, the two roundings of torch's conv + bias add under
-// autocast -> coalesced token rows, or fp32 NCHW planes + the residual image for the 3-channel projection).
+// autocast -> coalesced token rows).  The 3-channel OutputProj has its own kernel below (op::outproj_mma_kernel).
 #pragma once
 #include "tc_helpers.cuh"
 #include "tma.cuh"
@@ -35,17 +35,15 @@ struct Tap { int dc, dj, dq, di; };
 
 struct Args {
     int B, Hout, Wout;
-    int N;                       // GEMM columns (Cout; 16 for the 3-channel projection)
-    int n_real;                  // real output channels
+    int N;                       // GEMM columns (Cout)
+    int n_real;                  // == N
     int px_shift;                // tile = (128 >> px_shift) rows x (1 << px_shift) columns of output pixels
     int tiles_x, tiles_y, col_tiles, tiles;
     int ntaps, nkc;
     Tap taps[16];
     const float* bias;           // [n_real]
-    __nv_bfloat16* out_tok;      // MODE 0: [B, Hout, Wout, ld_out]
+    __nv_bfloat16* out_tok;      // [B, Hout, Wout, ld_out]
     long long ld_out;
-    float* out_img;              // MODE 1: [B, n_real, Hout, Wout] fp32
-    const float* resid_img;      // MODE 1: optional image added to the result (Uformer.forward: x + y), same layout
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -57,22 +55,8 @@ __device__ __forceinline__ void load_5d(void* smem_dst, const CUtensorMap* map, 
         ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// MODE 0: bf16 token rows + bias;  MODE 1: fp32 NCHW planes (n_real <= 16 channels) + bias (+ residual image)
-template <int KCH, int BN, int MODE>
+// epilogue: bf16 token rows + bias
+template <int KCH, int BN>
 __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const Args a, const __grid_constant__ CUtensorMap amap,
                                                                 const __grid_constant__ CUtensorMap wmap, int S) {
     constexpr int A_CHUNK = 128 * KCH * 2, W_CHUNK = BN * KCH * 2, STAGE = A_CHUNK + ((W_CHUNK + 1023) / 1024) * 1024;
@@ -174,26 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const Args a, co
             tc::mbar_wait(&tfull[acc], static_cast<uint32_t>(it >> 1) & 1u);
             tc::tc_fence_after();
             const uint32_t t_addr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(acc * ACC);
-            if constexpr (MODE == 1) {
-                if (half == 0) {
-                    float v[16];
-                    tmem_ld16(t_addr, v);
-                    tc::tc_fence_before();
-                    mbar_arrive(&tempty[acc]);
-                    if (ok) {
-                        const long long plane = static_cast<long long>(a.Hout) * a.Wout;
-                        const long long o = static_cast<long long>(b) * a.n_real * plane + static_cast<long long>(gy) * a.Wout + gx;
-                        for (int c = 0; c < a.n_real; ++c) {
-                            float y = Act<__nv_bfloat16>::round(Act<__nv_bfloat16>::round(v[c]) + s_bias[c]);      // conv -> bf16, + bias -> bf16
-                            if (a.resid_img) y += a.resid_img[o + c * plane];
-                            a.out_img[o + c * plane] = y;
-                        }
-                    }
-                } else {
-                    tc::tc_fence_before();
-                    mbar_arrive(&tempty[acc]);
-                }
-            } else {
+            {
                 const long long oy = ok ? ((static_cast<long long>(b) * a.Hout + gy) * a.Wout + gx) * a.ld_out + ct * BN : -1;
                 const float* bs = s_bias + ct * BN;
                 for (int c = half; c < NCH; c += NCG) {
@@ -274,7 +239,173 @@ __global__ void conv_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     }
 }
 
-template <int KCH, int BN, int MODE>
+// ------------------------------------------------------------------------------------------------------------------
+// OutputProj (Cout <= 8 channels): the implicit GEMM above reloads every input pixel once per tap (9 boxes per tile) and
+// measured L2-bound (355 us per 1664^2 canvas).  Here the (16+2) x (16+2) x 64-channel halo tile is fetched ONCE by TMA
+// (SWIZZLE_128B, zero fill == the conv padding), and the 9 shifted views are gathered from it by ldmatrix row addresses
+// (one 128-byte row per pixel, conflict-free through the swizzle) into mma.sync.m16n8k16 A fragments; the n8 B fragments of
+// the 3 x Cin x 9 weights live in shared memory in fragment order.  HBM traffic = the map once.
+namespace op {
+constexpr int TY = 16, TX = 16, HY = TY + 2, HX = TX + 2, SLAB = 64;
+constexpr int TILE_BYTES = HY * HX * SLAB * 2;                    // 41472
+constexpr int TILE_STRIDE = (TILE_BYTES + 1023) / 1024 * 1024;    // SWIZZLE_128B destinations are 1024-byte aligned
+constexpr int THREADS = 256;
+
+struct Args {
+    int B, H, W, Cin, Cout, Hout, pad;
+    int tiles_x, tiles_y, tiles;
+    const float* weight;         // [Cout, Cin, 3, 3]
+    const float* bias;
+    const float* resid;          // [B, Cout, Hout, W] or null
+    float* out;                  // [B, Cout, Hout, W]
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(THREADS, 2) outproj_mma_kernel(const Args a, const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* tiles = base;                                              // [2][TILE_STRIDE]
+    uint2* bfrag = reinterpret_cast<uint2*>(tiles + 2 * TILE_STRIDE);         // [nslab][9 taps][4 kk][32 lanes]
+    const int nslab = a.Cin / SLAB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bfrag + nslab * 9 * 4 * 32);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+
+    for (int i = tid; i < nslab * 9 * 4 * 32; i += THREADS) {                 // B fragments: b0 = B[k = 2tq, 2tq+1][n = gq], b1 = B[k + 8][n]
+        const int l = i & 31, kk = (i >> 5) & 3, r = i >> 7, tap = r % 9, sl = r / 9;
+        const int n = l >> 2, c0 = sl * SLAB + kk * 16 + 2 * (l & 3);
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n < a.Cout) {
+            const float* wr = a.weight + static_cast<long long>(n) * a.Cin * 9 + tap;
+            w[0] = wr[(c0) * 9]; w[1] = wr[(c0 + 1) * 9]; w[2] = wr[(c0 + 8) * 9]; w[3] = wr[(c0 + 9) * 9];
+        }
+        bfrag[i] = make_uint2(tc::pack_bf16(w[0], w[1]), tc::pack_bf16(w[2], w[3]));
+    }
+    if (tid == 0) {
+        tma::prefetch_map(&xmap);
+        tma::mbar_init(&bars[0], 1);
+        tma::mbar_init(&bars[1], 1);
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int units = a.tiles * nslab;
+    auto fetch = [&](int u, int bufi) {
+        if (tid != 0) return;
+        const int t = u / nslab, sl = u - t * nslab;
+        const int tx = t % a.tiles_x, r = t / a.tiles_x, ty = r % a.tiles_y, b = r / a.tiles_y;
+        tma::mbar_expect_tx(&bars[bufi], TILE_BYTES);
+        tma::load_4d(tiles + bufi * TILE_STRIDE, &xmap, &bars[bufi], sl * SLAB, tx * TX - 1, ty * TY - a.pad, b);
+    };
+    // my unit sequence: tiles blockIdx.x, + gridDim.x, ... each with nslab slabs
+    const int my_tiles = (a.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int my_units = my_tiles * nslab;
+    auto unit_of = [&](int j) { return (static_cast<int>(blockIdx.x) + (j / nslab) * static_cast<int>(gridDim.x)) * nslab + (j % nslab); };
+    (void)units;
+    if (my_units > 0) fetch(unit_of(0), 0);
+    uint32_t phase[2] = {0u, 0u};
+    float acc[2][4];
+    const float b0v = (2 * tq < a.Cout) ? Act<__nv_bfloat16>::round(a.bias[2 * tq]) : 0.f;
+    const float b1v = (2 * tq + 1 < a.Cout) ? Act<__nv_bfloat16>::round(a.bias[2 * tq + 1]) : 0.f;
+    for (int j = 0; j < my_units; ++j) {
+        const int bufi = j & 1;
+        if (j + 1 < my_units) fetch(unit_of(j + 1), bufi ^ 1);
+        const int u = unit_of(j), t = u / nslab, sl = u - t * nslab;
+        if (sl == 0) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[m][c] = 0.f;
+        }
+        tma::mbar_wait(&bars[bufi], phase[bufi]);
+        phase[bufi] ^= 1u;
+        const uint32_t tile_u = tc::smem_u32(tiles + bufi * TILE_STRIDE);
+        const uint2* bf = bfrag + sl * (9 * 4 * 32) + lane;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                // my row address of this tap with the swizzle key folded in: chunk = 2 kk + hi, so (chunk ^ key) << 4 ==
+                // (kk << 5) ^ ((hi ^ key) << 4), and with 128-byte aligned rows the whole address is one XOR per k-step
+                uint32_t rowa[2];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int pix = (2 * warp + m + ky) * HX + (lane & 15) + kx;
+                    rowa[m] = tile_u + pix * 128 + ((((lane >> 4) ^ pix) & 7) << 4);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint2 b = bf[((ky * 3 + kx) * 4 + kk) * 32];
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        uint32_t af[4];
+                        ldsm_x4(af, rowa[m] ^ (kk << 5));
+                        mma16816(acc[m], af, b.x, b.y);
+                    }
+                }
+            }
+        if (sl == nslab - 1) {
+            const int tx = t % a.tiles_x, r = t / a.tiles_x, ty = r % a.tiles_y, b = r / a.tiles_y;
+            const long long plane = static_cast<long long>(a.Hout) * a.W;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int gy = ty * TY + 2 * warp + m;
+                if (gy >= a.Hout) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int gx = tx * TX + gq + 8 * h;
+                    if (gx >= a.W) continue;
+                    const long long o = static_cast<long long>(b) * a.Cout * plane + static_cast<long long>(gy) * a.W + gx;
+                    if (2 * tq < a.Cout) {
+                        float y = Act<__nv_bfloat16>::round(Act<__nv_bfloat16>::round(acc[m][2 * h]) + b0v);       // conv -> bf16, + bias -> bf16
+                        if (a.resid) y += a.resid[o + (2 * tq) * plane];
+                        a.out[o + (2 * tq) * plane] = y;
+                    }
+                    if (2 * tq + 1 < a.Cout) {
+                        float y = Act<__nv_bfloat16>::round(Act<__nv_bfloat16>::round(acc[m][2 * h + 1]) + b1v);
+                        if (a.resid) y += a.resid[o + (2 * tq + 1) * plane];
+                        a.out[o + (2 * tq + 1) * plane] = y;
+                    }
+                }
+            }
+        }
+        __syncthreads();                                   // every warp is done with this buffer before it is refilled
+    }
+}
+
+inline cudaError_t launch(Args a, const void* x, int ldx, int num_sms, cudaStream_t stream) {
+    a.tiles_x = (a.W + TX - 1) / TX;
+    a.tiles_y = (a.Hout + TY - 1) / TY;
+    a.tiles = a.B * a.tiles_x * a.tiles_y;
+    tma::EncodeTiledFn fn = tma::encode_fn();
+    if (!fn) return cudaErrorNotSupported;
+    CUtensorMap map{};
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.Cin), static_cast<cuuint64_t>(a.W), static_cast<cuuint64_t>(a.H), static_cast<cuuint64_t>(a.B)};
+    const cuuint64_t st[3] = {static_cast<cuuint64_t>(ldx) * 2, static_cast<cuuint64_t>(a.W) * ldx * 2, static_cast<cuuint64_t>(a.H) * a.W * ldx * 2};
+    const cuuint32_t box[4] = {SLAB, HX, HY, 1u};
+    const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+    if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorNotSupported;
+    const size_t smem = 1024 + 2 * TILE_STRIDE + static_cast<size_t>(a.Cin / SLAB) * 9 * 4 * 32 * 8 + 64;
+    cudaError_t e = cudaFuncSetAttribute(outproj_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    int grid = 2 * num_sms;
+    if (grid > a.tiles) grid = a.tiles;
+    outproj_mma_kernel<<<grid, THREADS, smem, stream>>>(a, map);
+    return cudaGetLastError();
+}
+}  // namespace op
+
+template <int KCH, int BN>
 inline cudaError_t launch_inst(Args& a, const CUtensorMap& amap, const CUtensorMap& wmap, int num_sms, cudaStream_t stream) {
     constexpr int A_CHUNK = 128 * KCH * 2, W_CHUNK = BN * KCH * 2, STAGE = A_CHUNK + ((W_CHUNK + 1023) / 1024) * 1024;
     const size_t fixed = 1024 + NEW * STG_BUF + static_cast<size_t>(a.col_tiles) * BN * 4 + (2 * 8 + 4) * 8 + 16;
@@ -282,7 +413,7 @@ inline cudaError_t launch_inst(Args& a, const CUtensorMap& amap, const CUtensorM
     if (S > 8) S = 8;
     if (S < 2) return cudaErrorInvalidConfiguration;
     const size_t smem = fixed + static_cast<size_t>(S) * STAGE;
-    auto k = conv_igemm_kernel<KCH, BN, MODE>;
+    auto k = conv_igemm_kernel<KCH, BN>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     int grid = num_sms < a.tiles ? num_sms : a.tiles;

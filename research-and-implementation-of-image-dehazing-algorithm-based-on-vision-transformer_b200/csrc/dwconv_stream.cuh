@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a,
         __nv_bfloat16* op = a.out + obase;
         __nv_bfloat16* pp = a.preact ? a.preact + obase : nullptr;
         const __nv_bfloat16* ap = BWD ? a.aux + obase : nullptr;
-        const int rows_here = a.H - ty * TY;               // < TY only in the last tile row of a map whose height is not a multiple of 16
+        const int rows_here = (tx * TX + px < a.W) ? a.H - ty * TY : 0;   // < TY in the last tile row of a map whose height is not a
+                                                           // multiple of 16; 0 for the columns beyond a map narrower than the tile (W = 8)
 #pragma unroll
         for (int y = 0; y < TY; ++y) {
             if (y >= rows_here) break;                     // (the rows below the map were zero-filled: nothing to compute or store)
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a,
 
 inline bool supported(int H, int W, int Ch) {
     static const bool on = [] { const char* e = getenv("LEWIN_NO_STREAM_DWCONV"); return !(e && e[0] == '1'); }();
-    return on && H >= 1 && W % TX == 0 && Ch % SLAB == 0;      // any height: the last tile row is cut at the map's edge
+    return on && H >= 1 && W >= TX && W % 8 == 0 && Ch % SLAB == 0;   // any height; widths that are not a multiple of the tile are cut at the edge (an 8-wide map would waste half of every tile: first-generation kernel)
 }
 
 template <bool BWD>
@@ -222,7 +223,7 @@ inline cudaError_t launch_mode(const __nv_bfloat16* x, __nv_bfloat16* out, __nv_
     Args a{};
     a.x = x; a.out = out; a.preact = preact; a.aux = aux; a.w = w; a.bias = bias;
     a.B = B; a.H = H; a.W = W; a.Ch = Ch;
-    a.tiles_x = W / TX; a.tiles_y = (H + TY - 1) / TY;
+    a.tiles_x = (W + TX - 1) / TX; a.tiles_y = (H + TY - 1) / TY;
     a.spatial_tiles = B * a.tiles_x * a.tiles_y;
     a.total_tiles = a.spatial_tiles * (Ch / SLAB);
     int grid = 2 * num_sms;

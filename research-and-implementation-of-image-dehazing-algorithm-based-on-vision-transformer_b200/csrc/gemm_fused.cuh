@@ -38,7 +38,8 @@ struct GemmArgs {
     int mapA, mapY;       // 1: row m is in window order and maps to a token through `map`
     WinMap map;
     // residual epilogue
-    const T* R;           // indexed like Y
+    const T* R;           // residual rows, indexed like Y with row stride ldr (gemm_ws.cuh kernels; 0 = ldy)
+    long long ldr;
     const float* drop_scale;   // [B] or null (EPI_BIAS_RESID: scales the GEMM result per sample)
     int tokens_per_image;
     // backward helpers

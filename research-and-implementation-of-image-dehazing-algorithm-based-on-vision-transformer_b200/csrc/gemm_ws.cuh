@@ -83,7 +83,7 @@ template <int NCG>
 __device__ __forceinline__ void resid_prefetch(const GemmArgs<__nv_bfloat16>& g, uint32_t tile, int col0, unsigned char* sbuf, int lg, int lane) {
     const uint32_t m = tile * TC_BM + lg * 32 + lane;
     long long oy = -1;
-    if (m < g.M) oy = static_cast<long long>(g.mapY ? g.map.token32(m) : m) * g.ldy;
+    if (m < g.M) oy = static_cast<long long>(g.mapY ? g.map.token32(m) : m) * (g.ldr ? g.ldr : g.ldy);
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
         const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
@@ -112,12 +112,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
             __syncwarp();
         }
         const uint32_t m = tile * TC_BM + lg * 32 + lane;
-        long long oy = -1;
+        long long oy = -1, orr = -1;                  // element offsets of my output row and my residual row
         float sc = 1.f;
         uint32_t up_t00 = 0;                          // up2: output token of (di, dj) = (0, 0)
         if (m < g.M) {
             const uint32_t ry = g.mapY ? g.map.token32(m) : m;
             oy = static_cast<long long>(ry) * g.ldy;
+            orr = static_cast<long long>(ry) * (g.ldr ? g.ldr : g.ldy);
             if (EPI == EPI_BIAS_RESID && g.drop_scale) sc = g.drop_scale[ry / static_cast<uint32_t>(g.tokens_per_image)];
             if (g.up2) {
                 const uint32_t hw = static_cast<uint32_t>(g.up_H) * g.up_W;
@@ -135,7 +136,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
-                    const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                    const long long o = __shfl_sync(0xffffffffu, orr, rl);
                     if (o >= 0) cp_async16(my_stg + q * STG_BUF + rl * STG_ROW + cc * 16, g.R + o + n0 + c * 32 + cc * 8);
                 }
             }
@@ -172,7 +173,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs<__nv_bfloat16>& g, 
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
-                        const long long o = __shfl_sync(0xffffffffu, oy, rl);
+                        const long long o = __shfl_sync(0xffffffffu, orr, rl);
                         if (o >= 0)
                             *reinterpret_cast<uint4*>(sb + rl * STG_ROW + cc * 16) =
                                 *reinterpret_cast<const uint4*>(g.R + o + n0 + c * 32 + cc * 8);

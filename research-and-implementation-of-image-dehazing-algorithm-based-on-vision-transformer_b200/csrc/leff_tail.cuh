@@ -50,6 +50,7 @@ struct Args {
     const float* drop_scale;     // [B] or null
     const uint16_t* gelu_tab2;   // device address of the 8192-entry table (common.cuh)
     int B, H, W;
+    int ld_out;                  // elements between consecutive output tokens (>= C; the right half of a concat buffer)
     int tiles_x, tiles_y, tiles;
 };
 
@@ -246,14 +247,14 @@ __global__ void __launch_bounds__(THREADS, 1) leff_tail_kernel(const Args a, con
         const int cnt0 = count_of(0), cnt1 = count_of(1), total = cnt0 + cnt1;
         unsigned char* my_stg = stg + warp * 2 * NCH * STG_BUF;
         const int r = lg * 32 + lane, py = r >> 4, px = r & 15;
-        auto row_off = [&](int j, float* sc) -> long long {          // element offset of my row of item j (or -1), DropPath scale
+        auto row_off = [&](int j, float* sc) -> long long {          // token index of my row of item j (or -1), DropPath scale
             const int t = j & 1, k = j >> 1;
             int b, ty, tx;
             decode(static_cast<int>(blockIdx.x) * TEAMS + t + k * TEAMS * G, b, ty, tx);
             const int gy = ty * TY + py;
             if (sc) *sc = a.drop_scale ? a.drop_scale[b] : 1.f;
             if (gy >= a.H) return -1;
-            return ((static_cast<long long>(b) * a.H + gy) * a.W + tx * TX + px) * C;
+            return (static_cast<long long>(b) * a.H + gy) * a.W + tx * TX + px;
         };
         auto prefetch = [&](int j) {                                 // residual rows of item j -> staging set j & 1
             const long long oy = row_off(j, nullptr);
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, 1) leff_tail_kernel(const Args a, con
                 for (int jj = 0; jj < 4; ++jj) {
                     const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
                     const long long o = __shfl_sync(0xffffffffu, oy, rl);
-                    if (o >= 0) cp_async16(set + c * STG_BUF + rl * STG_ROW + cc * 16, a.resid + o + c * 32 + cc * 8);
+                    if (o >= 0) cp_async16(set + c * STG_BUF + rl * STG_ROW + cc * 16, a.resid + o * C + c * 32 + cc * 8);
                 }
         };
         if (total > 0) prefetch(0);
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) leff_tail_kernel(const Args a, con
                     const int i = lane + 32 * jj, rl = i >> 2, cc = i & 3;
                     const uint4 val = *reinterpret_cast<const uint4*>(sb + rl * STG_ROW + cc * 16);
                     const long long o = __shfl_sync(0xffffffffu, oy, rl);
-                    if (o >= 0) *reinterpret_cast<uint4*>(a.out + o + c * 32 + cc * 8) = val;
+                    if (o >= 0) *reinterpret_cast<uint4*>(a.out + o * a.ld_out + c * 32 + cc * 8) = val;
                 }
             }
             __syncwarp();                                            // staging set reusable (prefetch of item j + 2)

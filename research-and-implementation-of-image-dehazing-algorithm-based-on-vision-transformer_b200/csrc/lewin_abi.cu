@@ -332,6 +332,7 @@ int check_leff(const LewinLeffFwdArgs* a) {
     if (a->save_for_backward && (!a->a1 || !a->a2)) return LEWIN_E_NULL;
     if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->hidden <= 0) return LEWIN_E_SHAPE;
     if (a->C % 32 || a->hidden % 32) return LEWIN_E_SHAPE;
+    if (a->ld_out != 0 && (a->ld_out < a->C || a->ld_out % 8)) return LEWIN_E_SHAPE;
     const void* ps[] = {a->y, a->out, a->ln_w, a->ln_b, a->w1, a->b1, a->w_dw, a->b_dw, a->w2, a->b2, a->h1, a->h2, a->a1, a->a2,
                         a->w1_bf16, a->w2_bf16};
     for (const void* p : ps)
@@ -361,6 +362,18 @@ inline LeffPlan plan_leff(const LewinLeffFwdArgs* a, bool bf) {
     return p;
 }
 
+// `out` with a row stride > C: the fused tail and the warp-specialised / streamed-W linear2 epilogues address the output and
+// the residual rows separately; the first-generation kernels do not
+inline bool leff_ld_out_ok(const LewinLeffFwdArgs* a, const LeffPlan& p) {
+    if (a->ld_out == 0 || a->ld_out == a->C) return true;
+    if (!a->fused || a->save_for_backward) return false;
+    if (p.tail || p.ws_gemm) return true;
+    if (!p.async_gemm) return false;
+    GemmArgs<__nv_bfloat16> g{};                 // the linear2 GEMM as leff_fwd builds it
+    g.lda = a->hidden; g.M = static_cast<long long>(a->B) * a->H * a->W; g.N = a->C; g.K = a->hidden;
+    return ws::wss_supported(g);
+}
+
 template <typename T>
 int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (int rc = check_leff(a)) return rc;
@@ -378,6 +391,8 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
 
     const KTimer kt{a->timing, stream};
     const LeffPlan plan = plan_leff(a, Act<T>::kIsBf16);
+    if (!leff_ld_out_ok(a, plan)) return LEWIN_E_SHAPE;
+    const long long ldo = a->ld_out > 0 ? a->ld_out : a->C;
     if constexpr (Act<T>::kIsBf16) CK(launch_gelu_tab_init(stream));     // idempotent 8 KB table (common.cuh)
     bool async_gemm = false;
     __nv_bfloat16* xhat = nullptr; __nv_bfloat16* w1b = nullptr; __nv_bfloat16* w2b = nullptr;
@@ -455,7 +470,7 @@ int leff_fwd(const LewinLeffFwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         GemmArgs<T> g{};
         g.A = static_cast<const T*>(a->h2); g.lda = Ch;
         g.Wt = a->w2; g.bias = a->b2;
-        g.Y = static_cast<T*>(a->out); g.ldy = C;
+        g.Y = static_cast<T*>(a->out); g.ldy = ldo; g.ldr = C;
         g.M = tokens; g.N = C; g.K = Ch;
         g.tokens_per_image = a->H * a->W;
         kt.begin(LEWIN_LEFF_K_FC2);
@@ -637,6 +652,12 @@ int lewin_leff_fwd_kernel_mask(const LewinLeffFwdArgs* a, int dtype) {
     const LeffPlan p = plan_leff(a, dtype == LEWIN_DTYPE_BF16);
     if (p.tail) return (1 << LEWIN_LEFF_K_FC1) | (1 << LEWIN_LEFF_K_TAIL);
     return (p.ln_stats ? 1 : 0) | 0xE;
+}
+int lewin_leff_fwd_supports_ld_out(const LewinLeffFwdArgs* a, int dtype) {
+    if (!a || check_leff(a) != 0) return 0;
+    LewinLeffFwdArgs b = *a;
+    if (b.ld_out == 0 || b.ld_out == b.C) b.ld_out = b.C + 8;      // ask about a strided output
+    return leff_ld_out_ok(&b, plan_leff(&b, dtype == LEWIN_DTYPE_BF16)) ? 1 : 0;
 }
 int lewin_leff_fwd_f32(const LewinLeffFwdArgs* a, void* ws, size_t n, lewin_stream_t s) {
     return leff_fwd<float>(a, ws, n, reinterpret_cast<cudaStream_t>(s));

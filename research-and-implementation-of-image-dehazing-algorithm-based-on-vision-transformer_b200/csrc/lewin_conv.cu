@@ -85,55 +85,30 @@ int lewin_downsample_fwd_bf16(const LewinDownsampleArgs* a, void* ws, size_t ws_
                                       static_cast<unsigned long long>(a->H) * a->W * ld2};
     CUtensorMap amap{}, wmap{};
     if (!cv::make_5d(&amap, a->x, dims, st, KCH, 8, 16, KCH == 64) || !cv::make_w2d(&wmap, wb, 16ll * N, Cin, BN, KCH)) return LEWIN_E_SHAPE;
-    if (KCH == 32) { CK((cv::launch_inst<32, 64, 0>(k, amap, wmap, sms, stream))); }
-    else if (BN == 128) { CK((cv::launch_inst<64, 128, 0>(k, amap, wmap, sms, stream))); }
-    else { CK((cv::launch_inst<64, 256, 0>(k, amap, wmap, sms, stream))); }
+    if (KCH == 32) { CK((cv::launch_inst<32, 64>(k, amap, wmap, sms, stream))); }
+    else if (BN == 128) { CK((cv::launch_inst<64, 128>(k, amap, wmap, sms, stream))); }
+    else { CK((cv::launch_inst<64, 256>(k, amap, wmap, sms, stream))); }
     return 0;
 }
 
-size_t lewin_output_proj_fwd_workspace_bytes(const LewinOutputProjArgs* a, int) {
-    return a ? align_up(static_cast<size_t>(9) * 16 * a->Cin * 2, 256) : 0;
-}
+size_t lewin_output_proj_fwd_workspace_bytes(const LewinOutputProjArgs*, int) { return 0; }
 
-int lewin_output_proj_fwd_bf16(const LewinOutputProjArgs* a, void* ws, size_t ws_bytes, lewin_stream_t s) {
+int lewin_output_proj_fwd_bf16(const LewinOutputProjArgs* a, void*, size_t, lewin_stream_t s) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(s);
     if (!a || !a->x || !a->weight || !a->bias || !a->out) return LEWIN_E_NULL;
     const int Cin = a->Cin;
     const int ldx = a->ld_x > 0 ? a->ld_x : Cin;
-    if (a->B <= 0 || a->H < 3 || a->W < 8 || a->W % 8 || Cin % 64 || Cin > 1024 || a->Cout < 1 || a->Cout > 16 || ldx < Cin || ldx % 8)
+    if (a->B <= 0 || a->H < 3 || a->W < 1 || Cin % 64 || Cin > 256 || a->Cout < 1 || a->Cout > 8 || ldx < Cin || ldx % 8)
         return LEWIN_E_SHAPE;
     if (!aligned16(a->x)) return LEWIN_E_ALIGN;
     int sms = 0;
     if (int rc = device_sms(&sms)) return rc;
-    if (!ws || ws_bytes < lewin_output_proj_fwd_workspace_bytes(a, LEWIN_DTYPE_BF16)) return LEWIN_E_WORKSPACE;
-    if (!aligned16(ws)) return LEWIN_E_ALIGN;
-    __nv_bfloat16* wb = static_cast<__nv_bfloat16*>(ws);
-    CK(prep(a->weight, wb, a->Cout, 16, Cin, 9, stream));
-
-    const int pad = a->pad_h ? 1 : 0;
-    cv::Args k{};
-    k.B = a->B; k.Hout = pad ? a->H : a->H - 2; k.Wout = a->W;
-    k.N = 16; k.n_real = a->Cout;
-    k.px_shift = (a->W % 16 == 0) ? 4 : 3;
-    const int PX = 1 << k.px_shift, PY = 128 >> k.px_shift;
-    k.tiles_x = a->W / PX; k.tiles_y = (k.Hout + PY - 1) / PY; k.col_tiles = 1;
-    k.tiles = a->B * k.tiles_x * k.tiles_y;
-    k.ntaps = 9; k.nkc = Cin / 64;
-    for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx) {
-            cv::Tap& t = k.taps[ky * 3 + kx];
-            t.dc = 0; t.dj = kx - 1; t.dq = 0; t.di = ky - pad;
-        }
-    k.bias = a->bias;
-    k.out_img = a->out; k.resid_img = a->residual;
-    const unsigned long long ld2 = static_cast<unsigned long long>(ldx) * 2;
-    const unsigned long long dims[5] = {static_cast<unsigned long long>(Cin), static_cast<unsigned long long>(a->W), 1ull,
-                                        static_cast<unsigned long long>(a->H), static_cast<unsigned long long>(a->B)};
-    const unsigned long long st[4] = {ld2, static_cast<unsigned long long>(a->W) * ld2, static_cast<unsigned long long>(a->W) * ld2,
-                                      static_cast<unsigned long long>(a->H) * a->W * ld2};
-    CUtensorMap amap{}, wmap{};
-    if (!cv::make_5d(&amap, a->x, dims, st, 64, PX, PY, true) || !cv::make_w2d(&wmap, wb, 9ll * 16, Cin, 16, 64)) return LEWIN_E_SHAPE;
-    CK((cv::launch_inst<64, 16, 1>(k, amap, wmap, sms, stream)));
+    cv::op::Args k{};
+    k.B = a->B; k.H = a->H; k.W = a->W; k.Cin = Cin; k.Cout = a->Cout;
+    k.pad = a->pad_h ? 1 : 0;
+    k.Hout = k.pad ? a->H : a->H - 2;
+    k.weight = a->weight; k.bias = a->bias; k.resid = a->residual; k.out = a->out;
+    CK(cv::op::launch(k, a->x, ldx, sms, stream));
     return 0;
 }
 

@@ -18,6 +18,7 @@ int leff_tail_launch(const LewinLeffFwdArgs* a, const uint16_t* gelu_tab2, int n
     k.drop_scale = a->drop_scale;
     k.gelu_tab2 = gelu_tab2;
     k.B = a->B; k.H = a->H; k.W = a->W;
+    k.ld_out = a->ld_out > 0 ? a->ld_out : a->C;
     return static_cast<int>(lt::launch(a->C, k, num_sms, stream));
 }
 

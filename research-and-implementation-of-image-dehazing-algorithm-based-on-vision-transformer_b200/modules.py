@@ -283,7 +283,7 @@ def dense_shift_mask(H, W, win_size, shift, device, dtype=torch.float32):
     return d.masked_fill(d != 0, -100.0).masked_fill(d == 0, 0.0).to(dtype)
 
 
-def lewin_block_forward(blk, x, mask=None, index_sample=None):
+def lewin_block_forward(blk, x, mask=None, index_sample=None, out=None):
     """LeWinTransformerBlock.forward (My_model_1.py:785-875) on the sm_100a ops.
 
     ``blk`` is any module with the reference attribute layout (norm1, attn.ProbSpare.*, attn.
@@ -322,7 +322,7 @@ def lewin_block_forward(blk, x, mask=None, index_sample=None):
     return ops.lewin_leff(
         y, B=B, H=H, W=W, ln_w=blk.norm2.weight, ln_b=blk.norm2.bias,
         w1=mlp.linear1[0].weight, b1=mlp.linear1[0].bias, w_dw=mlp.dwconv[0].weight, b_dw=mlp.dwconv[0].bias,
-        w2=mlp.linear2[0].weight, b2=mlp.linear2[0].bias, drop_scale=s1, fused=True)
+        w2=mlp.linear2[0].weight, b2=mlp.linear2[0].bias, drop_scale=s1, fused=True, out=out)
 
 
 def _cat_qkv(ps):
@@ -377,5 +377,7 @@ class LeWinTransformerBlock(nn.Module):
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "
                 f"win_size={self.win_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
 
-    def forward(self, x, mask=None, index_sample=None):
-        return lewin_block_forward(self, x, mask, index_sample)
+    def forward(self, x, mask=None, index_sample=None, out=None):
+        """out: optional destination view for the block's result (see ops.lewin_leff); the returned tensor is `out` when the
+        call could use it."""
+        return lewin_block_forward(self, x, mask, index_sample, out=out)

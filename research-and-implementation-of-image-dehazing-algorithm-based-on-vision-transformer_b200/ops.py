@@ -290,7 +290,7 @@ class _AttnFn(torch.autograd.Function):
 
 class _LeffFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom):
+    def forward(ctx, y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom, out_view=None):
         B, H, W, fused, need_grad = geom
         lib = _lib.load()
         dt = _dtype_tag(y)
@@ -307,13 +307,17 @@ class _LeffFn(torch.autograd.Function):
         a2 = torch.empty_like(h1) if need_grad else None
         ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_ = [_f32c(t) for t in (ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale)]
         a = _lib.LewinLeffFwdArgs(
-            B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=int(need_grad), reserved=0,
+            B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=int(need_grad), ld_out=0,
             y=_ptr(y), out=_ptr(out), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w1=_ptr(w1_), b1=_ptr(b1_),
             w_dw=_ptr(wdw_), b_dw=_ptr(bdw_), w2=_ptr(w2_), b2=_ptr(b2_), drop_scale=_ptr(ds_),
             h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
         if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:
             w1_b, w2_b = _bf16_image(w1_), _bf16_image(w2_)
             a.w1_bf16, a.w2_bf16 = _ptr(w1_b), _ptr(w2_b)
+        if out_view is not None and not need_grad and lib.lewin_leff_fwd_supports_ld_out(a, _lib.DTYPE_TAG[dt]):
+            # the caller's column block of a wider buffer (the right half of the decoder's concat buffer): written in place
+            out = out_view
+            a.out, a.ld_out = _ptr(out), out.stride(-2)
         mask = lib.lewin_leff_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
         if not (mask >> 4 & 1):       # LEWIN_LEFF_K_TAIL clear: the three-kernel pipeline writes h2 = GELU(dwconv(h1))
             h2 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
@@ -345,7 +349,7 @@ class _LeffFn(torch.autograd.Function):
         dy = torch.empty_like(y)
         d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2 = _zero_grads((ln_w, ln_b, w1, b1, wdw, bdw, w2, b2), dev)
         fwd = _lib.LewinLeffFwdArgs(
-            B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=1, reserved=0,
+            B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=1, ld_out=0,
             y=_ptr(y), out=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w1=_ptr(w1), b1=_ptr(b1),
             w_dw=_ptr(wdw), b_dw=_ptr(bdw), w2=_ptr(w2), b2=_ptr(b2), drop_scale=_ptr(ds),
             h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
@@ -356,7 +360,7 @@ class _LeffFn(torch.autograd.Function):
         fn = getattr(lib, f"lewin_leff_bwd_{dt}")
         with torch.cuda.device(dev):
             _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_leff_bwd_{dt}")
-        return (dy, d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2, None, None)
+        return (dy, d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2, None, None, None)
 
 
 def lewin_attn(x, *, B, H, W, num_heads, shift, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out,
@@ -375,12 +379,20 @@ def lewin_attn(x, *, B, H, W, num_heads, shift, ln_w, ln_b, w_qkv, b_qkv, w_out,
     return (y, top) if return_top else y
 
 
-def lewin_leff(y, *, B, H, W, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale=None, fused=True):
-    """LeFF half of a LeWin block (fused=True: out = y + s * LeFF(LN2(y)); fused=False: out = LeFF(y))."""
+def lewin_leff(y, *, B, H, W, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale=None, fused=True, out=None):
+    """LeFF half of a LeWin block (fused=True: out = y + s * LeFF(LN2(y)); fused=False: out = LeFF(y)).
+    out: optional destination view shaped like y whose token stride may exceed C (a column block of a wider buffer);
+    used - and returned - when the call is inference and the library can address it (otherwise a new tensor is returned)."""
     need = torch.is_grad_enabled() and any(
         isinstance(t, torch.Tensor) and t.requires_grad for t in (y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2))
     geom = (int(B), int(H), int(W), bool(fused), need)
-    return _LeffFn.apply(y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom)
+    if out is not None:
+        ok = (out.shape == y.shape and out.dtype == y.dtype and out.device == y.device and out.stride(-1) == 1 and
+              out.stride(-2) % 8 == 0 and out.data_ptr() % 16 == 0 and
+              (out.dim() < 3 or out.shape[0] == 1 or out.stride(0) == out.shape[1] * out.stride(1)))
+        if not ok:
+            out = None
+    return _LeffFn.apply(y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom, out)
 
 
 class _CoreFn(torch.autograd.Function):
@@ -506,8 +518,7 @@ def lewin_downsample(x, weight, bias, *, B, H, W, pad_h=True, out=None):
 
 
 def output_proj_supported(x, Cin, Cout, W):
-    return (conv_igemm_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and Cin % 64 == 0 and Cin <= 1024 and 1 <= Cout <= 16 and
-            W % 8 == 0)
+    return (conv_igemm_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and Cin % 64 == 0 and Cin <= 256 and 1 <= Cout <= 8)
 
 
 def lewin_output_proj(x, weight, bias, *, B, H, W, residual=None, pad_h=True):

@@ -96,9 +96,10 @@ class Upsample(nn.Module):
             return False
         return xb
 
-    def forward(self, x, skip=None, hw=None):
+    def forward(self, x, skip=None, hw=None, cat_buf=None):
         """``skip`` given: returns torch.cat([up(x), skip], -1) (My_model_1.py:1189-1204) with the up half written in place.
-        hw: explicit (H, W) of a non-square token map (canvas row bands); default: square, as the reference assumes."""
+        hw: explicit (H, W) of a non-square token map (canvas row bands); default: square, as the reference assumes.
+        cat_buf: a [B, 4L, Cout + Cskip] buffer whose right half IS ``skip`` (the encoder wrote its output there): no copy."""
         d = self.deconv[0]
         xb = self._gemm_path(x)
         if xb is not False:
@@ -108,9 +109,12 @@ class Upsample(nn.Module):
             if skip is None:
                 return ops.lewin_upsample(xb, d.weight, d.bias, B=B, H=H, W=W)
             C = self.out_channel
-            buf = torch.empty((B, 4 * L, C + skip.shape[-1]), dtype=xb.dtype, device=x.device)
+            in_place = (cat_buf is not None and cat_buf.dtype == xb.dtype and tuple(cat_buf.shape) == (B, 4 * L, C + skip.shape[-1]) and
+                        cat_buf.is_contiguous() and skip.data_ptr() == cat_buf[..., C:].data_ptr() and skip.stride(-2) == cat_buf.stride(-2))
+            buf = cat_buf if in_place else torch.empty((B, 4 * L, C + skip.shape[-1]), dtype=xb.dtype, device=x.device)
             ops.lewin_upsample(xb, d.weight, d.bias, B=B, H=H, W=W, out=buf)
-            buf[..., C:] = skip
+            if not in_place:
+                buf[..., C:] = skip
             return buf
         y = torch.nn.functional.conv_transpose2d(_tokens_to_nchw(x, hw), _cl(d.weight), d.bias, stride=2)
         y = _nchw_to_tokens(y)
@@ -187,9 +191,11 @@ class BasicUformerLayer(nn.Module):
                                   se_layer=se_layer)
             for i in range(depth)])
 
-    def forward(self, x, mask=None, index_samples=None):
+    def forward(self, x, mask=None, index_samples=None, out=None):
+        """out: optional destination view for the layer's result (handed to the last block)."""
+        last = len(self.blocks) - 1
         for i, blk in enumerate(self.blocks):
-            x = blk(x, mask, None if index_samples is None else index_samples[i])
+            x = blk(x, mask, None if index_samples is None else index_samples[i], **({"out": out} if (out is not None and i == last) else {}))
         return x
 
 
@@ -288,17 +294,24 @@ class Uformer(nn.Module):
         sl = lambda i: idx[offs[i]:offs[i + 1]]
 
         y = self.pos_drop(self.input_proj(x))
-        conv0 = self.encoderlayer_0(y, mask, sl(0))
+        # bf16 inference: every encoder level writes its result straight into the right half of the buffer the decoder's
+        # torch.cat([up, skip], -1) (My_model_1.py:1189-1204) would build, so the four skip copies disappear
+        cats = [None] * 4
+        if y.is_cuda and y.dtype == torch.bfloat16 and not torch.is_grad_enabled():
+            B, L0, E = y.shape
+            cats = [torch.empty((B, L0 >> (2 * i), 2 * (E << i)), dtype=y.dtype, device=y.device) for i in range(4)]
+        dst = lambda i: {} if cats[i] is None else {"out": cats[i][..., cats[i].shape[-1] // 2:]}
+        conv0 = self.encoderlayer_0(y, mask, sl(0), **dst(0))
         pool0 = self.dowsample_0(conv0)
-        conv1 = self.encoderlayer_1(pool0, mask, sl(1))
+        conv1 = self.encoderlayer_1(pool0, mask, sl(1), **dst(1))
         pool1 = self.dowsample_1(conv1)
-        conv2 = self.encoderlayer_2(pool1, mask, sl(2))
+        conv2 = self.encoderlayer_2(pool1, mask, sl(2), **dst(2))
         pool2 = self.dowsample_2(conv2)
-        conv3 = self.encoderlayer_3(pool2, mask, sl(3))
+        conv3 = self.encoderlayer_3(pool2, mask, sl(3), **dst(3))
         pool3 = self.dowsample_3(conv3)
         conv4 = self.conv(pool3, mask, sl(4))
-        deconv0 = self.decoderlayer_0(self.upsample_0(conv4, conv3), mask, sl(5))      # cat([up, skip], -1)
-        deconv1 = self.decoderlayer_1(self.upsample_1(deconv0, conv2), mask, sl(6))
-        deconv2 = self.decoderlayer_2(self.upsample_2(deconv1, conv1), mask, sl(7))
-        deconv3 = self.decoderlayer_3(self.upsample_3(deconv2, conv0), mask, sl(8))
+        deconv0 = self.decoderlayer_0(self.upsample_0(conv4, conv3, cat_buf=cats[3]), mask, sl(5))      # cat([up, skip], -1)
+        deconv1 = self.decoderlayer_1(self.upsample_1(deconv0, conv2, cat_buf=cats[2]), mask, sl(6))
+        deconv2 = self.decoderlayer_2(self.upsample_2(deconv1, conv1, cat_buf=cats[1]), mask, sl(7))
+        deconv3 = self.decoderlayer_3(self.upsample_3(deconv2, conv0, cat_buf=cats[0]), mask, sl(8))
         return self.output_proj(deconv3, residual=x)                                   # x + y (My_model_1.py:1207)

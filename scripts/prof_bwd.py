@@ -21,4 +21,13 @@ for _ in range(3): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=90))
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        a = agg[ev.name[:100]]
+        a[0] += 1; a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+tot = sum(v[1] for v in agg.values())
+print(f"C={C} map {hw}x{hw} batch {B}: forward + backward kernel time {tot:.1f} us, {sum(v[0] for v in agg.values())} kernels")
+for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
+    print(f"{us:9.1f} us  x{n:3d}  {name}")

@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_helpers.cuh"
+#include "gemm_t32_api.h"
 #include "gemm_fused.cuh"
 
 #include <cstdlib>
@@ -786,6 +787,9 @@ template <typename T, int EPI>
 cudaError_t launch_gemm_any(const GemmArgs<T>& g, cudaStream_t stream) {
     if constexpr (Act<T>::kIsBf16) {
         if (tcgen05_enabled()) return launch_gemm_tc<EPI>(g, stream);
+    } else {
+        // fp32: 3xTF32 on tcgen05 (gemm_t32.cuh) for the forward shapes; mma.sync kernel otherwise
+        if (gemm_t32_supported(g, EPI)) return gemm_t32_launch(g, EPI, stream);
     }
     return launch_gemm<T, EPI>(g, stream);
 }

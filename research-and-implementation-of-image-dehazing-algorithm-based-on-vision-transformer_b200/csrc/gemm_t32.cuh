@@ -10,14 +10,14 @@
 // a_lo*b_lo term is below 2^-22 relative), so the result is fp32-grade -- the top-u selection downstream of q|k|v is
 // precision-critical (SURVEY finding 9) -- at three tensor-core passes instead of one.
 //
-// One persistent CTA per SM, 17 warps, every hand-over an mbarrier:
-//   * 8 producer warps : raw fp32 k-chunks (32 floats = one 128-byte swizzle row) of A (gathered through roll +
-//                        window_partition) and of W arrive by cp.async, S - 1 stages ahead, directly at their swizzled
-//                        position in the stage's hi tiles; once landed, the thread that issued a 16-byte piece applies
-//                        LayerNorm (A only), splits it and writes hi in place and lo into the stage's lo tile;
+// One persistent CTA per SM, 21 warps (25 under the GELU epilogue), every hand-over an mbarrier:
+//   * 16 producer warps: fp32 k-chunks (32 floats = one 128-byte swizzle row) of A (gathered through roll +
+//                        window_partition) and of W go global -> registers (two k-chunks per thread in flight) ->
+//                        LayerNorm (A only) -> hi / lo split -> the stage's four swizzled tiles; the only wait on the
+//                        tensor core is for the stage it consumed S k-chunks ago;
 //   * 1 MMA thread     : per k-chunk 4 k8-steps x 3 tcgen05.mma kind::tf32 (M = 128, N = BN) into one of two TMEM
 //                        accumulator stages; tcgen05.commit frees the stage / publishes the accumulator;
-//   * 8 epilogue warps : tcgen05.ld (thread == row) -> bias -> erf GELU | DropPath * residual -> per-warp staging tile ->
+//   * 4 / 8 epilogue warps: tcgen05.ld (thread == row) -> bias -> erf GELU | DropPath * residual -> per-warp staging tile ->
 //                        row-cooperative coalesced 16-byte stores through window_reverse + un-roll.
 // Tiles are walked column-fastest so the CTAs that work on one row band share its A rows in L2.
 #pragma once
@@ -29,11 +29,9 @@ namespace t32 {
 
 constexpr int BM = 128;
 constexpr int KC = 32;                        // floats per k-chunk: 128-byte rows (SWIZZLE_128B)
-constexpr int NEW = 8, NPW = 8;               // epilogue / producer warps
-constexpr int MMA_WARP = NEW;
-constexpr int WARPS = NEW + 1 + NPW;
-constexpr int THREADS = WARPS * 32;           // 544
-constexpr int PTHREADS = NPW * 32;
+// warp roles: [0, NEW) epilogue (warp % 4 == TMEM lane group, warp / 4 == column group), NEW: MMA issuer, then NPW producers.
+// The producers are bound by the latency of their own instruction stream, not by issue slots, so there are 16 of them;
+// 4 epilogue warps keep up everywhere except under the erf GELU, which gets 8.
 constexpr int A_TILE = BM * 128;              // bytes of one [128 x 32] fp32 tile
 constexpr int STG_ROW = 80;                   // staging row: 16 fp32 columns (64 B) + 16 B pad (conflict-free 16-byte accesses)
 constexpr int STG_BUF = 32 * STG_ROW;
@@ -56,32 +54,55 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PTHREADS) : "memory"); }
+template <int PT> __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory"); }
+// 32 lanes x 16 columns of fp32: thread i of the warp gets lane (lane_base + i), columns [col, col + 16)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 // byte offset of 16-byte piece `c` (0..7) of row `r` in a SWIZZLE_128B tile of 128-byte rows
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
 
+// hi = x rounded to tf32 (nearest, ties away: the same value cvt.rna.tf32.f32 gives for finite x, in two integer
+// instructions -- the cvt expands to four with its NaN / Inf select); lo = x - hi is exact in fp32 and is handed to the
+// tensor core as it is: kind::tf32 reads the upper 19 bits of the 32-bit container, and lo's 12 significant bits lose at
+// most 2^-22 of x to that truncation.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-    hi.x = __uint_as_float(f2tf32(v.x)); hi.y = __uint_as_float(f2tf32(v.y));
-    hi.z = __uint_as_float(f2tf32(v.z)); hi.w = __uint_as_float(f2tf32(v.w));
-    lo.x = __uint_as_float(f2tf32(v.x - hi.x)); lo.y = __uint_as_float(f2tf32(v.y - hi.y));
-    lo.z = __uint_as_float(f2tf32(v.z - hi.z)); lo.w = __uint_as_float(f2tf32(v.w - hi.w));
+    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
 }
 
 template <int BN>
 constexpr size_t stage_bytes() { return 2 * A_TILE + 2 * static_cast<size_t>(BN) * 128; }
-constexpr size_t fixed_smem() {
+constexpr size_t fixed_smem(int NEW) {
     return 1024 /*align*/ + NEW * STG_BUF + NTAB * BM * 12 + (2 * 8 + 4) * 8 + 16;
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(THREADS, 1) gemm_t32_kernel(const GemmArgs<float> g, int row_tiles, int col_tiles, int nkc, int S) {
+template <int BN, int EPI, int NEW, int NPW>
+__global__ void __launch_bounds__((NEW + 1 + NPW) * 32, 1) gemm_t32_kernel(const GemmArgs<float> g, int row_tiles, int col_tiles, int nkc, int S) {
+    constexpr int MMA_WARP = NEW;
+    constexpr int PTHREADS = NPW * 32;
+    constexpr int RPP = PTHREADS / 8;              // rows per producer pass (8 lanes x 16 B = one 128-byte row piece)
+    constexpr int AP = BM / RPP;                   // producer passes over the A rows
+    constexpr int WP = (BN + RPP - 1) / RPP;       // ... over the W rows (the last pass may be partial: BN = 96, RPP = 64)
+    constexpr int NCG = NEW / 4;                   // epilogue column groups
+    static_assert(NEW % 4 == 0 && BM % RPP == 0, "warp split");
     constexpr int W_TILE = BN * 128;
     constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;
     constexpr int ACC = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;     // TMEM columns per accumulator stage
     constexpr int TMEM_COLS = 2 * ACC;
     constexpr int NCH = BN / 32;                   // 32-column epilogue chunks
-    constexpr int WP = BN / 32;                    // producer passes over the W rows
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                (static_cast<uint32_t>(BM >> 4) << 24);            // D = f32, A = B = tf32, K-major
     static_assert(BN % 32 == 0 && BN <= 256, "tile width");
@@ -105,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_t32_kernel(const GemmArgs<flo
     const bool has_ln = g.mean != nullptr;
 
     if (tid == 0) {
-        for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], PTHREADS); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&full[i], NPW); tc::mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], NEW * 32); }
         tc::fence_barrier_init();
     }
@@ -117,97 +138,98 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_t32_kernel(const GemmArgs<flo
 
     if (warp > MMA_WARP) {
         // ============================================================ producers
-        const int pt = tid - (MMA_WARP + 1) * 32;      // 0 .. 255
-        const int row_l = pt >> 3, ch = pt & 7;        // 8 lanes x 16 B = one 128-byte row piece; 32 rows per pass
-        const uint32_t ring_u = tc::smem_u32(ring);
-        const int DD = S - 1 < 3 ? S - 1 : 3;          // stages issued ahead
+        // global -> registers (a two-stage register ring keeps the next two k-chunks of this thread in flight) -> LayerNorm
+        // (A) -> hi / lo split -> swizzled tiles.  No shared-memory round trip of the raw data, and the only wait on the
+        // tensor core is for the stage it consumed S k-chunks ago.
+        const int pt = tid - (MMA_WARP + 1) * 32;
+        const int row_l = pt >> 3, ch = pt & 7;        // 8 lanes x 16 B = one 128-byte row piece; RPP rows per pass
+        const uint32_t sw0 = swz(row_l, ch);           // pass p adds p * RPP * 128 bytes, the XOR term depends on row_l & 7 only
         const int total = my_tiles * nkc;
-        // issue side
-        int i_it = 0, i_kc = 0, i_s = 0;
-        uint32_t i_ph = 0;
-        auto issue = [&](int j) {
-            if (j < total) {
-                tc::mbar_wait(&empty[i_s], i_ph ^ 1u);
-                const int t = static_cast<int>(blockIdx.x) + i_it * static_cast<int>(gridDim.x);
-                const int rt = t / col_tiles, ct = t - rt * col_tiles;
-                const int tb = (i_it & (NTAB - 1)) * BM;
-                if (i_kc == 0) {                       // per-tile row table: gathered token index + LayerNorm statistics
-                    if (pt < BM) {
-                        const uint32_t m = static_cast<uint32_t>(rt) * BM + pt;
-                        uint32_t tok = 0xFFFFFFFFu;
-                        float mu = 0.f, rs = 1.f;
-                        if (m < g.M) {
-                            tok = g.mapA ? g.map.token32(m) : m;
-                            if (has_ln) { mu = g.mean[tok]; rs = g.rstd[tok]; }
-                        }
-                        t_tok[tb + pt] = tok; t_mu[tb + pt] = mu; t_rs[tb + pt] = rs;
+        float4 abuf[2][AP], wbuf[2][WP];
+        int l_it = 0, l_kc = 0;
+        auto load = [&](float4 (&a)[AP], float4 (&w)[WP], int j) {
+            if (j >= total) return;
+            const int t = static_cast<int>(blockIdx.x) + l_it * static_cast<int>(gridDim.x);
+            const int rt = t / col_tiles, ct = t - rt * col_tiles;
+            const int tb = (l_it & (NTAB - 1)) * BM;
+            if (l_kc == 0) {                           // per-tile row table: gathered token index + LayerNorm statistics
+                if (pt < BM) {
+                    const uint32_t m = static_cast<uint32_t>(rt) * BM + pt;
+                    uint32_t tok = 0xFFFFFFFFu;
+                    float mu = 0.f, rs = 1.f;
+                    if (m < g.M) {
+                        tok = g.mapA ? g.map.token32(m) : m;
+                        if (has_ln) { mu = g.mean[tok]; rs = g.rstd[tok]; }
                     }
-                    producer_bar();
+                    t_tok[tb + pt] = tok; t_mu[tb + pt] = mu; t_rs[tb + pt] = rs;
                 }
-                const uint32_t st_u = ring_u + static_cast<uint32_t>(i_s) * STAGE;
-                const int k0 = i_kc * KC + ch * 4;
-#pragma unroll
-                for (int p = 0; p < BM / 32; ++p) {
-                    const int r = p * 32 + row_l;
-                    const uint32_t tok = t_tok[tb + r];
-                    const bool ok = tok != 0xFFFFFFFFu;
-                    cp_async16_z(st_u + swz(r, ch), ok ? g.A + static_cast<long long>(tok) * g.lda + k0 : g.A, ok);
-                }
-                const float* wsrc = g.Wt + static_cast<long long>(ct * BN + row_l) * g.K + k0;
-#pragma unroll
-                for (int p = 0; p < WP; ++p)
-                    cp_async16_z(st_u + 2 * A_TILE + swz(p * 32 + row_l, ch), wsrc + static_cast<long long>(p) * 32 * g.K, true);
-                if (++i_kc == nkc) { i_kc = 0; ++i_it; }
-                if (++i_s == S) { i_s = 0; i_ph ^= 1u; }
+                producer_bar<PTHREADS>();
             }
-            cp_async_commit();
+            const int k0 = l_kc * KC + ch * 4;
+#pragma unroll
+            for (int p = 0; p < AP; ++p) {
+                const uint32_t tok = t_tok[tb + p * RPP + row_l];
+                a[p] = tok != 0xFFFFFFFFu ? __ldg(reinterpret_cast<const float4*>(g.A + static_cast<long long>(tok) * g.lda + k0))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float* wsrc = g.Wt + static_cast<long long>(ct * BN + row_l) * g.K + k0;
+#pragma unroll
+            for (int p = 0; p < WP; ++p)
+                if (BN % RPP == 0 || p * RPP + row_l < BN) w[p] = __ldg(reinterpret_cast<const float4*>(wsrc + static_cast<long long>(p) * RPP * g.K));
+            if (++l_kc == nkc) { l_kc = 0; ++l_it; }
         };
-        // convert side
         int c_it = 0, c_kc = 0, c_s = 0;
-        auto convert = [&]() {
-            unsigned char* st = ring + static_cast<size_t>(c_s) * STAGE;
+        uint32_t c_ph = 0;
+        auto convert = [&](const float4 (&a)[AP], const float4 (&w)[WP]) {
+            tc::mbar_wait(&empty[c_s], c_ph ^ 1u);     // the MMAs that read this stage S k-chunks ago have retired
+            unsigned char* st = ring + static_cast<size_t>(c_s) * STAGE + sw0;
             const int tb = (c_it & (NTAB - 1)) * BM;
             float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_ln) {
-                gam = *reinterpret_cast<const float4*>(g.ln_w + c_kc * KC + ch * 4);
-                bet = *reinterpret_cast<const float4*>(g.ln_b + c_kc * KC + ch * 4);
+                gam = __ldg(reinterpret_cast<const float4*>(g.ln_w + c_kc * KC + ch * 4));
+                bet = __ldg(reinterpret_cast<const float4*>(g.ln_b + c_kc * KC + ch * 4));
             }
+            float mu[AP], rs[AP];                      // read before the first store (the compiler cannot move a shared load above one)
 #pragma unroll
-            for (int p = 0; p < BM / 32; ++p) {
-                const int r = p * 32 + row_l;
-                unsigned char* a = st + swz(r, ch);
-                float4 v = *reinterpret_cast<const float4*>(a);
+            for (int p = 0; p < AP; ++p) { mu[p] = t_mu[tb + p * RPP + row_l]; rs[p] = t_rs[tb + p * RPP + row_l]; }
+#pragma unroll
+            for (int p = 0; p < AP; ++p) {
+                float4 v = a[p];
                 if (has_ln) {
-                    const float mu = t_mu[tb + r], rs = t_rs[tb + r];
-                    v.x = (v.x - mu) * rs * gam.x + bet.x;
-                    v.y = (v.y - mu) * rs * gam.y + bet.y;
-                    v.z = (v.z - mu) * rs * gam.z + bet.z;
-                    v.w = (v.w - mu) * rs * gam.w + bet.w;
+                    v.x = (v.x - mu[p]) * rs[p] * gam.x + bet.x;
+                    v.y = (v.y - mu[p]) * rs[p] * gam.y + bet.y;
+                    v.z = (v.z - mu[p]) * rs[p] * gam.z + bet.z;
+                    v.w = (v.w - mu[p]) * rs[p] * gam.w + bet.w;
                 }
                 float4 hi, lo;
                 split4(v, hi, lo);
-                *reinterpret_cast<float4*>(a) = hi;
-                *reinterpret_cast<float4*>(a + A_TILE) = lo;
+                *reinterpret_cast<float4*>(st + p * (RPP * 128)) = hi;
+                *reinterpret_cast<float4*>(st + p * (RPP * 128) + A_TILE) = lo;
             }
 #pragma unroll
             for (int p = 0; p < WP; ++p) {
-                unsigned char* w = st + 2 * A_TILE + swz(p * 32 + row_l, ch);
-                const float4 v = *reinterpret_cast<const float4*>(w);
-                float4 hi, lo;
-                split4(v, hi, lo);
-                *reinterpret_cast<float4*>(w) = hi;
-                *reinterpret_cast<float4*>(w + W_TILE) = lo;
+                if (BN % RPP == 0 || p * RPP + row_l < BN) {
+                    float4 hi, lo;
+                    split4(w[p], hi, lo);
+                    *reinterpret_cast<float4*>(st + 2 * A_TILE + p * (RPP * 128)) = hi;
+                    *reinterpret_cast<float4*>(st + 2 * A_TILE + p * (RPP * 128) + W_TILE) = lo;
+                }
             }
-            tc::fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor core
-            mbar_arrive(&full[c_s]);
+            tc::fence_proxy_async();                   // my generic-proxy smem writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[c_s]);
             if (++c_kc == nkc) { c_kc = 0; ++c_it; }
-            if (++c_s == S) c_s = 0;
+            if (++c_s == S) { c_s = 0; c_ph ^= 1u; }
         };
-        for (int d = 0; d < DD; ++d) issue(d);
-        for (int j = 0; j < total; ++j) {
-            issue(j + DD);
-            if (DD == 3) cp_async_wait<3>(); else if (DD == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-            convert();
+        load(abuf[0], wbuf[0], 0);
+        load(abuf[1], wbuf[1], 1);
+        for (int j = 0; j < total; j += 2) {
+            convert(abuf[0], wbuf[0]);
+            load(abuf[0], wbuf[0], j + 2);
+            if (j + 1 < total) {
+                convert(abuf[1], wbuf[1]);
+                load(abuf[1], wbuf[1], j + 3);
+            }
         }
     } else if (warp == MMA_WARP) {
         // ============================================================ MMA issuer (one thread)
@@ -289,40 +311,37 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_t32_kernel(const GemmArgs<flo
             tc::mbar_wait(&tfull[acc], aph);
             tc::tc_fence_after();
             const uint32_t t_addr = tmem_d + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(acc * ACC);
-            for (int c = half; c < NCH; c += NEW / 4) {
-                float v[32];
-                tc::tmem_ld32(t_addr + c * 32, v);
-                if (c + NEW / 4 >= NCH) {              // last chunk of this warp is in registers: hand the accumulator back
-                    tc::tc_fence_before();
-                    mbar_arrive(&tempty[acc]);
-                }
-                const int col0 = n0 + c * 32;
-                if (g.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
-                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                    }
-                }
-                if (EPI == EPI_BIAS_GELU && g.Y2) {    // training: pre-activation copy
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(srow + j * 4) = make_float4(v[hh * 16 + j], v[hh * 16 + j + 1], v[hh * 16 + j + 2], v[hh * 16 + j + 3]);
-                        flush16(g.Y2, col0 + hh * 16, false);
-                    }
-                }
-                if (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                }
+            for (int c = half; c < NCH; c += NCG) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
+                    float v[16];
+                    tmem_ld16(t_addr + c * 32 + hh * 16, v);
+                    if (c + NCG >= NCH && hh == 1) {   // last piece of this warp is in registers: hand the accumulator back
+                        tc::tc_fence_before();
+                        mbar_arrive(&tempty[acc]);
+                    }
+                    const int col = n0 + c * 32 + hh * 16;
+                    if (g.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    if (EPI == EPI_BIAS_GELU && g.Y2) {    // training: pre-activation copy
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(srow + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        flush16(g.Y2, col, false);
+                    }
+                    if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+                    }
 #pragma unroll
                     for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(srow + j * 4) = make_float4(v[hh * 16 + j], v[hh * 16 + j + 1], v[hh * 16 + j + 2], v[hh * 16 + j + 3]);
-                    flush16(g.Y, col0 + hh * 16, EPI == EPI_BIAS_RESID);
+                        *reinterpret_cast<float4*>(srow + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    flush16(g.Y, col, EPI == EPI_BIAS_RESID);
                 }
             }
             if (half >= NCH) {                         // this warp owns no chunk (BN == 32): still hand back
@@ -340,20 +359,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_t32_kernel(const GemmArgs<flo
 
 template <int BN, int EPI>
 cudaError_t launch_bn(const GemmArgs<float>& g, int num_sms, cudaStream_t stream) {
+    constexpr int NEW = EPI == EPI_BIAS_GELU ? 8 : 4, NPW = 16;
     constexpr size_t STAGE = stage_bytes<BN>();
-    constexpr size_t fixed = fixed_smem();
+    constexpr size_t fixed = fixed_smem(NEW);
     static_assert(fixed + 2 * STAGE <= SMEM_MAX, "two stages must fit");
     int S = static_cast<int>((SMEM_MAX - fixed) / STAGE);
     if (S > 8) S = 8;
     const size_t smem = fixed + static_cast<size_t>(S) * STAGE;
-    auto k = gemm_t32_kernel<BN, EPI>;
+    auto k = gemm_t32_kernel<BN, EPI, NEW, NPW>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const int row_tiles = static_cast<int>((g.M + BM - 1) / BM);
     const int col_tiles = g.N / BN;
     int grid = num_sms;
     if (grid > row_tiles * col_tiles) grid = row_tiles * col_tiles;
-    k<<<grid, THREADS, smem, stream>>>(g, row_tiles, col_tiles, g.K / KC, S);
+    k<<<grid, (NEW + 1 + NPW) * 32, smem, stream>>>(g, row_tiles, col_tiles, g.K / KC, S);
     return cudaGetLastError();
 }
 
@@ -371,6 +391,9 @@ inline bool supported(const GemmArgs<float>& g) {
 
 template <int EPI>
 cudaError_t launch(const GemmArgs<float>& g, int num_sms, cudaStream_t stream) {
+    static const bool wide = [] { const char* e = getenv("LEWIN_T32_NO_BN256"); return !(e && e[0] == '1'); }();
+    // tensor-bound shapes (long K): 256-wide tiles halve the A traffic per FLOP; two 96 KB stages
+    if (wide && g.N % 256 == 0 && g.K >= 128 && (g.M + BM - 1) / BM * (g.N / 256) >= num_sms) return launch_bn<256, EPI>(g, num_sms, stream);
     if (g.N % 128 == 0) return launch_bn<128, EPI>(g, num_sms, stream);
     if (g.N % 96 == 0) return launch_bn<96, EPI>(g, num_sms, stream);
     if (g.N % 64 == 0) return launch_bn<64, EPI>(g, num_sms, stream);

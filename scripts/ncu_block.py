@@ -1,6 +1,6 @@
 """One LeWin block forward at a benchmark shape, for `ncu --set full` captures of its kernels (GPU box):
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 -o gpurun_out/<name> python scripts/ncu_block.py dec3
-Levels as bench.LEVELS (name, C, map); the batch is the 169-tile step of config 3 unless given."""
+Levels as bench.LEVELS (name, C, map); the batch is the 169-tile step of config 3 unless given; third argument f32 = fp32 path."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,7 +14,8 @@ C, hw = LEVELS[name]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 blk = L.LeWinTransformerBlock(dim=C, input_resolution=(hw, hw), num_heads=C // 32, win_size=8, shift_size=4 if hw > 8 else 0).to(dev).eval()
-x = torch.randn(B, hw * hw, C, device=dev, dtype=torch.bfloat16)
+DT = torch.float32 if (len(sys.argv) > 3 and sys.argv[3] == "f32") else torch.bfloat16
+x = torch.randn(B, hw * hw, C, device=dev, dtype=DT)
 idx = torch.randint(64, (64, 25))
 with torch.no_grad():
     for _ in range(2):

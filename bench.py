@@ -427,8 +427,8 @@ def main():
             ent = tj.get("kernels", {}).get(dom["kernel"])
             if ent and tj.get("dtype") == args.dtype:
                 traffic = ent.get("dram_bytes_per_launch")
-                traffic_note = (f"ncu DRAM bytes of ONE launch ({tj.get('shape')}; {ent.get('ncu_kernel')}); algorithmic bytes of that "
-                                f"launch = {ent.get('algorithmic_bytes_per_launch')}; {tj.get('source')}")
+                traffic_note = (f"ncu DRAM bytes of ONE launch ({tj.get('shape')}; {ent.get('ncu_kernel')}; capture: {ent.get('capture')}); "
+                                f"algorithmic bytes of that launch = {ent.get('algorithmic_bytes_per_launch')}; {tj.get('source')}")
         except Exception:
             pass
     roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],

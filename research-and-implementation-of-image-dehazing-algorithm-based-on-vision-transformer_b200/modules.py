@@ -73,12 +73,28 @@ def _use_rpb():
     return bool(_options.is_relative_position_bias)
 
 
+_FP16_NOTE = [False]
+
+
 def _act_dtype(x):
-    """bf16 under torch.autocast(cuda, bfloat16), else the input dtype."""
-    if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+    """bf16 under torch.autocast(cuda, bfloat16), else the input dtype.
+
+    Under the reference's own fp16 autocast (My_train.py:224: ``torch.cuda.amp.autocast()`` + NativeScaler) the LeWin ops also
+    compute in bf16 - the library has no fp16 kernels - and hand bf16 activations to the surrounding autocast ops, which
+    cast them as they cast any other input.  bf16 has fp32's exponent range, so the scaler's loss scaling is unnecessary for
+    these ops but harmless; the training script runs unchanged (tests/test_gpu_bf16.py::test_fp16_autocast_runs_on_bf16_kernels)."""
+    if torch.is_autocast_enabled():
+        adt = torch.get_autocast_dtype("cuda")
+        if adt == torch.bfloat16:
+            return torch.bfloat16
+        if adt == torch.float16:
+            if not _FP16_NOTE[0]:
+                _FP16_NOTE[0] = True
+                import warnings
+                warnings.warn("lewin_b200: fp16 autocast requested; the LeWin ops compute in bf16 (no fp16 kernels)", stacklevel=3)
+            return torch.bfloat16
+    if x.dtype == torch.float16:
         return torch.bfloat16
-    if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.float16:
-        raise RuntimeError("lewin_b200: fp16 autocast is not supported; use torch.autocast('cuda', torch.bfloat16)")
     return x.dtype
 
 

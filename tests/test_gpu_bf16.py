@@ -144,6 +144,39 @@ def test_autocast_routes_to_bf16_kernels_and_trains():
         assert cos > 0.9, (k, cos)
 
 
+def test_fp16_autocast_runs_on_bf16_kernels():
+    """My_train.py:224 wraps the forward in torch.cuda.amp.autocast() (fp16) with a loss scaler.  The library has no fp16
+    kernels: under fp16 autocast the LeWin ops compute in bf16, so the reference's training step runs unchanged - the result
+    equals the bf16-autocast result bit for bit, and a GradScaler step produces finite, unscaled fp32 gradients."""
+    import warnings
+    import lewin_b200 as L
+    rng = np.random.default_rng(5)
+    C, nH, hw, B, shift = 64, 2, 16, 2, 4
+    p = O.random_block_params(C, nH, rng, std=0.1)
+    dev = torch.device("cuda:0")
+    blk = _mk(C, nH, shift, p, dev)
+    x = torch.from_numpy(rng.standard_normal((B, hw * hw, C)).astype(np.float32)).to(dev)
+    idx = torch.from_numpy(rng.integers(0, 64, size=(64, 25)).astype(np.int64))
+    with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+        ref = blk(x, None, idx)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.no_grad(), torch.autocast("cuda", torch.float16):
+            out = blk(x, None, idx)
+        assert out.dtype == torch.bfloat16 and torch.equal(out, ref)
+        scaler = torch.amp.GradScaler("cuda")
+        opt = torch.optim.SGD(blk.parameters(), lr=0.0)
+        blk.zero_grad()
+        with torch.autocast("cuda", torch.float16):
+            loss = blk(x, None, idx).float().pow(2).mean()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+    live = [v.grad for v in blk.parameters() if v.grad is not None]
+    assert len(live) == 19 and all(torch.isfinite(g).all() for g in live)
+    L.modules._FP16_NOTE[0] = False
+
+
 def test_gelu_table_edges_through_leff():
     """The branch-free GELU pair lookup defers its range test; inputs outside the 2^-28 <= |x| < 16 table (exact zeros,
     huge and tiny values) must take the exact slow path.  A LeFF whose depthwise kernel is zero makes the dwconv output

@@ -16,6 +16,7 @@
 #include "probsparse_core.cuh"
 #include "wgrad_args.cuh"
 #include "wgrad_bf16.cuh"
+#include "wgrad_tc_api.h"
 #include "core_bwd_args.cuh"
 #include "probsparse_core_bwd_v2.cuh"
 
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradArgs<T> g)
 template <typename T>
 cudaError_t launch_wgrad(WgradArgs<T> g, int num_sms, cudaStream_t st) {
     if constexpr (Act<T>::kIsBf16) {
+        if (wgrad_tc_supported(g)) return wgrad_tc_launch(g, num_sms, st);   // plain operands, C >= 128: tcgen05 (wgrad_tc.cuh)
         if (wg2::supported(g)) return wg2::launch(g, num_sms, st);      // pipelined bf16 path (wgrad_bf16.cuh)
     }
     const int tile = (g.N % 64 == 0 && g.K % 64 == 0) ? 64 : 32;
@@ -861,7 +863,7 @@ __global__ void __launch_bounds__(256) scale_gather_rows_kernel(const __nv_bfloa
 
 template <typename T>
 inline cudaError_t launch_dgrad_gemm(const GemmArgs<T>& g, __nv_bfloat16* wT_bf16, int sms, cudaStream_t st,
-                                     __nv_bfloat16* a_scratch = nullptr) {
+                                     __nv_bfloat16* a_scratch = nullptr, bool* scratch_filled = nullptr) {
     if constexpr (Act<T>::kIsBf16) {
         static const bool on = [] { const char* e = getenv("LEWIN_NO_WSS_DGRAD"); return !(e && e[0] == '1'); }();
         static const int min_dim = [] { const char* e = getenv("LEWIN_WSS_DGRAD_MIN"); return e ? atoi(e) : 128; }();
@@ -878,6 +880,7 @@ inline cudaError_t launch_dgrad_gemm(const GemmArgs<T>& g, __nv_bfloat16* wT_bf1
                                                                                          g.mapA, g.map, g.tokens_per_image);
                     cudaError_t e = cudaGetLastError();
                     if (e != cudaSuccess) return e;
+                    if (scratch_filled) *scratch_filled = true;   // [M, K] rows with the gather / DropPath scale applied
                 }
                 cudaError_t e = launch_convert_w(g.Wt, wT_bf16, static_cast<long long>(g.N) * g.K, st);
                 if (e != cudaSuccess) return e;
@@ -928,13 +931,14 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     BCK(launch_transpose(f.w_qkv, wqkvT, 3 * C, C, st));
     if (!f.windowed) BCK(launch_ln_stats<T>(x, tokens, C, mean, rstd, st));
 
+    bool dy_s_filled = false;
     {   // dctx = (s_b * gather(dy)) . W_out
         GemmArgs<T> g{};
         g.A = dy; g.lda = C; g.Wt = woT; g.bias = nullptr;
         g.Y = dctx; g.ldy = C; g.M = tokens; g.N = C; g.K = C;
         g.mapA = mapped; g.mapY = 0; g.map = map; g.tokens_per_image = tpi;
         g.a_row_scale = f.windowed ? nullptr : f.drop_scale;
-        BCK(launch_dgrad_gemm<T>(g, woT_b, sms, st, dy_s));
+        BCK(launch_dgrad_gemm<T>(g, woT_b, sms, st, dy_s, &dy_s_filled));
     }
     {   // dW_out += do^T ctx ; db_out += colsum(do)
         WgradArgs<T> w{};
@@ -942,6 +946,11 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         w.dW = a->d_w_out; w.db = a->d_b_out; w.M = tokens; w.N = C; w.K = C;
         w.mapDY = mapped; w.mapX = 0; w.map = map; w.tokens_per_image = tpi;
         w.dy_row_scale = f.windowed ? nullptr : f.drop_scale;
+        if constexpr (Act<T>::kIsBf16) {
+            if (dy_s_filled) {       // the data-gradient GEMM left the window-ordered, DropPath-scaled rows behind: plain operand
+                w.dY = dy_s; w.mapDY = 0; w.dy_row_scale = nullptr;
+            }
+        }
         BCK(launch_wgrad<T>(w, sms, st));
     }
     {   // core backward -> dq | dk | dv
@@ -962,6 +971,16 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         w.dW = a->d_w_qkv; w.db = a->d_b_qkv; w.M = tokens; w.N = 3 * C; w.K = C;
         w.mapDY = 0; w.mapX = mapped; w.map = map; w.tokens_per_image = tpi;
         if (!f.windowed) { w.mean = mean; w.rstd = rstd; w.ln_w = f.ln_w; w.ln_b = f.ln_b; }
+        if constexpr (Act<T>::kIsBf16) {
+            // C >= 128: LN1 + roll + window_partition in one C-sized pass (into dxh, which is free until the next GEMM writes
+            // it), so the weight gradient streams plain rows into the tcgen05 kernel
+            WgradArgs<T> v = w;
+            v.X = dxh; v.mapX = 0; v.mean = nullptr; v.rstd = nullptr; v.ln_w = nullptr; v.ln_b = nullptr;
+            if (!f.windowed && C >= 128 && wgrad_tc_supported(v)) {
+                BCK(launch_ln_apply(x, dxh, f.ln_w, f.ln_b, tokens, C, 1, map, st));
+                w = v;
+            }
+        }
         BCK(launch_wgrad<T>(w, sms, st));
     }
     {   // d(LN1 out) = dqkv . W_qkv, scattered back to token order (window_reverse + un-roll)
@@ -1022,19 +1041,23 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     BCK(launch_transpose(f.w1, w1T, Ch, C, st));      // [Ch, C] -> [C, Ch]  (N = C, K = Ch)
     if (f.fused) BCK(launch_ln_stats<T>(y, tokens, C, mean, rstd, st));
 
-    {   // dW2 += (s*dout)^T h2 ; db2 += colsum(s*dout)
-        WgradArgs<T> w{};
-        w.dY = dout; w.lddy = C; w.X = static_cast<const T*>(f.h2); w.ldx = Ch;
-        w.dW = a->d_w2; w.db = a->d_b2; w.M = tokens; w.N = C; w.K = Ch;
-        w.tokens_per_image = tpi; w.dy_row_scale = dscale;
-        BCK(launch_wgrad<T>(w, sms, st));
-    }
+    bool dout_s_filled = false;
     {   // dh2 = (s*dout) . W2
         GemmArgs<T> g{};
         g.A = dout; g.lda = C; g.Wt = w2T; g.bias = nullptr;
         g.Y = dh2; g.ldy = Ch; g.M = tokens; g.N = Ch; g.K = C;
         g.tokens_per_image = tpi; g.a_row_scale = dscale;
-        BCK(launch_dgrad_gemm<T>(g, w2T_b, sms, st, dout_s));
+        BCK(launch_dgrad_gemm<T>(g, w2T_b, sms, st, dout_s, &dout_s_filled));
+    }
+    {   // dW2 += (s*dout)^T h2 ; db2 += colsum(s*dout)
+        WgradArgs<T> w{};
+        w.dY = dout; w.lddy = C; w.X = static_cast<const T*>(f.h2); w.ldx = Ch;
+        w.dW = a->d_w2; w.db = a->d_b2; w.M = tokens; w.N = C; w.K = Ch;
+        w.tokens_per_image = tpi; w.dy_row_scale = dscale;
+        if constexpr (Act<T>::kIsBf16) {
+            if (dout_s_filled) { w.dY = dout_s; w.dy_row_scale = nullptr; }   // DropPath-scaled rows left by the GEMM above
+        }
+        BCK(launch_wgrad<T>(w, sms, st));
     }
     // depthwise conv backward: da1 = conv^T(dh2 * gelu'(a2)) * gelu'(a1); dWdw, dbdw
     {
@@ -1054,6 +1077,16 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         w.dW = a->d_w1; w.db = a->d_b1; w.M = tokens; w.N = Ch; w.K = C;
         w.tokens_per_image = tpi;
         if (f.fused) { w.mean = mean; w.rstd = rstd; w.ln_w = f.ln_w; w.ln_b = f.ln_b; }
+        if constexpr (Act<T>::kIsBf16) {
+            // C >= 128: LN2(y) in one C-sized pass (into dz, free until the next GEMM writes it) -> plain operand for the tcgen05 kernel
+            WgradArgs<T> v = w;
+            v.X = dz; v.mean = nullptr; v.rstd = nullptr; v.ln_w = nullptr; v.ln_b = nullptr;
+            if (f.fused && C >= 128 && wgrad_tc_supported(v)) {
+                WinMap nomap{};
+                BCK(launch_ln_apply(y, dz, f.ln_w, f.ln_b, tokens, C, 0, nomap, st));
+                w = v;
+            }
+        }
         BCK(launch_wgrad<T>(w, sms, st));
     }
     {   // dz = da1 . W1

@@ -229,15 +229,21 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dz, c
     for (long long row0 = warp_global * RPW; row0 < rows; row0 += nwarps * RPW) {
         const long long row = row0 + sub;
         const bool live = row < rows;
-        float xv[MAXV][EPL], dv[MAXV][EPL];
+        float xv[MAXV][EPL], dv[MAXV][EPL], rv[MAXV][EPL];   // all three operands are requested up front: one memory latency per row
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int k = (gl + i * G) * EPL;
-            if (live && k < C) { load(x + row * C + k, xv[i]); load(dz + row * C + k, dv[i]); }
-            else {
+            if (live && k < C) {
+                load(x + row * C + k, xv[i]); load(dz + row * C + k, dv[i]);
+                if (dres) load(dres + row * C + k, rv[i]);
+                else {
 #pragma unroll
-                for (int j = 0; j < EPL; ++j) { xv[i][j] = 0.f; dv[i][j] = 0.f; }
+                    for (int j = 0; j < EPL; ++j) rv[i][j] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) { xv[i][j] = 0.f; dv[i][j] = 0.f; rv[i][j] = 0.f; }
             }
 #pragma unroll
             for (int j = 0; j < EPL; ++j) s += xv[i][j];
@@ -276,13 +282,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dz, c
             const int k = (gl + i * G) * EPL;
             if (live && k < C) {
                 float r[EPL];
-                if (dres) load(dres + row * C + k, r);
-                else {
 #pragma unroll
-                    for (int j = 0; j < EPL; ++j) r[j] = 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < EPL; ++j) r[j] += rs * (dv[i][j] - s1 - xv[i][j] * s2);
+                for (int j = 0; j < EPL; ++j) r[j] = rv[i][j] + rs * (dv[i][j] - s1 - xv[i][j] * s2);
 #pragma unroll
                 for (int j = 0; j < EPL; j += 4) st4(dx + row * C + k + j, make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]));
             }
@@ -861,6 +862,16 @@ __global__ void __launch_bounds__(256) scale_gather_rows_kernel(const __nv_bfloa
     }
 }
 
+// window-ordered / DropPath-scaled copy of [M, K] bf16 rows (one pass), so that a TMA-fed kernel can stream plain rows
+inline cudaError_t launch_scale_gather_rows(const __nv_bfloat16* A, __nv_bfloat16* out, const float* row_scale, long long M, int K,
+                                            long long lda, int mapA, const WinMap& map, int tokens_per_image, int sms, cudaStream_t st) {
+    const long long chunks = M * (K / 8);
+    long long grid = (chunks + 255) / 256;
+    if (grid > static_cast<long long>(sms) * 16) grid = static_cast<long long>(sms) * 16;
+    scale_gather_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(A, out, row_scale, M, K, lda, mapA, map, tokens_per_image);
+    return cudaGetLastError();
+}
+
 template <typename T>
 inline cudaError_t launch_dgrad_gemm(const GemmArgs<T>& g, __nv_bfloat16* wT_bf16, int sms, cudaStream_t st,
                                      __nv_bfloat16* a_scratch = nullptr, bool* scratch_filled = nullptr) {
@@ -947,8 +958,13 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         w.mapDY = mapped; w.mapX = 0; w.map = map; w.tokens_per_image = tpi;
         w.dy_row_scale = f.windowed ? nullptr : f.drop_scale;
         if constexpr (Act<T>::kIsBf16) {
-            if (dy_s_filled) {       // the data-gradient GEMM left the window-ordered, DropPath-scaled rows behind: plain operand
-                w.dY = dy_s; w.mapDY = 0; w.dy_row_scale = nullptr;
+            // plain operand for the tcgen05 kernel: the window-ordered, DropPath-scaled rows (left behind by the data-gradient
+            // GEMM at C >= 128, made here otherwise)
+            WgradArgs<T> v = w;
+            v.dY = dy_s; v.mapDY = 0; v.dy_row_scale = nullptr;
+            if ((w.mapDY || w.dy_row_scale) && wgrad_tc_supported(v)) {
+                if (!dy_s_filled) BCK(launch_scale_gather_rows(dy, dy_s, w.dy_row_scale, tokens, C, C, mapped, map, tpi, sms, st));
+                w = v;
             }
         }
         BCK(launch_wgrad<T>(w, sms, st));
@@ -972,11 +988,11 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         w.mapDY = 0; w.mapX = mapped; w.map = map; w.tokens_per_image = tpi;
         if (!f.windowed) { w.mean = mean; w.rstd = rstd; w.ln_w = f.ln_w; w.ln_b = f.ln_b; }
         if constexpr (Act<T>::kIsBf16) {
-            // C >= 128: LN1 + roll + window_partition in one C-sized pass (into dxh, which is free until the next GEMM writes
+            // LN1 + roll + window_partition in one C-sized pass (into dxh, which is free until the next GEMM writes
             // it), so the weight gradient streams plain rows into the tcgen05 kernel
             WgradArgs<T> v = w;
             v.X = dxh; v.mapX = 0; v.mean = nullptr; v.rstd = nullptr; v.ln_w = nullptr; v.ln_b = nullptr;
-            if (!f.windowed && C >= 128 && wgrad_tc_supported(v)) {
+            if (!f.windowed && wgrad_tc_supported(v)) {
                 BCK(launch_ln_apply(x, dxh, f.ln_w, f.ln_b, tokens, C, 1, map, st));
                 w = v;
             }
@@ -1055,7 +1071,13 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         w.dW = a->d_w2; w.db = a->d_b2; w.M = tokens; w.N = C; w.K = Ch;
         w.tokens_per_image = tpi; w.dy_row_scale = dscale;
         if constexpr (Act<T>::kIsBf16) {
-            if (dout_s_filled) { w.dY = dout_s; w.dy_row_scale = nullptr; }   // DropPath-scaled rows left by the GEMM above
+            WgradArgs<T> v = w;                  // DropPath-scaled rows: left by the GEMM above at C >= 128, made here otherwise
+            v.dY = dout_s; v.dy_row_scale = nullptr;
+            if (w.dy_row_scale && wgrad_tc_supported(v)) {
+                WinMap nomap{};
+                if (!dout_s_filled) BCK(launch_scale_gather_rows(dout, dout_s, dscale, tokens, C, C, 0, nomap, tpi, sms, st));
+                w = v;
+            }
         }
         BCK(launch_wgrad<T>(w, sms, st));
     }
@@ -1078,10 +1100,10 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
         w.tokens_per_image = tpi;
         if (f.fused) { w.mean = mean; w.rstd = rstd; w.ln_w = f.ln_w; w.ln_b = f.ln_b; }
         if constexpr (Act<T>::kIsBf16) {
-            // C >= 128: LN2(y) in one C-sized pass (into dz, free until the next GEMM writes it) -> plain operand for the tcgen05 kernel
+            // LN2(y) in one C-sized pass (into dz, free until the next GEMM writes it) -> plain operand for the tcgen05 kernel
             WgradArgs<T> v = w;
             v.X = dz; v.mean = nullptr; v.rstd = nullptr; v.ln_w = nullptr; v.ln_b = nullptr;
-            if (f.fused && C >= 128 && wgrad_tc_supported(v)) {
+            if (f.fused && wgrad_tc_supported(v)) {
                 WinMap nomap{};
                 BCK(launch_ln_apply(y, dz, f.ln_w, f.ln_b, tokens, C, 0, nomap, st));
                 w = v;

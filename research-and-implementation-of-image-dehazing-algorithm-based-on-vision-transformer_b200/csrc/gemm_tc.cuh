@@ -530,6 +530,46 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(const __nv_bfloat16* __re
         }
     }
 }
+// C in {32, 64, 128}: G = C / 8 lanes per row (one 16-byte load each), 32 / G rows per warp and pass, two passes in flight
+template <int G>
+__global__ void __launch_bounds__(256) ln_apply_small_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             long long rows, int mapped, WinMap map) {
+    constexpr int C = G * 8, RPW = 32 / G;
+    const int lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
+    const long long warp_global = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + gl * 8), g1 = *reinterpret_cast<const float4*>(gamma + gl * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + gl * 8), b1 = *reinterpret_cast<const float4*>(beta + gl * 8 + 4);
+    auto fetch = [&](long long m) -> uint4 {
+        if (m >= rows) return make_uint4(0u, 0u, 0u, 0u);
+        const long long tok = mapped ? static_cast<long long>(map.token32(static_cast<uint32_t>(m))) : m;
+        return *reinterpret_cast<const uint4*>(x + tok * C + gl * 8);
+    };
+    long long m = warp_global * RPW + sub;
+    uint4 nxt = fetch(m);
+    for (; m - sub < rows; m += nwarps * RPW) {
+        const uint4 u = nxt;
+        nxt = fetch(m + nwarps * RPW);
+        float f[8];
+        f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xFFFF0000u);
+        f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xFFFF0000u);
+        f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xFFFF0000u);
+        f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xFFFF0000u);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+        const float mu = group_sum<G>(s) / C;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { f[j] -= mu; q += f[j] * f[j]; }
+        const float rs = rsqrtf(group_sum<G>(q) / C + 1e-5f);
+        if (m < rows)
+            *reinterpret_cast<uint4*>(out + m * C + gl * 8) = make_uint4(
+                tc::pack_bf16(f[0] * rs * g0.x + b0.x, f[1] * rs * g0.y + b0.y), tc::pack_bf16(f[2] * rs * g0.z + b0.z, f[3] * rs * g0.w + b0.w),
+                tc::pack_bf16(f[4] * rs * g1.x + b1.x, f[5] * rs * g1.y + b1.y), tc::pack_bf16(f[6] * rs * g1.z + b1.z, f[7] * rs * g1.w + b1.w));
+    }
+}
 // general C <= 1024 (any multiple of 8): one warp per row
 __global__ void __launch_bounds__(256) ln_apply_any_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -584,6 +624,13 @@ inline cudaError_t launch_ln_apply(const __nv_bfloat16* x, __nv_bfloat16* out, c
         ln_apply_kernel<1, 4><<<static_cast<unsigned>((rows + 31) / 32), 256, 0, st>>>(x, out, gamma, beta, rows, mapped, map);
     } else if (C == 512) {
         ln_apply_kernel<2, 4><<<static_cast<unsigned>((rows + 31) / 32), 256, 0, st>>>(x, out, gamma, beta, rows, mapped, map);
+    } else if ((C == 32 || C == 64 || C == 128) && rows < (1ll << 31)) {
+        long long blocks = (rows + 8 * (256 / C) - 1) / (8 * (256 / C));
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        const unsigned gb = static_cast<unsigned>(blocks);
+        if (C == 32) ln_apply_small_kernel<4><<<gb, 256, 0, st>>>(x, out, gamma, beta, rows, mapped, map);
+        else if (C == 64) ln_apply_small_kernel<8><<<gb, 256, 0, st>>>(x, out, gamma, beta, rows, mapped, map);
+        else ln_apply_small_kernel<16><<<gb, 256, 0, st>>>(x, out, gamma, beta, rows, mapped, map);
     } else {
         ln_apply_any_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(x, out, gamma, beta, rows, C, mapped, map);
     }

@@ -7,7 +7,8 @@
 // tcgen05.mma reads MN-major operands directly: a TMA box of [64 tokens x 64 features] in SWIZZLE_128B is exactly the
 // canonical MN-major atom ((8,n),(8,k)):((1,LBO),(8,SBO)) with SBO = 1024 B between 8-token groups and LBO = 8 KB between
 // 64-feature blocks, so no transposition happens anywhere:
-//   * CTA = one [128 x BK] tile of dW (128 dY features x BK <= 256 X features) for one contiguous range of tokens;
+//   * CTA = one [128 x BK] tile of dW (128 dY features x BK <= 256 X features) for one contiguous range of tokens; feature
+//     counts that are not multiples of 128 / 64 (C = 32, 64 levels) ride on the TMA unit's zero fill of out-of-range columns;
 //   * one TMA thread streams 64-token stages (2 boxes of dY, BK / 64 boxes of X) through an S-deep ring;
 //   * one MMA thread issues 4 x tcgen05.mma kind::f16 (a_major = b_major = MN, K = 16 tokens each) per stage into the TMEM
 //     accumulator, plus 4 N = 16 MMAs against a constant all-ones tile whose result column is colsum(dY) (the bias gradient);
@@ -42,14 +43,14 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
            (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BK>
 constexpr size_t fixed_smem() { return 1024 + BLK /*ones*/ + 4 * 32 * STG_LD * 4 + (2 * 8 + 1) * 8 + 16; }
 
 template <int BK>
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgradArgs<__nv_bfloat16> g, const __grid_constant__ CUtensorMap dymap,
                                                              const __grid_constant__ CUtensorMap xmap, int S) {
-    constexpr int STAGE = 2 * BLK + (BK / 64) * BLK;
-    constexpr int TMEM_COLS = BK + 16 <= 256 ? 256 : 512;
+    constexpr int NB = (BK + 63) / 64;            // 64-feature blocks of X per stage
+    constexpr int STAGE = 2 * BLK + NB * BLK;
+    constexpr int TMEM_COLS = BK + 16 <= 64 ? 64 : BK + 16 <= 128 ? 128 : BK + 16 <= 256 ? 256 : 512;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(BK >> 3) << 17) |
                                (static_cast<uint32_t>(NT >> 4) << 24);
     constexpr uint32_t IDESC_DB = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(16 >> 3) << 17) |
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgradArgs<__
                 tma::load_2d(dst, &dymap, &full[s], n0, m);
                 tma::load_2d(dst + BLK, &dymap, &full[s], n0 + 64, m);
 #pragma unroll
-                for (int j = 0; j < BK / 64; ++j) tma::load_2d(dst + (2 + j) * BLK, &xmap, &full[s], k0 + 64 * j, m);
+                for (int j = 0; j < NB; ++j) tma::load_2d(dst + (2 + j) * BLK, &xmap, &full[s], k0 + 64 * j, m);
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
@@ -132,22 +133,23 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgradArgs<__
         tc::tc_fence_after();
         if (stages > 0) {
             const uint32_t t_addr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-            float* dst = g.dW + static_cast<long long>(n0 + warp * 32) * g.K + k0;
+            const int row0 = n0 + warp * 32;          // this warp's first dW row; rows >= N exist only as zero-filled operand rows
+            float* dst = g.dW + static_cast<long long>(row0) * g.K + k0;
+            const int nrows = g.N - row0 < 32 ? g.N - row0 : 32;
 #pragma unroll 1
             for (int c = 0; c < BK / 32; ++c) {
                 float v[32];
-                tc::tmem_ld32(t_addr + c * 32, v);
+                tc::tmem_ld32(t_addr + c * 32, v);    // (warp-collective: also executed by warps whose rows are all >= N)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) my[lane * STG_LD + j] = v[j];
                 __syncwarp();
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) atomicAdd(dst + static_cast<long long>(r) * g.K + c * 32 + lane, my[r * STG_LD + lane]);
+                for (int r = 0; r < nrows; ++r) atomicAdd(dst + static_cast<long long>(r) * g.K + c * 32 + lane, my[r * STG_LD + lane]);
                 __syncwarp();
             }
             if (want_db) {
                 float v[32];
                 tc::tmem_ld32(t_addr + BK, v);       // 16 identical columns (+ 16 unused): colsum(dY) of this row's feature
-                atomicAdd(g.db + n0 + warp * 32 + lane, v[0]);
+                if (lane < nrows) atomicAdd(g.db + row0 + lane, v[0]);
             }
         }
     }
@@ -158,7 +160,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgradArgs<__
 
 inline bool supported(const WgradArgs<__nv_bfloat16>& g) {
     if (!enabled() || g.mapDY || g.mapX || g.dy_row_scale || g.mean || g.dy_aux) return false;
-    if (g.N % NT || g.K % 128 || g.M < 1024 || g.M >= (1ll << 31)) return false;
+    if (g.N % 32 || g.K % 32 || (g.K > 256 && g.K % 256) || g.M < 1024 || g.M >= (1ll << 31)) return false;
+    if (!(g.K % 256 == 0 || g.K == 32 || g.K == 64 || g.K == 96 || g.K == 128 || g.K == 192)) return false;
     if ((g.lddy % 8) || (g.ldx % 8)) return false;
     if ((reinterpret_cast<uintptr_t>(g.dY) & 15) || (reinterpret_cast<uintptr_t>(g.X) & 15)) return false;
     return tma::encode_fn() != nullptr;
@@ -166,8 +169,8 @@ inline bool supported(const WgradArgs<__nv_bfloat16>& g) {
 
 template <int BK>
 cudaError_t launch_bk(WgradArgs<__nv_bfloat16> g, int num_sms, cudaStream_t stream) {
-    constexpr int STAGE = 2 * BLK + (BK / 64) * BLK;
-    constexpr size_t fixed = fixed_smem<BK>();
+    constexpr int STAGE = 2 * BLK + ((BK + 63) / 64) * BLK;
+    constexpr size_t fixed = fixed_smem();
     int S = static_cast<int>((SMEM_MAX - fixed) / STAGE);
     if (S > 8) S = 8;
     const size_t smem = fixed + static_cast<size_t>(S) * STAGE;
@@ -177,7 +180,8 @@ cudaError_t launch_bk(WgradArgs<__nv_bfloat16> g, int num_sms, cudaStream_t stre
     auto k = wgrad_tc_kernel<BK>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    const long long tiles = static_cast<long long>(g.N / NT) * (g.K / BK);
+    const int n_tiles = (g.N + NT - 1) / NT;
+    const long long tiles = static_cast<long long>(n_tiles) * (g.K / BK);
     long long want = (num_sms + tiles - 1) / tiles;                  // about one CTA per SM
     const long long max_splits = (g.M + 4 * TOK - 1) / (4 * TOK);    // at least four stages per CTA
     if (want > max_splits) want = max_splits;
@@ -186,13 +190,18 @@ cudaError_t launch_bk(WgradArgs<__nv_bfloat16> g, int num_sms, cudaStream_t stre
     rps = (rps + TOK - 1) / TOK * TOK;
     const unsigned splits = static_cast<unsigned>((g.M + rps - 1) / rps);
     g.rows_per_split = rps;
-    k<<<dim3(g.N / NT, g.K / BK, splits), THREADS, smem, stream>>>(g, dymap, xmap, S);
+    k<<<dim3(n_tiles, g.K / BK, splits), THREADS, smem, stream>>>(g, dymap, xmap, S);
     return cudaGetLastError();
 }
 
 inline cudaError_t launch(const WgradArgs<__nv_bfloat16>& g, int num_sms, cudaStream_t stream) {
     if (g.K % 256 == 0) return launch_bk<256>(g, num_sms, stream);
-    return launch_bk<128>(g, num_sms, stream);
+    if (g.K == 128) return launch_bk<128>(g, num_sms, stream);
+    if (g.K == 64) return launch_bk<64>(g, num_sms, stream);
+    if (g.K == 32) return launch_bk<32>(g, num_sms, stream);
+    if (g.K == 96) return launch_bk<96>(g, num_sms, stream);
+    if (g.K == 192) return launch_bk<192>(g, num_sms, stream);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace wg3

@@ -878,21 +878,20 @@ inline cudaError_t launch_dgrad_gemm(const GemmArgs<T>& g, __nv_bfloat16* wT_bf1
     if constexpr (Act<T>::kIsBf16) {
         static const bool on = [] { const char* e = getenv("LEWIN_NO_WSS_DGRAD"); return !(e && e[0] == '1'); }();
         static const int min_dim = [] { const char* e = getenv("LEWIN_WSS_DGRAD_MIN"); return e ? atoi(e) : 128; }();
-        if (on && wT_bf16 && g.K >= min_dim && g.N >= min_dim) {
+        if (on) {
             GemmArgs<T> h = g;
             const bool prepass = (g.mapA || g.a_row_scale) && a_scratch && !g.mean && g.K % 8 == 0 && g.M < (1ll << 31);
             if (prepass) { h.A = a_scratch; h.lda = g.K; h.mapA = 0; h.a_row_scale = nullptr; }
-            if (ws::wss_supported(h)) {
+            const bool big = wT_bf16 && g.K >= min_dim && g.N >= min_dim && ws::wss_supported(h);   // streamed-W tcgen05 kernel
+            const bool small = !big && ws::plain_supported(h);                                      // resident-W warp-specialised kernel
+            if (big || small) {
                 if (prepass) {
-                    const long long chunks = g.M * (g.K / 8);
-                    long long grid = (chunks + 255) / 256;
-                    if (grid > static_cast<long long>(sms) * 16) grid = static_cast<long long>(sms) * 16;
-                    scale_gather_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(g.A, a_scratch, g.a_row_scale, g.M, g.K, g.lda,
-                                                                                         g.mapA, g.map, g.tokens_per_image);
-                    cudaError_t e = cudaGetLastError();
+                    cudaError_t e = launch_scale_gather_rows(g.A, a_scratch, g.a_row_scale, g.M, g.K, g.lda, g.mapA, g.map,
+                                                             g.tokens_per_image, sms, st);
                     if (e != cudaSuccess) return e;
                     if (scratch_filled) *scratch_filled = true;   // [M, K] rows with the gather / DropPath scale applied
                 }
+                if (small) return ws::launch_plain(h, sms, st);
                 cudaError_t e = launch_convert_w(g.Wt, wT_bf16, static_cast<long long>(g.N) * g.K, st);
                 if (e != cudaSuccess) return e;
                 return ws::wss_launch<EPI_BIAS>(h, wT_bf16, sms, st);
@@ -940,7 +939,6 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
     // W_out [C(out), C(in)] -> as the [N = in, K = out] operand of dctx = do . W_out
     BCK(launch_transpose(f.w_out, woT, C, C, st));
     BCK(launch_transpose(f.w_qkv, wqkvT, 3 * C, C, st));
-    if (!f.windowed) BCK(launch_ln_stats<T>(x, tokens, C, mean, rstd, st));
 
     bool dy_s_filled = false;
     {   // dctx = (s_b * gather(dy)) . W_out
@@ -997,6 +995,7 @@ int attn_bwd(const LewinAttnBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
                 w = v;
             }
         }
+        if (w.mean) BCK(launch_ln_stats<T>(x, tokens, C, mean, rstd, st));      // only the register-prologue kernels need them
         BCK(launch_wgrad<T>(w, sms, st));
     }
     {   // d(LN1 out) = dqkv . W_qkv, scattered back to token order (window_reverse + un-roll)
@@ -1055,7 +1054,6 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
 
     BCK(launch_transpose(f.w2, w2T, C, Ch, st));      // [C, Ch] -> [Ch, C]  (N = Ch, K = C)
     BCK(launch_transpose(f.w1, w1T, Ch, C, st));      // [Ch, C] -> [C, Ch]  (N = C, K = Ch)
-    if (f.fused) BCK(launch_ln_stats<T>(y, tokens, C, mean, rstd, st));
 
     bool dout_s_filled = false;
     {   // dh2 = (s*dout) . W2
@@ -1109,6 +1107,7 @@ int leff_bwd(const LewinLeffBwdArgs* a, void* ws, size_t ws_bytes, cudaStream_t 
                 w = v;
             }
         }
+        if (w.mean) BCK(launch_ln_stats<T>(y, tokens, C, mean, rstd, st));      // only the register-prologue kernels need them
         BCK(launch_wgrad<T>(w, sms, st));
     }
     {   // dz = da1 . W1

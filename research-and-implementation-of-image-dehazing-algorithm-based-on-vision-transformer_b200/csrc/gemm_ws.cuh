@@ -775,5 +775,23 @@ cudaError_t launch(const GemmArgs<__nv_bfloat16>& g, bool ln, int num_sms, cudaS
     }
 }
 
+// Plain bf16 operand, no LayerNorm, bias-only epilogue (optionally scattered through window_reverse + un-roll): the
+// data-gradient GEMMs dX = dY . W of the C <= 64 levels (N in {32, 64} or the 4C-wide dh2), weights resident in shared memory.
+inline bool plain_supported(const GemmArgs<__nv_bfloat16>& g) {
+    if (!enabled() || g.mapA || g.a_row_scale || g.aux || g.mean || g.up2 || g.Y2 || g.R) return false;
+    if (g.M < 4 * TC_BM || (g.lda % 8) || (g.ldy % 8)) return false;
+    if (g.N == 32) return g.K % 32 == 0 && g.K <= 256;
+    if (g.N == 64) return g.K % 64 == 0 && g.K <= 512;
+    if (g.N == 128) return g.K == 32;
+    if (g.N == 256) return g.K == 64;
+    return false;
+}
+inline cudaError_t launch_plain(const GemmArgs<__nv_bfloat16>& g, int num_sms, cudaStream_t stream) {
+    if (g.N == 32) return launch_inst<32, 32, 1, EPI_BIAS, false>(g, num_sms, stream);
+    if (g.N == 64) return launch_inst<64, 64, 1, EPI_BIAS, false>(g, num_sms, stream);
+    if (g.N == 128) return launch_inst<128, 32, 1, EPI_BIAS, false>(g, num_sms, stream);
+    return launch_inst<256, 64, 1, EPI_BIAS, false>(g, num_sms, stream);
+}
+
 }  // namespace ws
 }  // namespace lewin

@@ -373,8 +373,11 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __res
                                                                   float* __restrict__ dw, float* __restrict__ dbias,
                                                                   int B, int H, int W, int Ch) {
     constexpr int EPC = 16 / sizeof(T), SLAB = 8 * EPC, TY = 8, HX = TX + 2, HY = TY + 2, PPT = TY * TX / 32;
-    __shared__ __align__(16) unsigned char ht[HY * HX * 8 * 16];      // h1 halo tile
-    __shared__ __align__(16) unsigned char dt[TY * TX * 8 * 16];      // da2 interior tile
+    // two buffers of (h1 halo tile, da2 interior tile): the next tile arrives by cp.async while this one is accumulated
+    constexpr int HT_BYTES = HY * HX * 8 * 16, DT_BYTES = TY * TX * 8 * 16;
+    extern __shared__ __align__(16) unsigned char wg_smem[];
+    unsigned char* const ht0 = wg_smem;
+    unsigned char* const dt0 = wg_smem + 2 * HT_BYTES;
     const int tid = threadIdx.x, ch = tid & 7, lane = tid >> 3;
     const int px = lane % TX, py0 = (lane / TX) * PPT;
     const int slab = blockIdx.y, c0 = slab * SLAB;
@@ -387,28 +390,36 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __res
 #pragma unroll
         for (int t = 0; t < 9; ++t) wacc[t][j] = 0.f;
     }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    auto issue = [&](int tile, int buf) {
         int t = tile;
         const int tx = t % tiles_x; t /= tiles_x;
         const int ty = t % tiles_y;
         const int b = t / tiles_y;
         const int y0 = ty * TY - 1, x0 = tx * TX - 1;
-        __syncthreads();
+        unsigned char* hb = ht0 + buf * HT_BYTES;
+        unsigned char* db = dt0 + buf * DT_BYTES;
         for (int i = tid; i < HY * HX * 8; i += 256) {
             const int c = i & 7, p = i >> 3, hy = p / HX, hx = p - hy * HX;
             const int yy = y0 + hy, xx = x0 + hx;
             const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
             const long long o = ((static_cast<long long>(b) * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * Ch + c0 + c * EPC;
-            cp_async16_zfill(ht + i * 16, h1 + o, ok);
+            cp_async16_zfill(hb + i * 16, h1 + o, ok);
         }
         for (int i = tid; i < TY * TX * 8; i += 256) {
             const int c = i & 7, p = i >> 3, iy = p / TX, ix = p - iy * TX;
             const long long o = ((static_cast<long long>(b) * H + ty * TY + iy) * W + tx * TX + ix) * Ch + c0 + c * EPC;
-            cp_async16(dt + i * 16, da2 + o);
+            cp_async16(db + i * 16, da2 + o);
         }
         cp_async_commit();
+    };
+    int buf = 0;
+    if (static_cast<int>(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         cp_async_wait<0>();
-        __syncthreads();
+        __syncthreads();               // this tile has landed; everyone is done with the other buffer
+        if (tile + static_cast<int>(gridDim.x) < ntiles) issue(tile + gridDim.x, buf ^ 1);
+        const unsigned char* ht = ht0 + buf * HT_BYTES;
+        const unsigned char* dt = dt0 + buf * DT_BYTES;
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
             float dv[EPC];
@@ -428,7 +439,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __res
     }
     // lanes tid, tid^8, tid^16, tid^24 of a warp share the channel chunk: shuffle-reduce, then across the 8 warps
     __syncthreads();
-    float* red = reinterpret_cast<float*>(ht);           // [8 warps][8 chunks][10 * EPC]
+    float* red = reinterpret_cast<float*>(ht0);          // [8 warps][8 chunks][10 * EPC]
 #pragma unroll
     for (int t = 0; t < 10; ++t)
 #pragma unroll
@@ -475,7 +486,9 @@ bool launch_dwconv_bwd_tiled(const T* g2, const T* a2, const T* h1, const T* a1,
         }
         const int ntiles = B * (H / 8) * (W / 16);
         int gx = (2 * num_sms + slabs - 1) / slabs; if (gx > ntiles) gx = ntiles;
-        dwconv_bwd_wgrad_kernel<T, 16><<<dim3(gx, slabs), 256, 0, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);
+        constexpr int wg_smem16 = 2 * (10 * (16 + 2) * 128 + 8 * 16 * 128);
+        cudaFuncSetAttribute(dwconv_bwd_wgrad_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem16);
+        dwconv_bwd_wgrad_kernel<T, 16><<<dim3(gx, slabs), 256, wg_smem16, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);
     } else {
         const unsigned grid = static_cast<unsigned>(B) * (H / 8) * (W / 8) * slabs;
         constexpr int smem8 = 2 * 10 * 10 * 128 + 9 * SLAB * 4 + kGeluTabSize * 2;
@@ -483,7 +496,9 @@ bool launch_dwconv_bwd_tiled(const T* g2, const T* a2, const T* h1, const T* a1,
         dwconv_bwd_data_kernel<T, 8><<<grid, 256, smem8, st>>>(g2, a2, a1, da1, da2_scratch, w, B, H, W, Ch);
         const int ntiles = B * (H / 8) * (W / 8);
         int gx = (2 * num_sms + slabs - 1) / slabs; if (gx > ntiles) gx = ntiles;
-        dwconv_bwd_wgrad_kernel<T, 8><<<dim3(gx, slabs), 256, 0, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);
+        constexpr int wg_smem8 = 2 * (10 * (8 + 2) * 128 + 8 * 8 * 128);
+        cudaFuncSetAttribute(dwconv_bwd_wgrad_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem8);
+        dwconv_bwd_wgrad_kernel<T, 8><<<dim3(gx, slabs), 256, wg_smem8, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);
     }
     *err = cudaGetLastError();
     return true;

@@ -161,6 +161,14 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a,
         const __nv_bfloat16* ap = BWD ? a.aux + obase : nullptr;
         const int rows_here = (tx * TX + px < a.W) ? a.H - ty * TY : 0;   // < TY in the last tile row of a map whose height is not a
                                                            // multiple of 16; 0 for the columns beyond a map narrower than the tile (W = 8)
+        // BWD: this thread's pre-activations a1 of all TY rows are requested up front (the loop's early exit keeps the compiler
+        // from hoisting them, and a dependent global load per row was the critical path of the backward pass)
+        uint2 pav[BWD ? TY : 1];
+        if constexpr (BWD) {
+#pragma unroll
+            for (int y = 0; y < TY; ++y)
+                pav[y] = y < rows_here ? __ldg(reinterpret_cast<const uint2*>(ap + y * rstride)) : make_uint2(0u, 0u);
+        }
 #pragma unroll
         for (int y = 0; y < TY; ++y) {
             if (y >= rows_here) break;                     // (the rows below the map were zero-filled: nothing to compute or store)
@@ -175,8 +183,7 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_stream_kernel(const Args a,
                         ffma2(acc0, win[(y + 2 - ky) % 3][2 - kx][0], wk[ky * 3 + kx][0]);
                         ffma2(acc1, win[(y + 2 - ky) % 3][2 - kx][1], wk[ky * 3 + kx][1]);
                     }
-                const uint2 pa = *reinterpret_cast<const uint2*>(ap);
-                ap += rstride;
+                const uint2 pa = pav[y];
                 uint32_t oor = 0;
                 uint32_t g0 = gelu_pair_fast(gtab, pa.x, oor), g1 = gelu_pair_fast(gtab, pa.y, oor);     // gtab holds gelu' here
                 if (__builtin_expect(gelu_pair_oor(oor), 0)) { g0 = gelu_grad_pair_exact(gtab, pa.x); g1 = gelu_grad_pair_exact(gtab, pa.y); }

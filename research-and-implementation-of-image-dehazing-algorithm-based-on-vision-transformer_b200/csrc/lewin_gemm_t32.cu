@@ -37,7 +37,8 @@ cudaError_t gemm_t32_launch(const GemmArgs<float>& g, int epi, cudaStream_t stre
 
 }  // namespace lewin
 
-// diagnostic: copy the LEWIN_T32_PROF counters to `out` (8 launch slots x 16 values) and optionally clear them; returns 0 if profiling is off
+#ifdef LEWIN_T32_PROF_BUILD
+// diagnostic build only (nvcc -DLEWIN_T32_PROF_BUILD): copy the LEWIN_T32_PROF counters to `out` (8 launch slots x 16 values) and optionally clear them; returns 0 if profiling is off
 extern "C" int lewin_debug_t32_prof(unsigned long long* out, int reset) {
     unsigned long long* p = lewin::t32::prof_buffer();
     if (!p) return 0;
@@ -46,3 +47,4 @@ extern "C" int lewin_debug_t32_prof(unsigned long long* out, int reset) {
     if (reset) { cudaMemset(p, 0, 128 * sizeof(unsigned long long)); lewin::t32::prof_launches() = 0; }
     return 1;
 }
+#endif

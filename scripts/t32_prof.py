@@ -1,5 +1,5 @@
 """Per-role cycle counters of the fp32 tcgen05 GEMMs (LEWIN_T32_PROF=1) for one LeWin block at a benchmark shape - GPU box.
-usage: LEWIN_T32_PROF=1 python scripts/t32_prof.py dec3 [tiles]"""
+usage (library built with -DLEWIN_T32_PROF_BUILD added to NVCC_FLAGS in __graft_entry__.py): LEWIN_T32_PROF=1 python scripts/t32_prof.py dec3 [tiles]"""
 import ctypes, os, sys
 import numpy as np
 import torch

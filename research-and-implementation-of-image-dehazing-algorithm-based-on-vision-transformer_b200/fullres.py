@@ -47,6 +47,43 @@ def from_tiles(tiles, L, ps=128):
     return tiles.view(n, n, C, ps, ps).permute(2, 0, 3, 1, 4).reshape(1, C, L, L).contiguous()
 
 
+_GLUE = {}
+
+
+def tile_glue_indices(H, W, C, ps, rank, world, device):
+    """Index form of wrap_pad + to_tiles (input side) and from_tiles + crop (output side) for the tiles of `rank`:
+
+      tiles_of_rank = img.reshape(-1).index_select(0, in_idx).view(n_mine, C, ps, ps)
+      restored      = gathered.reshape(-1).index_select(0, out_idx).view(1, C, H, W)
+
+    where `gathered` is the all-gathered [world * per, C, ps, ps] buffer (rank r's tiles at r * per).  Pure data movement,
+    so the result is bit-identical to the slicing functions above; one kernel on each side instead of ~5, and a rank only
+    touches the pixels of its own tiles.  Built once per geometry by running the slicing functions on a pixel-id image."""
+    key = (H, W, C, ps, rank, world, str(device))
+    g = _GLUE.get(key)
+    if g is None:
+        L = canvas_size(H, W, ps)
+        n = L // ps
+        T = n * n
+        pid = torch.arange(H * W, dtype=torch.float64).view(1, 1, H, W)           # exact integers up to 2^53
+        src = to_tiles(wrap_pad(pid, ps=ps), ps).to(torch.int64)                    # [T, 1, ps, ps] source pixel of every tile pixel
+        s, e = shard_range(T, rank, world)
+        chan = (torch.arange(C, dtype=torch.int64) * (H * W)).view(1, C, 1, 1)
+        in_idx = (src[s:e] + chan).reshape(-1)
+        per = (T + world - 1) // world
+        pos = torch.empty(T, dtype=torch.int64)
+        for r in range(world):
+            rs, re = shard_range(T, r, world)
+            pos[rs:re] = r * per + torch.arange(re - rs)
+        q = from_tiles(torch.arange(T * ps * ps, dtype=torch.float64).view(T, 1, ps, ps), L, ps)[:, :, :H, :W].to(torch.int64)
+        t, rem = q // (ps * ps), q % (ps * ps)
+        out_idx = (pos[t] * (C * ps * ps) + rem + (torch.arange(C, dtype=torch.int64) * (ps * ps)).view(1, C, 1, 1)).reshape(-1)
+        assert int(in_idx.max()) < 2 ** 31 and int(out_idx.max()) < 2 ** 31
+        g = (in_idx.to(torch.int32).to(device), out_idx.to(torch.int32).to(device), per, s, e)
+        _GLUE[key] = g
+    return g
+
+
 def shard_range(T, rank, world):
     """Contiguous tile range of `rank` (the first T % world ranks get one extra tile)."""
     base, extra = divmod(T, world)
@@ -131,10 +168,6 @@ def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=
 
     B, C, H, W = img.shape
     assert B == 1
-    canvas = wrap_pad(img, ps=ps)
-    L = canvas.shape[-1]
-    tiles = to_tiles(canvas, ps)
-    T = tiles.shape[0]
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
@@ -146,8 +179,9 @@ def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=
         dist.broadcast(idx, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         index_samples = idx
 
-    s, e = shard_range(T, rank, world)
-    mine = tiles[s:e]
+    # wrap-pad + tiling and stitching + crop as two index gathers (tile_glue_indices): this rank's tiles only
+    in_idx, out_idx, per, s, e = tile_glue_indices(H, W, C, ps, rank, world, img.device)
+    mine = img.reshape(-1).index_select(0, in_idx).view(e - s, C, ps, ps)
     if graphed is not None:                      # GraphedForward captured for exactly this rank's tile-batch shape
         out = graphed(mine, index_samples)
     else:
@@ -159,18 +193,12 @@ def dehaze_tiled(model, img, ps=128, index_samples=None, group=None, tile_batch=
         out = torch.cat(outs, 0) if outs else mine.new_zeros((0, C, ps, ps))
 
     if distributed:
-        per = (T + world - 1) // world
-        padded = out.new_zeros((per, C, ps, ps))
+        padded = out.new_empty((per, C, ps, ps))     # (a rank with one tile fewer leaves the last slot unread)
         padded[:e - s] = out
         gathered = out.new_empty((world * per, C, ps, ps))
         dist.all_gather_into_tensor(gathered, padded, group=group)
-        parts = []
-        for r in range(world):
-            rs, re = shard_range(T, r, world)
-            parts.append(gathered[r * per:r * per + (re - rs)])
-        out = torch.cat(parts, 0)
-    restored = from_tiles(out, L, ps)
-    return restored[:, :, :H, :W].clamp(0, 1)
+        out = gathered
+    return out.reshape(-1).index_select(0, out_idx).view(1, C, H, W).clamp_(0, 1)
 
 
 def rows_needed(H, W, rank, world, ps=128):

@@ -243,3 +243,29 @@ def test_uformer_constructor_rejects_unbuilt_configurations_with_a_message():
     with pytest.raises(NotImplementedError, match="head_dim"):
         L.WindowAttention(48, 8, 3)
     L.WindowAttention(128, 8, 1)        # head_dim 128 (BASELINE config 5) constructs
+
+
+@pytest.mark.parametrize("H,W,world", [(200, 300, 1), (200, 300, 3), (250, 130, 2), (1200, 1600, 8)])
+def test_tile_glue_indices_equal_the_slicing_functions(H, W, world):
+    """fullres.tile_glue_indices (one index gather per side) == wrap_pad + to_tiles / from_tiles + crop (test_long_GPU.py:85-93
+    geometry), for every rank of a sharded run, including the all-gather layout with one padded slot per short rank."""
+    from lewin_b200 import fullres
+    ps, C = 128, 3
+    torch.manual_seed(H + W + world)
+    img = torch.rand(1, C, H, W)
+    L = fullres.canvas_size(H, W, ps)
+    tiles = fullres.to_tiles(fullres.wrap_pad(img, ps=ps), ps)
+    T = tiles.shape[0]
+    per = (T + world - 1) // world
+    gathered = torch.full((world * per, C, ps, ps), float("nan"))
+    fake_out = tiles * 2.0 + 1.0                                   # stands in for the model: any per-tile function
+    for r in range(world):
+        in_idx, out_idx, per_r, s, e = fullres.tile_glue_indices(H, W, C, ps, r, world, img.device)
+        assert per_r == per and (s, e) == fullres.shard_range(T, r, world)
+        mine = img.reshape(-1).index_select(0, in_idx).view(e - s, C, ps, ps)
+        assert torch.equal(mine, tiles[s:e])
+        gathered[r * per:r * per + (e - s)] = fake_out[s:e]
+    for r in range(world):
+        _, out_idx, _, _, _ = fullres.tile_glue_indices(H, W, C, ps, r, world, img.device)
+        got = gathered.reshape(-1).index_select(0, out_idx).view(1, C, H, W)
+        assert torch.equal(got, fullres.from_tiles(fake_out, L, ps)[:, :, :H, :W])

@@ -292,7 +292,8 @@ class StreamingDehazer:
     Here the host->device copy of image i+1 and the device->host copy of result i-1 run on two side streams while image i
     is computed (double-buffered device images, event-ordered; every image is still copied in and its result copied out
     in full), so a sequence runs at max(compute, copy) per image instead of their sum.  `fn(device_image) -> restored`
-    is e.g. ``lambda x: dehaze_tiled(model, x, graphed=g)``; host tensors should be pinned."""
+    is e.g. ``lambda x: dehaze_tiled(model, x, graphed=g)``, or a staged function returning ``(restored, event)`` such as
+    ``lambda x: pipeline.submit(x, idx)`` of a `TiledPipeline` with the same depth; host tensors should be pinned."""
 
     def __init__(self, fn, shape, device, depth=2, dtype=torch.float32, rows=None, download=True, out_shape=None):
         """rows: image row ranges this rank's tiles read (`rows_needed`; None = the whole image) - only those are uploaded,
@@ -325,7 +326,22 @@ class StreamingDehazer:
         cur.wait_event(self.loaded[i])
         if not first:
             cur.wait_event(self.drained[i])                  # the previous result of this slot has left the device
-        self.y[i].copy_(self.fn(self.x[i]))
+        res = self.fn(self.x[i])
+        if isinstance(res, tuple):
+            # staged function (TiledPipeline.submit): the result is produced on ITS side stream and announced by an event.  The
+            # input slot is free once the compute stream has passed the call; the conversion / copy-out run on the download
+            # stream.  (Both rings have the same depth and advance in lockstep: this slot's `drained` event, awaited above,
+            # also covers the pipeline's reuse of its result slot.)
+            out_t, ev = res
+            self.consumed[i].record(cur)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev)
+                self.y[i].copy_(out_t)
+                if self.download:
+                    out_host.copy_(self.y[i], non_blocking=True)
+                self.drained[i].record(self.s_out)
+            return
+        self.y[i].copy_(res)
         self.consumed[i].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.consumed[i])

@@ -309,6 +309,18 @@ def test_tiled_pipeline_matches_the_serial_call(dt):
         assert a.dtype == b.dtype and torch.equal(a, b)
     for (o, _), b in zip(outs2, refs[:2]):
         assert torch.equal(o, b)
+    # the staged function under StreamingDehazer (host image in, host result out; the stitch and the fp32 conversion run on
+    # side streams): 5 images through the two 2-slot rings in lockstep
+    pipe2 = fullres.TiledPipeline(model, graphed, (1, 3, H, W), dev)
+    sd = fullres.StreamingDehazer(lambda x: pipe2.submit(x, idx), (1, 3, H, W), dev)
+    hosts = [x.cpu().pin_memory() for x in imgs]
+    outs = [torch.empty(1, 3, H, W).pin_memory() for _ in imgs]
+    for a, b in zip(hosts, outs):
+        sd.submit(a, b)
+    sd.flush()
+    torch.cuda.synchronize()
+    for b, r in zip(outs, refs):
+        assert torch.equal(b, r.float().cpu())
 
 
 def test_full_size_tile_batch_invariance_bf16():

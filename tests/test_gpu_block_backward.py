@@ -167,12 +167,17 @@ def test_strict_dropin_modules_forward_backward_f32():
         assert np.abs(got - ref_g).max() < RTOL * max(np.abs(ref_g).max(), 1e-3), k
 
 
-@pytest.mark.parametrize("C,nH,hw,B,shift", [(32, 1, 32, 1, 4), (64, 2, 32, 1, 4), (128, 4, 16, 2, 4), (256, 8, 16, 2, 4)])
-def test_block_backward_bf16_close_to_oracle(C, nH, hw, B, shift):
-    """bf16 backward (pipelined weight-gradient kernel, core backward v2, streaming dwconv data gradient) against the fp64
-    oracle backward evaluated on the bf16-rounded inputs with the GPU's own top-u selection forced.  The bf16 path rounds
-    every intermediate to bf16, so the gate is statistical: cosine similarity and max error relative to the gradient's scale."""
-    rng = np.random.default_rng(2000 + C + hw)
+@pytest.mark.parametrize("C,nH,hw,B,shift,drop", [
+    (32, 1, 32, 1, 4, False), (64, 2, 32, 1, 4, False), (128, 4, 16, 2, 4, False), (256, 8, 16, 2, 4, False),
+    # >= 1024 tokens: the tcgen05 weight-gradient kernel (wgrad_tc.cuh) at every tile shape it is built for, multi-tile dW
+    # (N up to 2048, K up to 2048) and split-K over tokens; `drop`: DropPath scales on (the scale_gather_rows pre-pass)
+    (128, 4, 32, 1, 4, False), (256, 8, 32, 1, 4, False), (512, 16, 32, 1, 0, False), (512, 16, 16, 5, 4, False),
+    (64, 2, 32, 2, 4, True), (256, 8, 16, 5, 4, True)])
+def test_block_backward_bf16_close_to_oracle(C, nH, hw, B, shift, drop):
+    """bf16 backward (tcgen05 / pipelined weight-gradient kernels, core backward v2, streaming dwconv data gradient) against
+    the fp64 oracle backward evaluated on the bf16-rounded inputs with the GPU's own top-u selection forced.  The bf16 path
+    rounds every intermediate to bf16, so the gate is statistical: cosine similarity and max error relative to the gradient's scale."""
+    rng = np.random.default_rng(2000 + C + hw + 7 * B)
     p = O.random_block_params(C, nH, rng, std=0.1)
     p = {k: O.rbf(v) for k, v in p.items()}
     x = O.rbf(rng.standard_normal((B, hw * hw, C)).astype(np.float32))
@@ -180,15 +185,23 @@ def test_block_backward_bf16_close_to_oracle(C, nH, hw, B, shift):
     idx = rng.integers(0, 64, size=(64, 25)).astype(np.int64)
     dev = torch.device("cuda:0")
     import lewin_b200 as L
-    blk = L.LeWinTransformerBlock(dim=C, input_resolution=(128, 128), num_heads=nH, win_size=8, shift_size=shift)
+    blk = L.LeWinTransformerBlock(dim=C, input_resolution=(128, 128), num_heads=nH, win_size=8, shift_size=shift,
+                                  drop_path=0.25 if drop else 0.)
     sd = blk.state_dict()
     for k, v in p.items():
         sd[k].copy_(torch.from_numpy(v))
     blk = blk.to(dev).eval()
+    drop_scale = None
+    if drop:                                     # per-sample DropPath factors (0 or 1 / keep) for the two residual branches
+        keep = 0.75
+        drop_scale = (rng.random((2, B)) < keep).astype(np.float32) / keep
+        drop_scale[:, 0] = 1.0 / keep            # at least one live sample per branch
+        blk.train(True)
+        force_drop_scales(blk, drop_scale, dev)
     xs = torch.from_numpy(x).to(dev).to(torch.bfloat16).requires_grad_(True)
     out, dx, grads, top = _run_block_with_grads(blk, xs, torch.from_numpy(dout).to(dev).to(torch.bfloat16), torch.from_numpy(idx))
     p64 = O.as_dtype(p, np.float64)
-    dx_ref, g_ref = O.lewin_block_bwd(dout.astype(np.float64), x.astype(np.float64), p64, shift, idx,
+    dx_ref, g_ref = O.lewin_block_bwd(dout.astype(np.float64), x.astype(np.float64), p64, shift, idx, None, True, drop_scale,
                                       top=np.sort(top.astype(np.int64), -1))
 
     def close(a, b, name, cos_min=0.995, rel_max=6e-2):

@@ -39,7 +39,7 @@ extern "C" {
 typedef struct CUstream_st* lewin_stream_t; /* == cudaStream_t */
 typedef struct CUevent_st*  lewin_event_t;  /* == cudaEvent_t  */
 
-#define LEWIN_ABI_VERSION 4
+#define LEWIN_ABI_VERSION 5
 
 /* error codes (negative) */
 #define LEWIN_E_NULL      (-1)  /* a required pointer is NULL */
@@ -335,6 +335,26 @@ typedef struct LewinOutputProjArgs {
 } LewinOutputProjArgs;
 int    lewin_output_proj_fwd_bf16(const LewinOutputProjArgs* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
 size_t lewin_output_proj_fwd_workspace_bytes(const LewinOutputProjArgs* a, int dtype);
+
+/* Conv2d(Cin, Cout, kernel 3, stride 1, padding 1) + bias (+ ReLU) on channel-last bf16 maps: the conv / ReLU pairs of the frozen
+ * VGG19 feature extractor behind the reference's contrastive loss (My_CR.py:56-84 Vgg19.forward, :86-123 ContrastLoss.forward;
+ * SURVEY 8(f) rank 1), and - with the kernel flipped and its channel axes swapped by the caller - their data gradients (the VGG
+ * weights are frozen, so no weight gradient exists).  Implicit GEMM on tcgen05: one TMA box per (tap, 64-channel chunk), zero fill
+ * outside the map = the padding, TMEM accumulator, bias / ReLU in the epilogue.  w_bf16: optional caller-owned image
+ * [9][Cout][Cin] bf16 (tap = ky * 3 + kx) of the constant weights; otherwise `weight` is converted into the workspace per call. */
+typedef struct LewinConv3x3Args {
+    int32_t B, H, W, Cin, Cout;    /* W % 8 == 0; Cin, Cout multiples of 64, <= 512 */
+    int32_t ld_x;                  /* elements between consecutive input pixels (0 = Cin) */
+    int32_t ld_out;                /* elements between consecutive output pixels (0 = Cout) */
+    int32_t relu;                  /* 1: ReLU after the bias */
+    const void*  x;                /* [B, H, W, ld_x] bf16 (== an NCHW tensor in channels_last memory format) */
+    const float* weight;           /* [Cout, Cin, 3, 3] fp32, or NULL if w_bf16 is given */
+    const void*  w_bf16;           /* [9, Cout, Cin] bf16 or NULL */
+    const float* bias;             /* [Cout] or NULL */
+    void*        out;              /* [B, H, W, ld_out] bf16 */
+} LewinConv3x3Args;
+int    lewin_conv3x3_fwd_bf16(const LewinConv3x3Args* a, void* workspace, size_t workspace_bytes, lewin_stream_t stream);
+size_t lewin_conv3x3_fwd_workspace_bytes(const LewinConv3x3Args* a, int dtype);
 
 int         lewin_abi_version(void);     /* == LEWIN_ABI_VERSION */
 long long   lewin_launch_count(void);    /* kernels launched by this library in this process (diagnostic counter) */

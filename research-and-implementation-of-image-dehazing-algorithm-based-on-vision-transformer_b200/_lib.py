@@ -112,6 +112,14 @@ class LewinOutputProjArgs(C.Structure):
     ]
 
 
+class LewinConv3x3Args(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+        ("ld_x", C.c_int32), ("ld_out", C.c_int32), ("relu", C.c_int32),
+        ("x", c_ptr), ("weight", c_ptr), ("w_bf16", c_ptr), ("bias", c_ptr), ("out", c_ptr),
+    ]
+
+
 # every symbol include/lewin_b200.h declares (tests check the .so exports all of them)
 EXPORTS = (
     "lewin_attn_fwd_f32", "lewin_attn_fwd_bf16", "lewin_attn_bwd_f32", "lewin_attn_bwd_bf16",
@@ -124,10 +132,11 @@ EXPORTS = (
     "lewin_attn_fwd_kernel_mask", "lewin_leff_fwd_kernel_mask", "lewin_leff_fwd_supports_ld_out",
     "lewin_upsample_fwd_bf16", "lewin_upsample_fwd_workspace_bytes", "lewin_input_proj_fwd_bf16",
     "lewin_downsample_fwd_bf16", "lewin_downsample_fwd_workspace_bytes",
+    "lewin_conv3x3_fwd_bf16", "lewin_conv3x3_fwd_workspace_bytes",
     "lewin_output_proj_fwd_bf16", "lewin_output_proj_fwd_workspace_bytes",
 )
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 DTYPE_TAG = {"f32": 0, "bf16": 1}
 
 _lib = None
@@ -157,7 +166,7 @@ def load():
     lib.lewin_upsample_fwd_bf16.restype = C.c_int
     lib.lewin_upsample_fwd_workspace_bytes.argtypes = [C.POINTER(LewinUpsampleFwdArgs), C.c_int]
     lib.lewin_upsample_fwd_workspace_bytes.restype = C.c_size_t
-    for nm, at in (("downsample", LewinDownsampleArgs), ("output_proj", LewinOutputProjArgs)):
+    for nm, at in (("downsample", LewinDownsampleArgs), ("output_proj", LewinOutputProjArgs), ("conv3x3", LewinConv3x3Args)):
         fn = getattr(lib, f"lewin_{nm}_fwd_bf16")
         fn.argtypes = [C.POINTER(at), C.c_void_p, C.c_size_t, C.c_void_p]
         fn.restype = C.c_int

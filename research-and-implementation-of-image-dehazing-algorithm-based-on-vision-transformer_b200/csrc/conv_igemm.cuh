@@ -42,6 +42,7 @@ struct Args {
     int ntaps, nkc;
     Tap taps[16];
     const float* bias;           // [n_real]
+    int relu;                    // 1: max(0, .) after the bias (conv + ReLU pairs of the VGG19 feature extractor, My_CR.py:56-84)
     __nv_bfloat16* out_tok;      // [B, Hout, Wout, ld_out]
     long long ld_out;
 };
@@ -175,7 +176,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_igemm_kernel(const Args a, co
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int i = j * 8 + 2 * e;
-                            pk[e] = tc::pack_bf16(Act<__nv_bfloat16>::round(v[i]) + bs[c * 32 + i], Act<__nv_bfloat16>::round(v[i + 1]) + bs[c * 32 + i + 1]);
+                            float o0 = Act<__nv_bfloat16>::round(v[i]) + bs[c * 32 + i], o1 = Act<__nv_bfloat16>::round(v[i + 1]) + bs[c * 32 + i + 1];
+                            if (a.relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+                            pk[e] = tc::pack_bf16(o0, o1);
                         }
                         *reinterpret_cast<uint4*>(srow + j * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }

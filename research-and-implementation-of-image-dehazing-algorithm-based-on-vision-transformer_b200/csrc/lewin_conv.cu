@@ -91,6 +91,56 @@ int lewin_downsample_fwd_bf16(const LewinDownsampleArgs* a, void* ws, size_t ws_
     return 0;
 }
 
+size_t lewin_conv3x3_fwd_workspace_bytes(const LewinConv3x3Args* a, int) {
+    return (a && !a->w_bf16) ? align_up(static_cast<size_t>(9) * a->Cout * a->Cin * 2, 256) : 0;
+}
+
+int lewin_conv3x3_fwd_bf16(const LewinConv3x3Args* a, void* ws, size_t ws_bytes, lewin_stream_t s) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(s);
+    if (!a || !a->x || (!a->weight && !a->w_bf16) || !a->out) return LEWIN_E_NULL;
+    const int Cin = a->Cin, N = a->Cout;
+    const int ldx = a->ld_x > 0 ? a->ld_x : Cin, ldo = a->ld_out > 0 ? a->ld_out : N;
+    if (a->B <= 0 || a->H < 1 || a->W < 8 || a->W % 8 || Cin % 64 || Cin > 512 || N % 64 || N > 512 || ldx < Cin || ldx % 8 || ldo < N || ldo % 8)
+        return LEWIN_E_SHAPE;
+    if (!aligned16(a->x) || !aligned16(a->out) || (a->w_bf16 && !aligned16(a->w_bf16))) return LEWIN_E_ALIGN;
+    int sms = 0;
+    if (int rc = device_sms(&sms)) return rc;
+    const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(a->w_bf16);
+    if (!wb) {
+        if (!ws || ws_bytes < lewin_conv3x3_fwd_workspace_bytes(a, LEWIN_DTYPE_BF16)) return LEWIN_E_WORKSPACE;
+        if (!aligned16(ws)) return LEWIN_E_ALIGN;
+        CK(prep(a->weight, static_cast<__nv_bfloat16*>(ws), N, N, Cin, 9, stream));
+        wb = static_cast<const __nv_bfloat16*>(ws);
+    }
+    cv::Args k{};
+    k.B = a->B; k.Hout = a->H; k.Wout = a->W;
+    k.N = N; k.n_real = N;
+    k.px_shift = (a->W % 16 == 0) ? 4 : 3;                       // 8 x 16 or 16 x 8 output pixels per tile
+    const int PX = 1 << k.px_shift, PY = 128 >> k.px_shift;
+    const int BN = N < 256 ? N : 256;
+    k.tiles_x = a->W / PX; k.tiles_y = (a->H + PY - 1) / PY; k.col_tiles = N / BN;
+    k.tiles = a->B * k.tiles_x * k.tiles_y * k.col_tiles;
+    k.ntaps = 9; k.nkc = Cin / 64;
+    for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+            cv::Tap& t = k.taps[ky * 3 + kx];
+            t.dj = kx - 1; t.dc = 0; t.di = ky - 1; t.dq = 0;   // zero fill outside the map == padding 1
+        }
+    k.bias = a->bias; k.relu = a->relu ? 1 : 0;
+    k.out_tok = static_cast<__nv_bfloat16*>(a->out); k.ld_out = ldo;
+    const unsigned long long ld2 = static_cast<unsigned long long>(ldx) * 2;
+    const unsigned long long dims[5] = {static_cast<unsigned long long>(Cin), static_cast<unsigned long long>(a->W), 1ull,
+                                        static_cast<unsigned long long>(a->H), static_cast<unsigned long long>(a->B)};
+    const unsigned long long st[4] = {ld2, static_cast<unsigned long long>(a->W) * ld2, static_cast<unsigned long long>(a->W) * ld2,
+                                      static_cast<unsigned long long>(a->H) * a->W * ld2};
+    CUtensorMap amap{}, wmap{};
+    if (!cv::make_5d(&amap, a->x, dims, st, 64, PX, PY, true) || !cv::make_w2d(&wmap, wb, 9ll * N, Cin, BN, 64)) return LEWIN_E_SHAPE;
+    if (BN == 64) { CK((cv::launch_inst<64, 64>(k, amap, wmap, sms, stream))); }
+    else if (BN == 128) { CK((cv::launch_inst<64, 128>(k, amap, wmap, sms, stream))); }
+    else { CK((cv::launch_inst<64, 256>(k, amap, wmap, sms, stream))); }
+    return 0;
+}
+
 size_t lewin_output_proj_fwd_workspace_bytes(const LewinOutputProjArgs*, int) { return 0; }
 
 int lewin_output_proj_fwd_bf16(const LewinOutputProjArgs* a, void*, size_t, lewin_stream_t s) {

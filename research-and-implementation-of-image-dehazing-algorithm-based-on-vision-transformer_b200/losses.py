@@ -13,7 +13,9 @@ five indices as My_CR.py:62-76).  What changes is how the three VGG passes are r
   * the network is kept channels-last, so under autocast every convolution is a bf16 NHWC implicit GEMM on the tensor
     cores without layout transposes;
   * all shapes are static, so the loss is CUDA-graph capturable together with the model's step (scripts/train_step.py).
-The convolutions themselves are stock cuDNN (library code outside the LeWin hot path).
+On the GPU under bf16 autocast 12 of the 13 convolutions of `features[0:30]` (+ their ReLUs) run on this library's implicit-GEMM tcgen05 kernel
+(`lewin_conv3x3_fwd_bf16`), forward and data gradient (the VGG weights are frozen: no weight gradient); the 3-channel conv1_1
+and the max-pools stay on torch.  Elsewhere (CPU, fp32, trainable VGG) the stock modules run.
 """
 from __future__ import annotations
 
@@ -56,12 +58,59 @@ class Vgg19(nn.Module):
                 p.requires_grad = False
 
     def forward(self, X):
+        if self._own_kernels(X):
+            return self._forward_own(X)
         h1 = self.slice1(X)
         h2 = self.slice2(h1)
         h3 = self.slice3(h2)
         h4 = self.slice4(h3)
         h5 = self.slice5(h4)
         return [h1, h2, h3, h4, h5]
+
+    # ---- B200 path: every conv + ReLU pair with Cin >= 64 (12 of the 13) as one implicit-GEMM tcgen05 kernel, forward and data
+    #      gradient (ops.conv3x3_relu -> lewin_conv3x3_fwd_bf16); conv1_1 (3 input channels) and the max-pools stay on torch
+    def _own_kernels(self, X):
+        import os
+        if not X.is_cuda or os.environ.get("LEWIN_VGG_CUDNN") == "1":
+            return False
+        if any(p.requires_grad for p in self.parameters()):
+            return False                                  # the kernel path has no weight gradient (the reference freezes VGG too)
+        return torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16 and X.shape[-1] % 128 == 0
+
+    def _images(self, conv):
+        from . import ops
+        cache = self.__dict__.setdefault("_w_images", {})
+        key = id(conv)
+        ent = cache.get(key)
+        if ent is None or ent[0] != conv.weight._version or ent[1].device != conv.weight.device:
+            fwd, bwd = ops.conv3x3_weight_images(conv.weight)
+            ent = (conv.weight._version, fwd, bwd)
+            cache[key] = ent
+        return ent[1], ent[2]
+
+    def _forward_own(self, X):
+        from . import ops
+        outs = []
+        h = X
+        for sl in (self.slice1, self.slice2, self.slice3, self.slice4, self.slice5):
+            mods = list(sl.children())
+            i = 0
+            while i < len(mods):
+                m = mods[i]
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if isinstance(m, nn.Conv2d) and isinstance(nxt, nn.ReLU) and m.kernel_size == (3, 3) and m.padding == (1, 1) and \
+                        m.stride == (1, 1) and h.dtype == torch.bfloat16 and ops.conv3x3_supported(h, m.in_channels, m.out_channels):
+                    fwd, bwd = self._images(m)
+                    h = ops.conv3x3_relu(h, fwd, bwd, m.bias)
+                    i += 2
+                    continue
+                h = m(h)
+                if isinstance(m, nn.ReLU) or isinstance(m, nn.MaxPool2d) or isinstance(m, nn.Conv2d):
+                    if h.dim() == 4 and not h.is_contiguous(memory_format=torch.channels_last):
+                        h = h.contiguous(memory_format=torch.channels_last)
+                i += 1
+            outs.append(h)
+        return outs
 
 
 class ContrastLoss(nn.Module):

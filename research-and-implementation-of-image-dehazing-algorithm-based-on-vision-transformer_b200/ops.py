@@ -517,6 +517,60 @@ def lewin_downsample(x, weight, bias, *, B, H, W, pad_h=True, out=None):
     return out
 
 
+def conv3x3_supported(x, Cin, Cout):
+    """x: NCHW tensor in channels_last memory format, bf16, on the GPU; Cin, Cout multiples of 64 up to 512; W % 8 == 0."""
+    return (conv_igemm_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and Cin % 64 == 0 and Cin <= 512 and
+            Cout % 64 == 0 and Cout <= 512 and x.shape[3] % 8 == 0 and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def conv3x3_weight_images(weight):
+    """bf16 operand images of a frozen Conv2d(Cin, Cout, 3, padding=1) weight [Cout, Cin, 3, 3]:
+    forward [9, Cout, Cin] (tap = ky * 3 + kx) and data-gradient [9, Cin, Cout] (kernel flipped, channel axes swapped)."""
+    w = weight.detach().float()
+    Cout, Cin = w.shape[0], w.shape[1]
+    fwd = w.permute(2, 3, 0, 1).reshape(9, Cout, Cin).to(torch.bfloat16).contiguous()
+    bwd = w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, Cin, Cout).to(torch.bfloat16).contiguous()
+    return fwd, bwd
+
+
+def lewin_conv3x3(x, w_img, bias, relu):
+    """Conv2d(kernel 3, padding 1) + bias (+ ReLU) on a channels_last bf16 NCHW tensor through lewin_conv3x3_fwd_bf16 (implicit
+    GEMM on tcgen05).  w_img: [9, Cout, Cin] bf16 (conv3x3_weight_images).  Returns a channels_last bf16 NCHW tensor."""
+    lib = _lib.load()
+    B, Cin, H, W = x.shape
+    Cout = w_img.shape[1]
+    assert w_img.shape == (9, Cout, Cin) and w_img.dtype == torch.bfloat16 and w_img.is_contiguous()
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((B, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    b_ = _f32c(bias) if bias is not None else None
+    a = _lib.LewinConv3x3Args(B=B, H=H, W=W, Cin=Cin, Cout=Cout, ld_x=Cin, ld_out=Cout, relu=int(bool(relu)),
+                              x=_ptr(x), weight=None, w_bf16=_ptr(w_img), bias=_ptr(b_) if b_ is not None else None, out=_ptr(out))
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lewin_conv3x3_fwd_bf16(a, None, 0, _stream()), "lewin_conv3x3_fwd_bf16")
+    return out
+
+
+class _ConvReluFn(torch.autograd.Function):
+    """relu(conv3x3(x) + b) with frozen weights: forward and data gradient on the implicit-GEMM kernel (no weight gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, w_fwd, w_bwd, bias):
+        y = lewin_conv3x3(x, w_fwd, bias, True)
+        if x.requires_grad:
+            ctx.save_for_backward(y, w_bwd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, w_bwd = ctx.saved_tensors
+        g = (dy.to(torch.bfloat16) * (y > 0)).contiguous(memory_format=torch.channels_last)
+        return lewin_conv3x3(g, w_bwd, None, False), None, None, None
+
+
+def conv3x3_relu(x, w_fwd, w_bwd, bias):
+    return _ConvReluFn.apply(x, w_fwd, w_bwd, bias)
+
+
 def output_proj_supported(x, Cin, Cout, W):
     return (conv_igemm_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and Cin % 64 == 0 and Cin <= 256 and 1 <= Cout <= 8)
 

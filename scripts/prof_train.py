@@ -23,4 +23,14 @@ for _ in range(3): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=32, max_name_column_width=80))
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        a = agg[ev.name[:110]]
+        a[0] += 1; a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+tot = sum(v[1] for v in agg.values())
+lew = sum(v[1] for k, v in agg.items() if "lewin" in k)
+print(f"training step (eager, Charbonnier only): kernel time {tot / 1e3:.2f} ms in {sum(v[0] for v in agg.values())} kernels; lewin:: kernels {lew / 1e3:.2f} ms")
+for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+    print(f"{us:9.1f} us  x{n:4d}  {name}")

@@ -198,169 +198,195 @@ def _bf16_image(w):
     return weight_images.get(w)
 
 
+def _attn_forward(x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask, drop_scale, geom):
+    """One lewin_attn_fwd_* call.  Returns (y, top, saved): ``saved`` is what the backward call needs (the fp32 parameter
+    tensors as they crossed the ABI, the int32 sample indices, q|k|v, ctx, top).  Shared by the autograd.Function below and
+    the torch.library ops of compile_ops.py."""
+    B, H, W, nH, shift, windowed, use_rpb, analytic, need_grad = geom[:9]
+    band = geom[9] if len(geom) > 9 else None          # (y0, Hg): row band of a taller image (forward only)
+    lib = _lib.load()
+    dt = _dtype_tag(x)
+    x = x.contiguous()
+    C = x.shape[-1]
+    tokens = B * H * W
+    assert x.numel() == tokens * C, (x.shape, B, H, W, C)
+    dev = x.device
+    y = torch.empty_like(x)
+    top = torch.empty((tokens // 64, nH, 25), dtype=torch.uint8, device=dev)
+    params = [_f32c(t) for t in (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, mask, drop_scale)]
+    ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, mask_, ds_ = params
+    idx = prepare_index_sample(index_sample, dev)
+    a = _lib.LewinAttnFwdArgs(
+        B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
+        analytic_shift_mask=int(analytic), nW_mask=0 if mask_ is None else mask_.shape[0],
+        save_for_backward=int(need_grad), reserved=0,
+        x=_ptr(x), y=_ptr(y), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w_qkv=_ptr(w_qkv_), b_qkv=_ptr(b_qkv_),
+        w_out=_ptr(w_out_), b_out=_ptr(b_out_), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
+        index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
+        qkv=None, ctx=None, top=_ptr(top))
+    if band is not None:
+        if need_grad:
+            raise RuntimeError("lewin_b200.lewin_attn: row-band mode is forward only")
+        a.band_mode, a.band_y0, a.band_Hg = 1, int(band[0]), int(band[1])
+    kmask = lib.lewin_attn_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
+    if kmask == 2:          # LEWIN_ATTN_K_FUSED: q|k|v and ctx stay on chip, the ABI only wants valid placeholders
+        qkv = cbuf = torch.empty((16,), dtype=x.dtype, device=dev)
+    else:
+        qkv = torch.empty((tokens, 3 * C), dtype=x.dtype, device=dev)
+        cbuf = torch.empty((tokens, C), dtype=x.dtype, device=dev)
+    a.qkv, a.ctx = _ptr(qkv), _ptr(cbuf)
+    if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:      # constants of an inference call: convert once
+        wq_b, wo_b = _bf16_image(w_qkv_), _bf16_image(w_out_)
+        a.w_qkv_bf16, a.w_out_bf16 = _ptr(wq_b), _ptr(wo_b)
+    if KernelTimer.active is not None:
+        mask = kmask
+        tim = KernelTimer.active.events_for("attn", dict(tokens=tokens, C=C, nH=nH, dtype=dt),
+                                            tuple(k for k in range(5) if mask >> k & 1))
+        a.timing = ctypes_addr(tim)
+    ws = _workspace(lib.lewin_attn_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+    fn = getattr(lib, f"lewin_attn_fwd_{dt}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_attn_fwd_{dt}")
+    if TopRecorder.active is not None:
+        TopRecorder.active.tops.append(top)
+    return y, top, (x, ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, idx, mask_, ds_, qkv, cbuf, top)
+
+
+def _attn_backward(saved, geom, dy):
+    """One lewin_attn_bwd_* call on the tensors _attn_forward saved -> (dx, d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out,
+    d_rpb_table, d_rpb_dense); entries of absent parameters are None."""
+    (x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense, idx, mask, ds, qkv, cbuf, top) = saved
+    B, H, W, nH, shift, windowed, use_rpb, analytic, _ = geom[:9]
+    lib = _lib.load()
+    dt = _dtype_tag(x)
+    dev = x.device
+    C = x.shape[-1]
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab, d_dense = _zero_grads(
+        (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense if tab is None else None), dev)
+    fwd = _lib.LewinAttnFwdArgs(
+        B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
+        analytic_shift_mask=int(analytic), nW_mask=0 if mask is None else mask.shape[0],
+        save_for_backward=1, reserved=0,
+        x=_ptr(x), y=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w_qkv=_ptr(w_qkv), b_qkv=_ptr(b_qkv),
+        w_out=_ptr(w_out), b_out=_ptr(b_out), rpb_table=_ptr(tab), rpb_dense=_ptr(dense),
+        index_sample=_ptr(idx), mask=_ptr(mask), drop_scale=_ptr(ds),
+        qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
+    a = _lib.LewinAttnBwdArgs(
+        fwd=fwd, dy=_ptr(dy), dx=_ptr(dx), d_ln_w=_ptr(d_ln_w), d_ln_b=_ptr(d_ln_b),
+        d_w_qkv=_ptr(d_w_qkv), d_b_qkv=_ptr(d_b_qkv), d_w_out=_ptr(d_w_out), d_b_out=_ptr(d_b_out),
+        d_rpb_table=_ptr(d_tab), d_rpb_dense=_ptr(d_dense))
+    ws = _workspace(lib.lewin_attn_bwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+    fn = getattr(lib, f"lewin_attn_bwd_{dt}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_attn_bwd_{dt}")
+    # table path: d(relative_position_bias_table); dense path (AttentionLayer.forward's gathered bias, attn.py:385):
+    # d(relative_position_bias) [nH, 64, 64], which autograd scatters back into the caller's table through its own gather
+    return (dx, d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab, d_dense)
+
+
 class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
                 drop_scale, geom):
-        B, H, W, nH, shift, windowed, use_rpb, analytic, need_grad = geom[:9]
-        band = geom[9] if len(geom) > 9 else None          # (y0, Hg): row band of a taller image (forward only)
-        lib = _lib.load()
-        dt = _dtype_tag(x)
-        x = x.contiguous()
-        C = x.shape[-1]
-        tokens = B * H * W
-        assert x.numel() == tokens * C, (x.shape, B, H, W, C)
-        dev = x.device
-        y = torch.empty_like(x)
-        top = torch.empty((tokens // 64, nH, 25), dtype=torch.uint8, device=dev)
-        params = [_f32c(t) for t in (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, mask, drop_scale)]
-        ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, mask_, ds_ = params
-        idx = prepare_index_sample(index_sample, dev)
-        a = _lib.LewinAttnFwdArgs(
-            B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
-            analytic_shift_mask=int(analytic), nW_mask=0 if mask_ is None else mask_.shape[0],
-            save_for_backward=int(need_grad), reserved=0,
-            x=_ptr(x), y=_ptr(y), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w_qkv=_ptr(w_qkv_), b_qkv=_ptr(b_qkv_),
-            w_out=_ptr(w_out_), b_out=_ptr(b_out_), rpb_table=_ptr(tab_), rpb_dense=_ptr(dense_),
-            index_sample=_ptr(idx), mask=_ptr(mask_), drop_scale=_ptr(ds_),
-            qkv=None, ctx=None, top=_ptr(top))
-        if band is not None:
-            if need_grad:
-                raise RuntimeError("lewin_b200.lewin_attn: row-band mode is forward only")
-            a.band_mode, a.band_y0, a.band_Hg = 1, int(band[0]), int(band[1])
-        kmask = lib.lewin_attn_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
-        if kmask == 2:          # LEWIN_ATTN_K_FUSED: q|k|v and ctx stay on chip, the ABI only wants valid placeholders
-            qkv = cbuf = torch.empty((16,), dtype=x.dtype, device=dev)
-        else:
-            qkv = torch.empty((tokens, 3 * C), dtype=x.dtype, device=dev)
-            cbuf = torch.empty((tokens, C), dtype=x.dtype, device=dev)
-        a.qkv, a.ctx = _ptr(qkv), _ptr(cbuf)
-        if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:      # constants of an inference call: convert once
-            wq_b, wo_b = _bf16_image(w_qkv_), _bf16_image(w_out_)
-            a.w_qkv_bf16, a.w_out_bf16 = _ptr(wq_b), _ptr(wo_b)
-        if KernelTimer.active is not None:
-            mask = kmask
-            tim = KernelTimer.active.events_for("attn", dict(tokens=tokens, C=C, nH=nH, dtype=dt),
-                                                tuple(k for k in range(5) if mask >> k & 1))
-            a.timing = ctypes_addr(tim)
-        ws = _workspace(lib.lewin_attn_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
-        fn = getattr(lib, f"lewin_attn_fwd_{dt}")
-        with torch.cuda.device(dev):
-            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_attn_fwd_{dt}")
+        y, top, saved = _attn_forward(x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
+                                      drop_scale, geom)
         ctx.geom = geom
-        ctx.dt = dt
-        ctx.save_for_backward(x, ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, idx, mask_, ds_, qkv, cbuf, top)
+        ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(top)
-        if TopRecorder.active is not None:
-            TopRecorder.active.tops.append(top)
         return y, top
 
     @staticmethod
     def backward(ctx, dy, _dtop):
-        (x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense, idx, mask, ds, qkv, cbuf, top) = ctx.saved_tensors
-        B, H, W, nH, shift, windowed, use_rpb, analytic, _ = ctx.geom[:9]
-        lib = _lib.load()
-        dt = ctx.dt
-        dev = x.device
-        C = x.shape[-1]
-        dy = dy.contiguous()
-        dx = torch.empty_like(x)
-        d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab, d_dense = _zero_grads(
-            (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense if tab is None else None), dev)
-        fwd = _lib.LewinAttnFwdArgs(
-            B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
-            analytic_shift_mask=int(analytic), nW_mask=0 if mask is None else mask.shape[0],
-            save_for_backward=1, reserved=0,
-            x=_ptr(x), y=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w_qkv=_ptr(w_qkv), b_qkv=_ptr(b_qkv),
-            w_out=_ptr(w_out), b_out=_ptr(b_out), rpb_table=_ptr(tab), rpb_dense=_ptr(dense),
-            index_sample=_ptr(idx), mask=_ptr(mask), drop_scale=_ptr(ds),
-            qkv=_ptr(qkv), ctx=_ptr(cbuf), top=_ptr(top))
-        a = _lib.LewinAttnBwdArgs(
-            fwd=fwd, dy=_ptr(dy), dx=_ptr(dx), d_ln_w=_ptr(d_ln_w), d_ln_b=_ptr(d_ln_b),
-            d_w_qkv=_ptr(d_w_qkv), d_b_qkv=_ptr(d_b_qkv), d_w_out=_ptr(d_w_out), d_b_out=_ptr(d_b_out),
-            d_rpb_table=_ptr(d_tab), d_rpb_dense=_ptr(d_dense))
-        ws = _workspace(lib.lewin_attn_bwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
-        fn = getattr(lib, f"lewin_attn_bwd_{dt}")
-        with torch.cuda.device(dev):
-            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_attn_bwd_{dt}")
-        # table path: d(relative_position_bias_table); dense path (AttentionLayer.forward's gathered bias, attn.py:385):
-        # d(relative_position_bias) [nH, 64, 64], which autograd scatters back into the caller's table through its own gather
-        return (dx, d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab, d_dense, None, None, None, None)
+        return _attn_backward(ctx.saved_tensors, ctx.geom, dy) + (None, None, None, None)
+
+
+def _leff_forward(y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom, out_view=None):
+    """One lewin_leff_fwd_* call.  Returns (out, saved): ``saved`` (None for an inference call) is what the backward call needs.
+    Shared by the autograd.Function below and the torch.library ops of compile_ops.py."""
+    B, H, W, fused, need_grad = geom
+    lib = _lib.load()
+    dt = _dtype_tag(y)
+    y = y.contiguous()
+    C = y.shape[-1]
+    hidden = w1.shape[0]
+    tokens = B * H * W
+    assert y.numel() == tokens * C, (y.shape, B, H, W, C)
+    dev = y.device
+    out = torch.empty_like(y)
+    h1 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
+    h2 = h1                       # placeholder until the library says whether h2 exists in global memory for this call
+    a1 = torch.empty_like(h1) if need_grad else None
+    a2 = torch.empty_like(h1) if need_grad else None
+    ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_ = [_f32c(t) for t in (ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale)]
+    a = _lib.LewinLeffFwdArgs(
+        B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=int(need_grad), ld_out=0,
+        y=_ptr(y), out=_ptr(out), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w1=_ptr(w1_), b1=_ptr(b1_),
+        w_dw=_ptr(wdw_), b_dw=_ptr(bdw_), w2=_ptr(w2_), b2=_ptr(b2_), drop_scale=_ptr(ds_),
+        h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
+    if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:
+        w1_b, w2_b = _bf16_image(w1_), _bf16_image(w2_)
+        a.w1_bf16, a.w2_bf16 = _ptr(w1_b), _ptr(w2_b)
+    if out_view is not None and not need_grad and lib.lewin_leff_fwd_supports_ld_out(a, _lib.DTYPE_TAG[dt]):
+        # the caller's column block of a wider buffer (the right half of the decoder's concat buffer): written in place
+        out = out_view
+        a.out, a.ld_out = _ptr(out), out.stride(-2)
+    mask = lib.lewin_leff_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
+    if not (mask >> 4 & 1):       # LEWIN_LEFF_K_TAIL clear: the three-kernel pipeline writes h2 = GELU(dwconv(h1))
+        h2 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
+        a.h2 = _ptr(h2)
+    if KernelTimer.active is not None:
+        tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt),
+                                            tuple(k for k in range(5) if mask >> k & 1))
+        a.timing = ctypes_addr(tim)
+    ws = _workspace(lib.lewin_leff_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+    fn = getattr(lib, f"lewin_leff_fwd_{dt}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_leff_fwd_{dt}")
+    return out, ((y, ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_, h1, h2, a1, a2) if need_grad else None)
+
+
+def _leff_backward(saved, geom, dout):
+    """One lewin_leff_bwd_* call on the tensors _leff_forward saved -> (dy, d_ln_w, d_ln_b, d_w1, d_b1, d_w_dw, d_b_dw, d_w2,
+    d_b2); entries of absent parameters are None."""
+    (y, ln_w, ln_b, w1, b1, wdw, bdw, w2, b2, ds, h1, h2, a1, a2) = saved
+    B, H, W, fused, _ = geom
+    lib = _lib.load()
+    dt = _dtype_tag(y)
+    dev = y.device
+    C = y.shape[-1]
+    hidden = w1.shape[0]
+    dout = dout.contiguous()
+    dy = torch.empty_like(y)
+    d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2 = _zero_grads((ln_w, ln_b, w1, b1, wdw, bdw, w2, b2), dev)
+    fwd = _lib.LewinLeffFwdArgs(
+        B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=1, ld_out=0,
+        y=_ptr(y), out=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w1=_ptr(w1), b1=_ptr(b1),
+        w_dw=_ptr(wdw), b_dw=_ptr(bdw), w2=_ptr(w2), b2=_ptr(b2), drop_scale=_ptr(ds),
+        h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
+    a = _lib.LewinLeffBwdArgs(
+        fwd=fwd, dout=_ptr(dout), dy=_ptr(dy), d_ln_w=_ptr(d_ln_w), d_ln_b=_ptr(d_ln_b),
+        d_w1=_ptr(d_w1), d_b1=_ptr(d_b1), d_w_dw=_ptr(d_wdw), d_b_dw=_ptr(d_bdw), d_w2=_ptr(d_w2), d_b2=_ptr(d_b2))
+    ws = _workspace(lib.lewin_leff_bwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
+    fn = getattr(lib, f"lewin_leff_bwd_{dt}")
+    with torch.cuda.device(dev):
+        _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_leff_bwd_{dt}")
+    return (dy, d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2)
 
 
 class _LeffFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom, out_view=None):
-        B, H, W, fused, need_grad = geom
-        lib = _lib.load()
-        dt = _dtype_tag(y)
-        y = y.contiguous()
-        C = y.shape[-1]
-        hidden = w1.shape[0]
-        tokens = B * H * W
-        assert y.numel() == tokens * C, (y.shape, B, H, W, C)
-        dev = y.device
-        out = torch.empty_like(y)
-        h1 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
-        h2 = h1                       # placeholder until the library says whether h2 exists in global memory for this call
-        a1 = torch.empty_like(h1) if need_grad else None
-        a2 = torch.empty_like(h1) if need_grad else None
-        ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_ = [_f32c(t) for t in (ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale)]
-        a = _lib.LewinLeffFwdArgs(
-            B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=int(need_grad), ld_out=0,
-            y=_ptr(y), out=_ptr(out), ln_w=_ptr(ln_w_), ln_b=_ptr(ln_b_), w1=_ptr(w1_), b1=_ptr(b1_),
-            w_dw=_ptr(wdw_), b_dw=_ptr(bdw_), w2=_ptr(w2_), b2=_ptr(b2_), drop_scale=_ptr(ds_),
-            h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
-        if dt == "bf16" and C >= 256 and not need_grad and _WEIGHT_IMAGES_ON:
-            w1_b, w2_b = _bf16_image(w1_), _bf16_image(w2_)
-            a.w1_bf16, a.w2_bf16 = _ptr(w1_b), _ptr(w2_b)
-        if out_view is not None and not need_grad and lib.lewin_leff_fwd_supports_ld_out(a, _lib.DTYPE_TAG[dt]):
-            # the caller's column block of a wider buffer (the right half of the decoder's concat buffer): written in place
-            out = out_view
-            a.out, a.ld_out = _ptr(out), out.stride(-2)
-        mask = lib.lewin_leff_fwd_kernel_mask(a, _lib.DTYPE_TAG[dt])
-        if not (mask >> 4 & 1):       # LEWIN_LEFF_K_TAIL clear: the three-kernel pipeline writes h2 = GELU(dwconv(h1))
-            h2 = torch.empty((tokens, hidden), dtype=y.dtype, device=dev)
-            a.h2 = _ptr(h2)
-        if KernelTimer.active is not None:
-            tim = KernelTimer.active.events_for("leff", dict(tokens=tokens, C=C, hidden=hidden, dtype=dt),
-                                                tuple(k for k in range(5) if mask >> k & 1))
-            a.timing = ctypes_addr(tim)
-        ws = _workspace(lib.lewin_leff_fwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
-        fn = getattr(lib, f"lewin_leff_fwd_{dt}")
-        with torch.cuda.device(dev):
-            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_leff_fwd_{dt}")
+        out, saved = _leff_forward(y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom, out_view)
         ctx.geom = geom
-        ctx.dt = dt
-        if need_grad:
-            ctx.save_for_backward(y, ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_, h1, h2, a1, a2)
+        if saved is not None:
+            ctx.save_for_backward(*saved)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (y, ln_w, ln_b, w1, b1, wdw, bdw, w2, b2, ds, h1, h2, a1, a2) = ctx.saved_tensors
-        B, H, W, fused, _ = ctx.geom
-        lib = _lib.load()
-        dt = ctx.dt
-        dev = y.device
-        C = y.shape[-1]
-        hidden = w1.shape[0]
-        dout = dout.contiguous()
-        dy = torch.empty_like(y)
-        d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2 = _zero_grads((ln_w, ln_b, w1, b1, wdw, bdw, w2, b2), dev)
-        fwd = _lib.LewinLeffFwdArgs(
-            B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=1, ld_out=0,
-            y=_ptr(y), out=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w1=_ptr(w1), b1=_ptr(b1),
-            w_dw=_ptr(wdw), b_dw=_ptr(bdw), w2=_ptr(w2), b2=_ptr(b2), drop_scale=_ptr(ds),
-            h1=_ptr(h1), h2=_ptr(h2), a1=_ptr(a1), a2=_ptr(a2))
-        a = _lib.LewinLeffBwdArgs(
-            fwd=fwd, dout=_ptr(dout), dy=_ptr(dy), d_ln_w=_ptr(d_ln_w), d_ln_b=_ptr(d_ln_b),
-            d_w1=_ptr(d_w1), d_b1=_ptr(d_b1), d_w_dw=_ptr(d_wdw), d_b_dw=_ptr(d_bdw), d_w2=_ptr(d_w2), d_b2=_ptr(d_b2))
-        ws = _workspace(lib.lewin_leff_bwd_workspace_bytes(a, _lib.DTYPE_TAG[dt]), dev)
-        fn = getattr(lib, f"lewin_leff_bwd_{dt}")
-        with torch.cuda.device(dev):
-            _lib.check(fn(a, ws.data_ptr(), ws.numel(), _stream()), f"lewin_leff_bwd_{dt}")
-        return (dy, d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2, None, None, None)
+        return _leff_backward(ctx.saved_tensors, ctx.geom, dout) + (None, None, None)
 
 
 def lewin_attn(x, *, B, H, W, num_heads, shift, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out,
@@ -374,6 +400,12 @@ def lewin_attn(x, *, B, H, W, num_heads, shift, ln_w, ln_b, w_qkv, b_qkv, w_out,
     geom = (int(B), int(H), int(W), int(num_heads), int(shift), bool(windowed), bool(use_rpb), bool(analytic_shift_mask), need)
     if band is not None:
         geom = geom + ((int(band[0]), int(band[1])),)
+    elif torch.compiler.is_compiling():        # traced by torch.compile / export: one opaque torch.library node (compile_ops.py)
+        y, top = compile_ops.lewin_attn(x, B=B, H=H, W=W, num_heads=num_heads, shift=shift, ln_w=ln_w, ln_b=ln_b, w_qkv=w_qkv,
+                                        b_qkv=b_qkv, w_out=w_out, b_out=b_out, rpb_table=rpb_table, rpb_dense=rpb_dense,
+                                        index_sample=index_sample, mask=mask, drop_scale=drop_scale, windowed=windowed,
+                                        use_rpb=use_rpb, analytic_shift_mask=analytic_shift_mask, need=need)
+        return (y, top) if return_top else y
     y, top = _AttnFn.apply(x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dense, index_sample, mask,
                            drop_scale, geom)
     return (y, top) if return_top else y
@@ -386,6 +418,9 @@ def lewin_leff(y, *, B, H, W, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale
     need = torch.is_grad_enabled() and any(
         isinstance(t, torch.Tensor) and t.requires_grad for t in (y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2))
     geom = (int(B), int(H), int(W), bool(fused), need)
+    if torch.compiler.is_compiling():          # traced: one opaque torch.library node; the in-place `out` view is not offered there
+        return compile_ops.lewin_leff(y, B=B, H=H, W=W, ln_w=ln_w, ln_b=ln_b, w1=w1, b1=b1, w_dw=w_dw, b_dw=b_dw, w2=w2, b2=b2,
+                                      drop_scale=drop_scale, fused=fused, need=need)
     if out is not None:
         ok = (out.shape == y.shape and out.dtype == y.dtype and out.device == y.device and out.stride(-1) == 1 and
               out.stride(-2) % 8 == 0 and out.data_ptr() % 16 == 0 and
@@ -613,3 +648,6 @@ def lewin_input_proj(x, weight, bias, negative_slope=0.01):
     with torch.cuda.device(x.device):
         _lib.check(lib.lewin_input_proj_fwd_bf16(a, _stream()), "lewin_input_proj_fwd_bf16")
     return out
+
+
+from . import compile_ops  # noqa: E402  (registers torch.ops.lewin_b200.*; imports this module back, so it comes last)

@@ -64,7 +64,7 @@ def attn_bwd(dy: Tensor, x: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tenso
     f = ops._f32c
     saved = (x.contiguous(), f(ln_w), f(ln_b), f(w_qkv), f(b_qkv), f(w_out), f(b_out), f(rpb_table), f(rpb_dense),
              ops.prepare_index_sample(index_sample, x.device), f(mask), f(drop_scale), qkv, ctx, top)
-    dx, d_ln_w, d_ln_b, d_wq, d_bq, d_wo, d_bo, d_tab, d_dense = ops._attn_backward(saved, geom, dy)
+    dx, d_ln_w, d_ln_b, d_wq, d_bq, d_wo, d_bo, d_tab, d_dense = ops._attn_backward(saved, geom, dy, separate_grads=True)
     d_rpb = d_tab if d_tab is not None else d_dense
     z = dx.new_empty((0,), dtype=torch.float32)
     return dx, _req(d_ln_w, z), _req(d_ln_b, z), d_wq, d_bq, d_wo, d_bo, _req(d_rpb, z)
@@ -137,7 +137,7 @@ def leff_bwd(dout: Tensor, y: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Ten
     """-> (dy, d_ln_w, d_ln_b, d_w1, d_b1, d_w_dw, d_b_dw, d_w2, d_b2)."""
     f = ops._f32c
     saved = (y.contiguous(), f(ln_w), f(ln_b), f(w1), f(b1), f(w_dw), f(b_dw), f(w2), f(b2), f(drop_scale), h1, h2, a1, a2)
-    dy, d_ln_w, d_ln_b, *rest = ops._leff_backward(saved, (B, H, W, fused, True), dout)
+    dy, d_ln_w, d_ln_b, *rest = ops._leff_backward(saved, (B, H, W, fused, True), dout, separate_grads=True)
     z = dy.new_empty((0,), dtype=torch.float32)
     return (dy, _req(d_ln_w, z), _req(d_ln_b, z)) + tuple(rest)
 

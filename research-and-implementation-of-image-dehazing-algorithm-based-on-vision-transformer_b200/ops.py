@@ -57,9 +57,12 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
-def _zero_grads(like, device):
+def _zero_grads(like, device, separate=False):
     """fp32 zero gradient buffers for the given parameter tensors (None entries stay None): ONE flat allocation and one
-    fill kernel, handed out as views (the backward kernels accumulate into them with atomics)."""
+    fill kernel, handed out as views (the backward kernels accumulate into them with atomics).  separate=True gives every
+    gradient its own storage (returns of a torch.library op may not alias each other)."""
+    if separate:
+        return [None if t is None else torch.zeros(t.shape, dtype=torch.float32, device=device) for t in like]
     sizes = [0 if t is None else t.numel() for t in like]
     flat = torch.zeros(sum((n + 3) // 4 * 4 for n in sizes), dtype=torch.float32, device=device)
     out, off = [], 0
@@ -252,7 +255,7 @@ def _attn_forward(x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, rpb_table, rpb_dens
     return y, top, (x, ln_w_, ln_b_, w_qkv_, b_qkv_, w_out_, b_out_, tab_, dense_, idx, mask_, ds_, qkv, cbuf, top)
 
 
-def _attn_backward(saved, geom, dy):
+def _attn_backward(saved, geom, dy, separate_grads=False):
     """One lewin_attn_bwd_* call on the tensors _attn_forward saved -> (dx, d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out,
     d_rpb_table, d_rpb_dense); entries of absent parameters are None."""
     (x, ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense, idx, mask, ds, qkv, cbuf, top) = saved
@@ -264,7 +267,7 @@ def _attn_backward(saved, geom, dy):
     dy = dy.contiguous()
     dx = torch.empty_like(x)
     d_ln_w, d_ln_b, d_w_qkv, d_b_qkv, d_w_out, d_b_out, d_tab, d_dense = _zero_grads(
-        (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense if tab is None else None), dev)
+        (ln_w, ln_b, w_qkv, b_qkv, w_out, b_out, tab, dense if tab is None else None), dev, separate_grads)
     fwd = _lib.LewinAttnFwdArgs(
         B=B, H=H, W=W, C=C, nH=nH, shift=shift, windowed=int(windowed), use_rpb=int(use_rpb),
         analytic_shift_mask=int(analytic), nW_mask=0 if mask is None else mask.shape[0],
@@ -347,7 +350,7 @@ def _leff_forward(y, ln_w, ln_b, w1, b1, w_dw, b_dw, w2, b2, drop_scale, geom, o
     return out, ((y, ln_w_, ln_b_, w1_, b1_, wdw_, bdw_, w2_, b2_, ds_, h1, h2, a1, a2) if need_grad else None)
 
 
-def _leff_backward(saved, geom, dout):
+def _leff_backward(saved, geom, dout, separate_grads=False):
     """One lewin_leff_bwd_* call on the tensors _leff_forward saved -> (dy, d_ln_w, d_ln_b, d_w1, d_b1, d_w_dw, d_b_dw, d_w2,
     d_b2); entries of absent parameters are None."""
     (y, ln_w, ln_b, w1, b1, wdw, bdw, w2, b2, ds, h1, h2, a1, a2) = saved
@@ -359,7 +362,7 @@ def _leff_backward(saved, geom, dout):
     hidden = w1.shape[0]
     dout = dout.contiguous()
     dy = torch.empty_like(y)
-    d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2 = _zero_grads((ln_w, ln_b, w1, b1, wdw, bdw, w2, b2), dev)
+    d_ln_w, d_ln_b, d_w1, d_b1, d_wdw, d_bdw, d_w2, d_b2 = _zero_grads((ln_w, ln_b, w1, b1, wdw, bdw, w2, b2), dev, separate_grads)
     fwd = _lib.LewinLeffFwdArgs(
         B=B, H=H, W=W, C=C, hidden=hidden, fused=int(fused), save_for_backward=1, ld_out=0,
         y=_ptr(y), out=None, ln_w=_ptr(ln_w), ln_b=_ptr(ln_b), w1=_ptr(w1), b1=_ptr(b1),

@@ -368,27 +368,45 @@ __global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const T* __restric
     }
 }
 
-template <typename T, int TX>
+__device__ __forceinline__ float2 dw_add2(const float2 a, const float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
+// USE_TMA (bf16): each tile is TWO cp.async.bulk.tensor boxes issued by thread 0 (h1 halo box, zero-filled outside the map by
+// the TMA unit = the convolution's padding; da2 interior box) completing on one mbarrier per buffer, instead of ~10 per-thread
+// 16-byte cp.async with their index arithmetic (ncu: those loops were 40 % of the kernel's instructions; the box layout
+// [row][column][64 channels] is exactly the layout the accumulation loop reads).
+template <typename T, int TX, bool USE_TMA = false>
 __global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __restrict__ da2, const T* __restrict__ h1,
                                                                   float* __restrict__ dw, float* __restrict__ dbias,
-                                                                  int B, int H, int W, int Ch) {
+                                                                  int B, int H, int W, int Ch,
+                                                                  const __grid_constant__ CUtensorMap hmap,
+                                                                  const __grid_constant__ CUtensorMap dmap) {
     constexpr int EPC = 16 / sizeof(T), SLAB = 8 * EPC, TY = 8, HX = TX + 2, HY = TY + 2, PPT = TY * TX / 32;
-    // two buffers of (h1 halo tile, da2 interior tile): the next tile arrives by cp.async while this one is accumulated
+    // two buffers of (h1 halo tile, da2 interior tile): the next tile arrives (cp.async / TMA) while this one is accumulated
     constexpr int HT_BYTES = HY * HX * 8 * 16, DT_BYTES = TY * TX * 8 * 16;
-    extern __shared__ __align__(16) unsigned char wg_smem[];
+    extern __shared__ __align__(128) unsigned char wg_smem_raw[];
+    unsigned char* const wg_smem = USE_TMA ? wg_smem_raw + ((128u - (tma::smem_u32(wg_smem_raw) & 127u)) & 127u) : wg_smem_raw;
     unsigned char* const ht0 = wg_smem;
     unsigned char* const dt0 = wg_smem + 2 * HT_BYTES;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(wg_smem + 2 * HT_BYTES + 2 * DT_BYTES);     // USE_TMA: one per buffer
     const int tid = threadIdx.x, ch = tid & 7, lane = tid >> 3;
     const int px = lane % TX, py0 = (lane / TX) * PPT;
     const int slab = blockIdx.y, c0 = slab * SLAB;
     const int tiles_x = W / TX, tiles_y = H / TY;
     const int ntiles = B * tiles_y * tiles_x;
-    float wacc[9][EPC], bacc[EPC];
+    // accumulators as fp32 pairs: the 9 taps + the bias sum cost one fma.rn.f32x2 / add.rn.f32x2 per two channels
+    // (same IEEE results as the scalar instructions, half the issue slots)
+    constexpr int EP2 = EPC / 2;
+    float2 wacc[9][EP2], bacc[EP2];
 #pragma unroll
-    for (int j = 0; j < EPC; ++j) {
-        bacc[j] = 0.f;
+    for (int j = 0; j < EP2; ++j) {
+        bacc[j] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) wacc[t][j] = 0.f;
+        for (int t = 0; t < 9; ++t) wacc[t][j] = make_float2(0.f, 0.f);
     }
     auto issue = [&](int tile, int buf) {
         int t = tile;
@@ -398,24 +416,48 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __res
         const int y0 = ty * TY - 1, x0 = tx * TX - 1;
         unsigned char* hb = ht0 + buf * HT_BYTES;
         unsigned char* db = dt0 + buf * DT_BYTES;
-        for (int i = tid; i < HY * HX * 8; i += 256) {
-            const int c = i & 7, p = i >> 3, hy = p / HX, hx = p - hy * HX;
-            const int yy = y0 + hy, xx = x0 + hx;
-            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-            const long long o = ((static_cast<long long>(b) * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * Ch + c0 + c * EPC;
-            cp_async16_zfill(hb + i * 16, h1 + o, ok);
+        if constexpr (USE_TMA) {
+            if (tid == 0) {
+                tma::mbar_expect_tx(&bars[buf], HT_BYTES + DT_BYTES);
+                tma::load_4d(hb, &hmap, &bars[buf], c0, x0, y0, b);
+                tma::load_4d(db, &dmap, &bars[buf], c0, tx * TX, ty * TY, b);
+            }
+        } else {
+            for (int i = tid; i < HY * HX * 8; i += 256) {
+                const int c = i & 7, p = i >> 3, hy = p / HX, hx = p - hy * HX;
+                const int yy = y0 + hy, xx = x0 + hx;
+                const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                const long long o = ((static_cast<long long>(b) * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * Ch + c0 + c * EPC;
+                cp_async16_zfill(hb + i * 16, h1 + o, ok);
+            }
+            for (int i = tid; i < TY * TX * 8; i += 256) {
+                const int c = i & 7, p = i >> 3, iy = p / TX, ix = p - iy * TX;
+                const long long o = ((static_cast<long long>(b) * H + ty * TY + iy) * W + tx * TX + ix) * Ch + c0 + c * EPC;
+                cp_async16(db + i * 16, da2 + o);
+            }
+            cp_async_commit();
         }
-        for (int i = tid; i < TY * TX * 8; i += 256) {
-            const int c = i & 7, p = i >> 3, iy = p / TX, ix = p - iy * TX;
-            const long long o = ((static_cast<long long>(b) * H + ty * TY + iy) * W + tx * TX + ix) * Ch + c0 + c * EPC;
-            cp_async16(db + i * 16, da2 + o);
-        }
-        cp_async_commit();
     };
     int buf = 0;
+    uint32_t bphase[2] = {0u, 0u};
+    if constexpr (USE_TMA) {
+        if (tid == 0) {
+            tma::prefetch_map(&hmap);
+            tma::prefetch_map(&dmap);
+            tma::mbar_init(&bars[0], 1);
+            tma::mbar_init(&bars[1], 1);
+            tma::fence_barrier_init();
+        }
+        __syncthreads();
+    }
     if (static_cast<int>(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        cp_async_wait<0>();
+        if constexpr (USE_TMA) {
+            tma::mbar_wait(&bars[buf], bphase[buf]);      // both boxes of this tile have landed (visible after the wait)
+            bphase[buf] ^= 1u;
+        } else {
+            cp_async_wait<0>();
+        }
         __syncthreads();               // this tile has landed; everyone is done with the other buffer
         if (tile + static_cast<int>(gridDim.x) < ntiles) issue(tile + gridDim.x, buf ^ 1);
         const unsigned char* ht = ht0 + buf * HT_BYTES;
@@ -424,8 +466,12 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __res
         for (int p = 0; p < PPT; ++p) {
             float dv[EPC];
             dw_unpack<T>(dt + (((py0 + p) * TX + px) * 8 + ch) * 16, dv);
+            float2 dv2[EP2];
 #pragma unroll
-            for (int j = 0; j < EPC; ++j) bacc[j] += dv[j];
+            for (int j = 0; j < EP2; ++j) {
+                dv2[j] = make_float2(dv[2 * j], dv[2 * j + 1]);
+                bacc[j] = dw_add2(bacc[j], dv2[j]);
+            }
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -433,7 +479,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __res
                     float hv[EPC];
                     dw_unpack<T>(ht + (((py0 + p + ky) * HX + px + kx) * 8 + ch) * 16, hv);
 #pragma unroll
-                    for (int j = 0; j < EPC; ++j) wacc[ky * 3 + kx][j] = fmaf(dv[j], hv[j], wacc[ky * 3 + kx][j]);
+                    for (int j = 0; j < EP2; ++j) dws::ffma2(wacc[ky * 3 + kx][j], dv2[j], make_float2(hv[2 * j], hv[2 * j + 1]));
                 }
         }
     }
@@ -444,7 +490,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_wgrad_kernel(const T* __res
     for (int t = 0; t < 10; ++t)
 #pragma unroll
         for (int j = 0; j < EPC; ++j) {
-            float v = t < 9 ? wacc[t][j] : bacc[j];
+            const float2 v2 = t < 9 ? wacc[t][j >> 1] : bacc[j >> 1];
+            float v = (j & 1) ? v2.y : v2.x;
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
             if ((tid & 31) < 8) red[(((tid >> 5) * 8 + ch) * 10 + t) * EPC + j] = v;
@@ -487,8 +534,23 @@ bool launch_dwconv_bwd_tiled(const T* g2, const T* a2, const T* h1, const T* a1,
         const int ntiles = B * (H / 8) * (W / 16);
         int gx = (2 * num_sms + slabs - 1) / slabs; if (gx > ntiles) gx = ntiles;
         constexpr int wg_smem16 = 2 * (10 * (16 + 2) * 128 + 8 * 16 * 128);
-        cudaFuncSetAttribute(dwconv_bwd_wgrad_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem16);
-        dwconv_bwd_wgrad_kernel<T, 16><<<dim3(gx, slabs), 256, wg_smem16, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);
+        CUtensorMap hmap{}, dmap{};
+        bool tma_done = false;
+        if constexpr (Act<T>::kIsBf16) {
+            static const bool tma_on = [] { const char* e = getenv("LEWIN_NO_TMA"); return !(e && e[0] == '1'); }();
+            if (tma_on && tma::make_nhwc_bf16(&hmap, h1, B, H, W, Ch, 10, 18, SLAB) &&
+                tma::make_nhwc_bf16(&dmap, da2_scratch, B, H, W, Ch, 8, 16, SLAB)) {
+                constexpr int smem_tma = wg_smem16 + 128 /*alignment*/ + 16 /*mbarriers*/;
+                cudaFuncSetAttribute(dwconv_bwd_wgrad_kernel<T, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tma);
+                dwconv_bwd_wgrad_kernel<T, 16, true><<<dim3(gx, slabs), 256, smem_tma, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch,
+                                                                                          hmap, dmap);
+                tma_done = true;
+            }
+        }
+        if (!tma_done) {
+            cudaFuncSetAttribute(dwconv_bwd_wgrad_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem16);
+            dwconv_bwd_wgrad_kernel<T, 16><<<dim3(gx, slabs), 256, wg_smem16, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch, hmap, dmap);
+        }
     } else {
         const unsigned grid = static_cast<unsigned>(B) * (H / 8) * (W / 8) * slabs;
         constexpr int smem8 = 2 * 10 * 10 * 128 + 9 * SLAB * 4 + kGeluTabSize * 2;
@@ -498,7 +560,8 @@ bool launch_dwconv_bwd_tiled(const T* g2, const T* a2, const T* h1, const T* a1,
         int gx = (2 * num_sms + slabs - 1) / slabs; if (gx > ntiles) gx = ntiles;
         constexpr int wg_smem8 = 2 * (10 * (8 + 2) * 128 + 8 * 8 * 128);
         cudaFuncSetAttribute(dwconv_bwd_wgrad_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem8);
-        dwconv_bwd_wgrad_kernel<T, 8><<<dim3(gx, slabs), 256, wg_smem8, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch);
+        CUtensorMap unused{};
+        dwconv_bwd_wgrad_kernel<T, 8><<<dim3(gx, slabs), 256, wg_smem8, st>>>(da2_scratch, h1, dw, dbias, B, H, W, Ch, unused, unused);
     }
     *err = cudaGetLastError();
     return true;

@@ -126,8 +126,12 @@ def test_compiled_block_is_traced_onto_the_custom_ops_and_matches_eager(dtype):
     assert sorted(g_c) == sorted(g_e)
     tol = 1e-4 if dtype == torch.float32 else 2e-2       # weight gradients are summed with atomics (order varies)
     assert float((dx_c.float() - dx_e.float()).abs().max()) <= tol * float(dx_e.float().abs().max())
+    gscale = max(float(v.abs().max()) for v in g_e.values())
+
+    def close(a, b, k):          # the key bias' gradient is analytically zero (rounding noise): floor every scale at 1e-3 of the largest
+        return float((a - b).abs().max()) <= tol * max(float(b.abs().max()), 1e-3 * gscale)
     for k in g_e:
-        assert float((g_c[k] - g_e[k]).abs().max()) <= tol * max(float(g_e[k].abs().max()), 1e-6), k
+        assert close(g_c[k], g_e[k], k), k
 
     # aot_eager traces forward AND backward ahead of time through the fake implementations
     torch._dynamo.reset()
@@ -135,7 +139,7 @@ def test_compiled_block_is_traced_onto_the_custom_ops_and_matches_eager(dtype):
     assert torch.equal(out_a, out_e)
     assert float((dx_a.float() - dx_e.float()).abs().max()) <= tol * float(dx_e.float().abs().max())
     for k in g_e:
-        assert float((g_a[k] - g_e[k]).abs().max()) <= tol * max(float(g_e[k].abs().max()), 1e-6), k
+        assert close(g_a[k], g_e[k], k), k
 
 
 @pytest.mark.gpu

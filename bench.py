@@ -297,6 +297,18 @@ def main():
             graphs[dt] = fullres.GraphedForward(model, ex, idx, torch.bfloat16 if dt == "bf16" else None)
         return graphs[dt]
 
+    lane_graphs = {}
+
+    def graphed_lanes(dt):
+        """`--lanes` graphs of the same forward (own static buffers each): TiledPipeline keeps that many images in flight."""
+        g0 = graphed_for(dt)
+        if g0 is None or args.lanes <= 1:
+            return g0
+        if dt not in lane_graphs:
+            lane_graphs[dt] = [g0] + [fullres.GraphedForward(model, torch.zeros_like(g0.x), idx, torch.bfloat16 if dt == "bf16" else None)
+                                      for _ in range(args.lanes - 1)]
+        return lane_graphs[dt]
+
     def forward(img):
         g = graphed_for(cur_dtype[0])
         if g is None and cur_dtype[0] == "bf16":
@@ -330,9 +342,9 @@ def main():
 
     def step_resident():
         dt = cur_dtype[0]
-        if world > 1 and not args.no_graph and ops.KernelTimer.active is None:
+        if (world > 1 or args.lanes > 1) and not args.no_graph and ops.KernelTimer.active is None:
             if dt not in tpipes:
-                tpipes[dt] = fullres.TiledPipeline(model, graphed_for(dt), (1, 3, IMG_H, IMG_W), dev, ps=PS,
+                tpipes[dt] = fullres.TiledPipeline(model, graphed_lanes(dt), (1, 3, IMG_H, IMG_W), dev, ps=PS,
                                                    dtype=torch.bfloat16 if dt == "bf16" else torch.float32)
             return tpipes[dt].submit(img_dev, idx)[0]
         return forward(img_dev)
@@ -359,7 +371,7 @@ def main():
         if args.no_graph or ops.KernelTimer.active is not None:
             return forward(x).float()
         if dt not in e2e_pipes:
-            e2e_pipes[dt] = fullres.TiledPipeline(model, graphed_for(dt), (1, 3, IMG_H, IMG_W), dev, ps=PS)
+            e2e_pipes[dt] = fullres.TiledPipeline(model, graphed_lanes(dt), (1, 3, IMG_H, IMG_W), dev, ps=PS)
         return e2e_pipes[dt].submit(x, idx)
 
     pipe = fullres.StreamingDehazer(e2e_fn, (1, 3, IMG_H, IMG_W), dev, rows=rows, download=(rank == 0))
@@ -376,15 +388,22 @@ def main():
     if rank == 0:
         sampler.start()
     n0 = lib.lewin_launch_count()
-    if world > 1:                      # the pipelined form must reproduce the serial call bit for bit
-        a = step_resident().clone(); finish_resident(); torch.cuda.synchronize()
-        assert torch.equal(a, forward(img_dev)), "TiledPipeline differs from dehaze_tiled"
+    if tpipes:                         # the pipelined form must reproduce the serial call bit for bit, on every lane
+        want = forward(img_dev).clone()
+        for _ in range(max(2, args.lanes)):
+            tp = tpipes[cur_dtype[0]]
+            k = tp.i % tp.depth
+            tp.out[k].zero_()              # the slot still holds an earlier (identical) result: make the check mean something
+            torch.cuda.synchronize()
+            a = step_resident(); finish_resident(); torch.cuda.synchronize()
+            assert torch.equal(a, want), "TiledPipeline differs from dehaze_tiled"
     ms_total = timed(step_resident, args.steps, finish=finish_resident)
     launches = lib.lewin_launch_count() - n0
     if args.dtype in graphs:          # graph replay: the captured library launches run once per replay
         launches += graphs[args.dtype].launches_per_replay * args.steps
     ms_e2e = timed(step_e2e, args.steps, finish=pipe.flush)
     ms_e2e_serial = timed(step_e2e_serial, args.steps)
+    ms_one = timed(lambda: forward(img_dev), args.steps)          # the serial call: one image at a time on one stream
     # second pass with per-kernel events (roofline of the dominant kernel type)
     with ops.KernelTimer() as kt:
         timed(step_resident, args.steps)
@@ -526,9 +545,15 @@ def main():
                    "leff": "C <= 64 levels: linear1 + GELU kernel, then ONE kernel for depthwise conv + GELU -> tcgen05.mma linear2 -> residual (h2 stays on chip); C >= 128: three kernels",
                    "attention": "C <= 64 levels: ONE fused kernel per block (LN1 -> q|k|v tcgen05.mma -> TMEM -> ProbSparse core -> out tcgen05.mma -> residual); C >= 128: three kernels",
                    "launch": "python launches" if args.no_graph else "CUDA graph replay of the per-rank tile-batch forward",
-                   "pipeline": ("N > 1: fullres.TiledPipeline - the forward of image i+1 overlaps the all_gather + stitch of image i on a side stream "
-                                "(bit-identical to the serial call, asserted before timing)" if (world > 1 and not args.no_graph) else
+                   "pipeline": ((f"fullres.TiledPipeline, {args.lanes} lane(s): image i runs on lane i mod {args.lanes} (own CUDA graph, own stream), so "
+                                 f"{args.lanes} forwards are in flight and one image's under-filled deep-level kernels share the SMs with the other's; "
+                                 "the all_gather + stitch of an image run on a side stream under the following forwards; every one of the K timed "
+                                 "steps is a whole image, started and finished inside the timed region; every lane's output is asserted "
+                                 "bit-identical to the serial call before timing") if ((world > 1 or args.lanes > 1) and not args.no_graph) else
                                 "serial: gather indices -> forward -> stitch on one stream"),
+                   "images_in_flight": args.lanes if ((world > 1 or args.lanes > 1) and not args.no_graph) else 1,
+                   "one_in_flight": {"value": 1e3 / (ms_one / args.steps), "ms_per_step": ms_one / args.steps,
+                                     "note": "fullres.dehaze_tiled, one image at a time on one stream (= the latency of an image)"},
                    "lewin_compute": "3xTF32 (fp32-grade): the four linears on tcgen05.mma kind::tf32 (hi/lo split in the producer warps, TMEM), mma.sync ProbSparse core" if args.dtype == "f32" else
                                     "bf16 operands, fp32 accumulate: warp-specialised tcgen05 GEMMs (TMEM, TMA at C >= 256), mma.sync ProbSparse core, TMA-fed depthwise conv"},
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "images/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,

@@ -208,12 +208,27 @@ class TiledPipeline:
     the collective and the stitching of every image (0.3 of 3.2 ms).  Here the forward of image i+1 (compute stream) overlaps the
     gather + stitch of image i (side stream): `submit` returns the restored image of ITS input and the event that marks it
     complete; results cycle through `depth` preallocated slots.  Same kernels, same order of operations per image, so the
-    output is bit-identical to `dehaze_tiled(model, img, graphed=graphed, broadcast_index_samples=False)`."""
+    output is bit-identical to `dehaze_tiled(model, img, graphed=graphed, broadcast_index_samples=False)`.
+
+    `graphed` may be a LIST of GraphedForward objects of the same model and shape ("lanes", each with its own static buffers):
+    image i then runs on lane i mod len(lanes), every lane on its own stream, so two forwards are in flight and the kernels of
+    one fill the SMs the other leaves idle (the deep levels of a small shard launch 11-88 CTAs for 148 SMs; the persistent
+    one-CTA-per-SM kernels cannot share an SM, the under-filled ones can).  Measured on one B200 (scripts/two_in_flight.py):
+    +3.6 % images/s at 169 tiles, +4.9 % at 85, +6.8 % at 43, +9.3 % at 22 (the 8-GPU shard); latency per image unchanged,
+    every image computed by the same kernels in the same order (bit-identical).  The caller's stream only waits for a lane to
+    have READ its input image (so the input buffer may be refilled once the caller's stream has passed `submit`, as before)."""
 
     def __init__(self, model, graphed, shape, device, ps=128, group=None, depth=2, dtype=torch.float32):
         import torch.distributed as dist
         B, C, H, W = shape
         assert B == 1
+        lanes = list(graphed) if isinstance(graphed, (list, tuple)) else [graphed]
+        if len(lanes) > 1:
+            assert all(g is not None for g in lanes)
+            depth = max(depth, 2 * len(lanes))                   # a multiple of the caller's ring depth (StreamingDehazer: 2)
+        graphed = lanes[0]
+        self.lanes = lanes
+        self.lane_streams = [torch.cuda.Stream(device=device) for _ in lanes] if len(lanes) > 1 else None
         self.model, self.graphed, self.group, self.depth = model, graphed, group, depth
         if graphed is not None:
             dtype = graphed.y.dtype                              # the captured forward's output dtype (bf16 under autocast)
@@ -227,6 +242,7 @@ class TiledPipeline:
         self.out = [torch.empty((1, C, H, W), dtype=dtype, device=device) for _ in range(depth)]
         self.ev_fwd = [torch.cuda.Event() for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_read = [torch.cuda.Event() for _ in range(depth)]
         self.used = [False] * depth
         self.post = torch.cuda.Stream(device=device)
         self.i = 0
@@ -238,12 +254,26 @@ class TiledPipeline:
         k = self.i % self.depth
         self.i += 1
         cur = torch.cuda.current_stream(img.device)
-        if self.used[k]:
-            cur.wait_event(self.ev_done[k])                      # the slot's previous image has been gathered and stitched
-        mine = img.reshape(-1).index_select(0, self.in_idx).view(self.n, C, ps, ps)
-        out = self.graphed(mine, index_samples) if self.graphed is not None else self.model(mine, index_samples=index_samples)
-        self.padded[k][:self.n].copy_(out)                       # (the graph's static output is overwritten by the next replay)
-        self.ev_fwd[k].record(cur)
+        if self.lane_streams is not None:
+            j = (self.i - 1) % len(self.lanes)
+            ls = self.lane_streams[j]
+            ls.wait_stream(cur)                                  # the caller produced img on its stream
+            with torch.cuda.stream(ls):
+                if self.used[k]:
+                    ls.wait_event(self.ev_done[k])               # the slot's previous image has been gathered and stitched
+                mine = img.reshape(-1).index_select(0, self.in_idx).view(self.n, C, ps, ps)
+                self.ev_read[k].record(ls)
+                out = self.lanes[j](mine, index_samples)
+                self.padded[k][:self.n].copy_(out)
+                self.ev_fwd[k].record(ls)
+            cur.wait_event(self.ev_read[k])                      # img may be overwritten once the caller's stream passed here
+        else:
+            if self.used[k]:
+                cur.wait_event(self.ev_done[k])                  # the slot's previous image has been gathered and stitched
+            mine = img.reshape(-1).index_select(0, self.in_idx).view(self.n, C, ps, ps)
+            out = self.graphed(mine, index_samples) if self.graphed is not None else self.model(mine, index_samples=index_samples)
+            self.padded[k][:self.n].copy_(out)                   # (the graph's static output is overwritten by the next replay)
+            self.ev_fwd[k].record(cur)
         with torch.cuda.stream(self.post):
             self.post.wait_event(self.ev_fwd[k])
             src = self.padded[k]

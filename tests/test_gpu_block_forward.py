@@ -323,6 +323,58 @@ def test_tiled_pipeline_matches_the_serial_call(dt):
         assert torch.equal(b, r.float().cpu())
 
 
+def test_tiled_pipeline_with_two_images_in_flight_matches_the_serial_call():
+    """TiledPipeline with two lanes (two CUDA graphs on two streams: image i on lane i mod 2, both forwards in flight) returns,
+    image for image, exactly what the serial dehaze_tiled returns: 9 different images back to back without any host wait
+    exercise the 4-slot result ring, both lanes' static buffers and the input hand-over (the input buffer is REUSED and
+    overwritten right after each submit, as StreamingDehazer does); then the same under StreamingDehazer from host memory."""
+    import lewin_b200 as L
+    from lewin_b200 import fullres
+    dev = torch.device("cuda:0")
+    torch.manual_seed(18)
+    model = L.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff").to(dev).eval()
+    idx = model.draw_index_samples()
+    H, W = 200, 300                                           # canvas 384^2 = 9 tiles
+    imgs = [torch.rand(1, 3, H, W, device=dev) for _ in range(9)]
+    lanes = [fullres.GraphedForward(model, torch.zeros(9, 3, 128, 128, device=dev), idx, torch.bfloat16) for _ in range(2)]
+    with torch.autocast("cuda", torch.bfloat16):
+        refs = [fullres.dehaze_tiled(model, x, ps=128, index_samples=idx, graphed=lanes[0], broadcast_index_samples=False).clone()
+                for x in imgs]
+    assert not torch.equal(refs[0], refs[1])
+    pipe = fullres.TiledPipeline(model, lanes, (1, 3, H, W), dev)
+    assert pipe.depth == 4 and len(pipe.lane_streams) == 2
+    buf = torch.empty_like(imgs[0])                           # one input buffer, overwritten after every submit
+    got = []
+    cur = torch.cuda.current_stream(dev)
+    for x in imgs:
+        buf.copy_(x)
+        out, ev = pipe.submit(buf, idx)
+        buf.fill_(float("nan"))                               # legal: the caller's stream has passed submit()
+        cur.wait_event(ev)
+        got.append(out.clone())                               # consumer on the caller's stream, ordered by the event only
+    pipe.flush()
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(got, refs)):
+        assert a.dtype == b.dtype and torch.equal(a, b), i
+    # no consumer in between: 4 results stay valid in the 4-slot ring
+    outs = [pipe.submit(x, idx)[0] for x in imgs[:4]]
+    pipe.flush()
+    torch.cuda.synchronize()
+    for o, b in zip(outs, refs[:4]):
+        assert torch.equal(o, b)
+    # under StreamingDehazer (2-slot host ring over the 4-slot device ring)
+    pipe2 = fullres.TiledPipeline(model, lanes, (1, 3, H, W), dev)
+    sd = fullres.StreamingDehazer(lambda x: pipe2.submit(x, idx), (1, 3, H, W), dev)
+    hosts = [x.cpu().pin_memory() for x in imgs]
+    res = [torch.empty(1, 3, H, W).pin_memory() for _ in imgs]
+    for a, b in zip(hosts, res):
+        sd.submit(a, b)
+    sd.flush()
+    torch.cuda.synchronize()
+    for i, (b, r) in enumerate(zip(res, refs)):
+        assert torch.equal(b, r.float().cpu()), i
+
+
 def test_full_size_tile_batch_invariance_bf16():
     """BASELINE config 3 at its full size (1200x1600 -> 1664^2 canvas -> 169 tiles), bf16: size-independent properties of
     the tiled computation.  (1) Determinism: two runs are bit-identical.  (2) Shard invariance: tiles are independent

@@ -246,6 +246,9 @@ def main():
                          "inference precision, always reported as well under 'fp32')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="images in flight per rank in the serving pipeline (fullres.TiledPipeline lanes: one CUDA graph and one "
+                         "stream each; 1 = one forward at a time)")
     ap.add_argument("--no-train-step", action="store_true", help="skip the config 2 / 4 training-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -246,6 +246,9 @@ def main():
                          "inference precision, always reported as well under 'fp32')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--e2e-lanes", type=int, default=0,
+                    help="lanes of the end-to-end (host to host) pipeline; 0 = --lanes on one GPU, 1 on several (measured: with the "
+                         "all_gather and the partial uploads in the loop two lanes were slower end to end at 2 GPUs)")
     ap.add_argument("--lanes", type=int, default=2,
                     help="images in flight per rank in the serving pipeline (fullres.TiledPipeline lanes: one CUDA graph and one "
                          "stream each; 1 = one forward at a time)")
@@ -366,6 +369,7 @@ def main():
     # gathered result to the host; `e2e.serial_value` keeps the naive form (every rank moves the whole image both ways).
     rows = fullres.rows_needed(IMG_H, IMG_W, rank, world) if world > 1 else None
     e2e_pipes = {}
+    e2e_lanes = args.e2e_lanes if args.e2e_lanes > 0 else (args.lanes if world == 1 else 1)
 
     def e2e_fn(x):
         """The device stage of the streaming call: staged (fullres.TiledPipeline: gather + stitch on a side stream, the fp32
@@ -374,7 +378,8 @@ def main():
         if args.no_graph or ops.KernelTimer.active is not None:
             return forward(x).float()
         if dt not in e2e_pipes:
-            e2e_pipes[dt] = fullres.TiledPipeline(model, graphed_lanes(dt), (1, 3, IMG_H, IMG_W), dev, ps=PS)
+            e2e_pipes[dt] = fullres.TiledPipeline(model, graphed_lanes(dt) if e2e_lanes > 1 else graphed_for(dt),
+                                                  (1, 3, IMG_H, IMG_W), dev, ps=PS)
         return e2e_pipes[dt].submit(x, idx)
 
     pipe = fullres.StreamingDehazer(e2e_fn, (1, 3, IMG_H, IMG_W), dev, rows=rows, download=(rank == 0))
@@ -559,7 +564,7 @@ def main():
                                      "note": "fullres.dehaze_tiled, one image at a time on one stream (= the latency of an image)"},
                    "lewin_compute": "3xTF32 (fp32-grade): the four linears on tcgen05.mma kind::tf32 (hi/lo split in the producer warps, TMEM), mma.sync ProbSparse core" if args.dtype == "f32" else
                                     "bf16 operands, fp32 accumulate: warp-specialised tcgen05 GEMMs (TMEM, TMA at C >= 256), mma.sync ProbSparse core, TMA-fed depthwise conv"},
-        "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "images/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
+        "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "images/s", "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "images_in_flight": e2e_lanes,
                 "mode": "fullres.StreamingDehazer over fullres.TiledPipeline: pinned host image -> H2D -> tile gather / forward -> (side stream) all_gather / stitch / crop -> D2H every step; the "
                         "copies run on side streams and overlap the neighbouring steps' compute (double-buffered); at N > 1 each rank uploads "
                         "only the image rows its tiles read and rank 0 downloads the gathered result (bytes = sum over ranks)",

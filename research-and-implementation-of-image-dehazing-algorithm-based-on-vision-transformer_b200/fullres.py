@@ -140,9 +140,33 @@ class GraphedForward:
             raise RuntimeError("GraphedForward: the model's parameters were modified in place after the capture "
                                "(the graph holds bf16 weight images of that moment); build a new GraphedForward")
         self.x.copy_(tiles, non_blocking=True)
-        self.idx.copy_(index_samples.to(dtype=torch.int32), non_blocking=True)
+        self._load_index_samples(index_samples)
         self.graph.replay()
         return self.y
+
+    def _load_index_samples(self, index_samples):
+        """Refresh the graph's static key-sample indices.  A copy from PAGEABLE host memory makes the host wait for everything
+        queued on the stream (cudaMemcpyAsync semantics), i.e. for the previous forward and whatever it waits on - the serving
+        loop could never run ahead of the device.  So: the same draw as last time (same tensor, same version) is not copied
+        again, a device tensor is copied device to device, and a new host draw goes through a small ring of pinned buffers."""
+        key = (id(index_samples), index_samples._version, index_samples.data_ptr())
+        if key == getattr(self, "_idx_key", None) and getattr(self, "_idx_ref", lambda: None)() is index_samples:
+            return
+        import weakref
+        if index_samples.is_cuda:
+            self.idx.copy_(index_samples.to(dtype=torch.int32), non_blocking=True)
+        else:
+            if not hasattr(self, "_idx_ring"):
+                self._idx_ring = [(torch.empty(self.idx.shape, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+                self._idx_ring_pos = 0
+            buf, ev = self._idx_ring[self._idx_ring_pos % 4]
+            if self._idx_ring_pos >= 4:
+                ev.synchronize()                                   # the copy that last read this pinned buffer (4 calls ago) is done
+            self._idx_ring_pos += 1
+            buf.copy_(index_samples)                               # host -> pinned host (int64 -> int32), no device involvement
+            self.idx.copy_(buf, non_blocking=True)
+            ev.record(torch.cuda.current_stream(self.idx.device))
+        self._idx_key, self._idx_ref = key, weakref.ref(index_samples)
 
 
 @torch.no_grad()

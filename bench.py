@@ -247,8 +247,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--e2e-lanes", type=int, default=0,
-                    help="lanes of the end-to-end (host to host) pipeline; 0 = --lanes on one GPU, 1 on several (measured: with the "
-                         "all_gather and the partial uploads in the loop two lanes were slower end to end at 2 GPUs)")
+                    help="lanes of the end-to-end (host to host) pipeline; 0 = the same as --lanes")
     ap.add_argument("--lanes", type=int, default=2,
                     help="images in flight per rank in the serving pipeline (fullres.TiledPipeline lanes: one CUDA graph and one "
                          "stream each; 1 = one forward at a time)")
@@ -369,7 +368,7 @@ def main():
     # gathered result to the host; `e2e.serial_value` keeps the naive form (every rank moves the whole image both ways).
     rows = fullres.rows_needed(IMG_H, IMG_W, rank, world) if world > 1 else None
     e2e_pipes = {}
-    e2e_lanes = args.e2e_lanes if args.e2e_lanes > 0 else (args.lanes if world == 1 else 1)
+    e2e_lanes = args.e2e_lanes if args.e2e_lanes > 0 else args.lanes
 
     def e2e_fn(x):
         """The device stage of the streaming call: staged (fullres.TiledPipeline: gather + stitch on a side stream, the fp32

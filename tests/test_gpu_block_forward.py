@@ -362,17 +362,19 @@ def test_tiled_pipeline_with_two_images_in_flight_matches_the_serial_call():
     torch.cuda.synchronize()
     for o, b in zip(outs, refs[:4]):
         assert torch.equal(o, b)
-    # under StreamingDehazer (2-slot host ring over the 4-slot device ring)
-    pipe2 = fullres.TiledPipeline(model, lanes, (1, 3, H, W), dev)
-    sd = fullres.StreamingDehazer(lambda x: pipe2.submit(x, idx), (1, 3, H, W), dev)
+    # under StreamingDehazer: a 2-slot host ring over the 4-slot device ring, and a 4-slot host ring in lockstep with it
+    # (what bench.py's e2e uses with two lanes)
     hosts = [x.cpu().pin_memory() for x in imgs]
-    res = [torch.empty(1, 3, H, W).pin_memory() for _ in imgs]
-    for a, b in zip(hosts, res):
-        sd.submit(a, b)
-    sd.flush()
-    torch.cuda.synchronize()
-    for i, (b, r) in enumerate(zip(res, refs)):
-        assert torch.equal(b, r.float().cpu()), i
+    for host_depth in (2, 4):
+        pipe2 = fullres.TiledPipeline(model, lanes, (1, 3, H, W), dev)
+        sd = fullres.StreamingDehazer(lambda x: pipe2.submit(x, idx), (1, 3, H, W), dev, depth=host_depth)
+        res = [torch.empty(1, 3, H, W).pin_memory() for _ in imgs]
+        for a, b in zip(hosts, res):
+            sd.submit(a, b)
+        sd.flush()
+        torch.cuda.synchronize()
+        for i, (b, r) in enumerate(zip(res, refs)):
+            assert torch.equal(b, r.float().cpu()), (host_depth, i)
 
 
 def test_full_size_tile_batch_invariance_bf16():

@@ -381,10 +381,9 @@ def main():
                                                   (1, 3, IMG_H, IMG_W), dev, ps=PS)
         return e2e_pipes[dt].submit(x, idx)
 
-    # the host ring is as deep as the device ring of the lanes (2 x lanes): with two forwards in flight a 2-slot host ring would
-    # hold image n back until image n-2 has been stitched, converted and downloaded (measured at 8 GPUs: e2e 282 vs value 344)
-    pipe = fullres.StreamingDehazer(e2e_fn, (1, 3, IMG_H, IMG_W), dev, rows=rows, download=(rank == 0),
-                                    depth=2 * e2e_lanes if (e2e_lanes > 1 and not args.no_graph) else 2)
+    # (a host ring as deep as the lanes' 4-slot device ring was measured: no change on one GPU - 60.0 images/s end to end - and
+    # SLOWER on two, 81 against 105 images/s, so the host ring keeps its two slots)
+    pipe = fullres.StreamingDehazer(e2e_fn, (1, 3, IMG_H, IMG_W), dev, rows=rows, download=(rank == 0))
 
     def step_e2e():
         pipe.submit(img_host, out_host)

@@ -94,6 +94,16 @@ COMPACT_CASES = [
 ]
 
 
+# head_dim = embed_dim 64 / 128 (My_model_1.py:962 makes head_dim = embed_dim; BASELINE config 5 sweeps embed_dim 32-128):
+# the same compact recording for a one-head C = 64 block, a two-head C = 128 block (head_dim 64) and a one-head C = 128 block
+# (head_dim 128), so those kernel instances are pinned to the unmodified reference as well, forward and backward.
+HEAD_DIM_CASES = [
+    ("block_c64_h1_s4_hd64_compact", 64, 1, 16, 2, 4, False, 0.0, False),
+    ("block_c128_h2_s0_hd64_compact", 128, 2, 8, 3, 0, False, 0.0, False),
+    ("block_c128_h1_s4_hd128_compact", 128, 1, 16, 1, 4, False, 0.0, False),
+]
+
+
 def grad_sample_ids(key, n, seed, k=4096):
     import zlib
     rng = np.random.default_rng([seed, zlib.crc32(key.encode()), 7])
@@ -325,6 +335,9 @@ def main():
     if only in ("", "compact"):
         for i, case in enumerate(COMPACT_CASES):
             make_block_case(ref, *case, seed=500 + 10 * i, compact=True)
+    if only in ("", "headdim"):
+        for i, case in enumerate(HEAD_DIM_CASES):
+            make_block_case(ref, *case, seed=700 + 10 * i, compact=True)
     if only in ("", "bf16"):
         for i, case in enumerate(BF16_CASES):
             make_bf16_case(ref, *case, seed=900 + 10 * i)

@@ -71,8 +71,8 @@ def test_block_backward_matches_reference_golden_f32(name):
 
 @pytest.mark.parametrize("name", COMPACT_FIXTURES)
 def test_deep_level_block_matches_reference_golden_f32(name):
-    """C = 256 (8 heads, shift 4) and C = 512 (16 heads) blocks against the unmodified reference's recording (compact
-    fixtures): output within 1e-3, identical top-u sets, dx and all 19 parameter gradients (sampled elements + L2 norms)
+    """C = 256 (8 heads, shift 4) and C = 512 (16 heads) blocks, and head_dim 64 / 128 blocks (C = 64 one head, C = 128 two heads /
+    one head: the reference's embed_dim 64 / 128 variants), against the unmodified reference's recording (compact fixtures): output within 1e-3, identical top-u sets, dx and all 19 parameter gradients (sampled elements + L2 norms)
     within 1e-3 of each gradient's scale."""
     fx = load_fixture(name)
     dev = torch.device("cuda:0")

@@ -35,7 +35,7 @@ def test_oracle_forward_backward_matches_reference(name, dtype):
 
 @pytest.mark.parametrize("name", COMPACT_FIXTURES)
 def test_oracle_matches_reference_at_deep_levels(name):
-    """C = 256 / 512 blocks (8 / 16 heads) recorded from the unmodified reference, compact fixtures: forward, dx, the
+    """C = 256 / 512 blocks (8 / 16 heads) and head_dim 64 / 128 blocks recorded from the unmodified reference, compact fixtures: forward, dx, the
     selected query sets and all 19 parameter gradients (sampled elements + norms)."""
     fx = load_fixture(name)
     p = O.as_dtype(fx["params"], np.float64)

@@ -13,7 +13,9 @@ BLOCK_FIXTURES = ["block_c32_h1_s0", "block_c32_h1_s4", "block_c64_h2_s4", "bloc
 
 # deep levels, stored compactly (oracle/make_golden.py COMPACT_CASES): parameters regenerated from the seed, parameter
 # gradients as L2 norm + a seeded sample of <= 4096 elements
-COMPACT_FIXTURES = ["block_c256_h8_s4_compact", "block_c512_h16_s0_compact"]
+COMPACT_FIXTURES = ["block_c256_h8_s4_compact", "block_c512_h16_s0_compact",
+                    # head_dim = embed_dim 64 / 128 (My_model_1.py:962; BASELINE config 5), oracle/make_golden.py HEAD_DIM_CASES
+                    "block_c64_h1_s4_hd64_compact", "block_c128_h2_s0_hd64_compact", "block_c128_h1_s4_hd128_compact"]
 
 # the UNMODIFIED reference under torch.autocast("cpu", bfloat16) (oracle/make_golden.py BF16_CASES): x, out, idx, top
 BF16_REF_FIXTURES = ["block_c64_h2_s4_bf16cpu", "block_c256_h8_s4_bf16cpu"]

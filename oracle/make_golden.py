@@ -251,10 +251,11 @@ def make_bf16_case(ref, name, C, nH, hw, B, shift, seed):
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **save)
 
 
-def make_model_case(ref, name, B, seed, mask=False):
-    """Uformer(img_size=128, embed_dim=32) forward, config 1 of BASELINE.json (B tiles)."""
+def make_model_case(ref, name, B, seed, mask=False, embed_dim=32):
+    """Uformer(img_size=128, embed_dim=32) forward, config 1 of BASELINE.json (B tiles); embed_dim 64: the head_dim 64 variant
+    (My_model_1.py:962), C = 64 ... 1024."""
     torch.manual_seed(seed)
-    model = ref.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff")
+    model = ref.Uformer(img_size=128, embed_dim=embed_dim, win_size=8, token_projection="linear", token_mlp="leff")
     param_fill.fill_module(model, seed)
     model.eval()
     g = torch.Generator().manual_seed(seed + 1)
@@ -270,9 +271,10 @@ def make_model_case(ref, name, B, seed, mask=False):
         seed=np.int64(seed), n_keys=np.int64(len(keys)),
         key_crc=np.int64(__import__("zlib").crc32("\n".join(
             f"{k}:{tuple(model.state_dict()[k].shape)}" for k in keys).encode())))
-    with open(os.path.join(GOLD, "uformer32_state_dict_keys.txt"), "w") as f:
-        for k in keys:
-            f.write(f"{k} {tuple(model.state_dict()[k].shape)} {str(model.state_dict()[k].dtype).replace('torch.', '')}\n")
+    if embed_dim == 32:
+        with open(os.path.join(GOLD, "uformer32_state_dict_keys.txt"), "w") as f:
+            for k in keys:
+                f.write(f"{k} {tuple(model.state_dict()[k].shape)} {str(model.state_dict()[k].dtype).replace('torch.', '')}\n")
     print(f"{name}: out range [{y.min():.3f}, {y.max():.3f}], |y-x| max {np.abs((y - x).numpy()).max():.3f}")
 
 
@@ -345,6 +347,8 @@ def main():
         make_canvas_case(ref, "uformer32_canvas_200x300", 200, 300, seed=4321)
     if only in ("", "model"):
         make_model_case(ref, "uformer32_b2", B=2, seed=1234)
+    if only in ("", "model64"):
+        make_model_case(ref, "uformer64_b1", B=1, seed=2345, embed_dim=64)
 
 
 if __name__ == "__main__":

@@ -157,8 +157,10 @@ def test_numeric_gradient_spot_check():
         assert abs(num - g[k][r, 0]) < 1e-5 * max(1.0, abs(num))
 
 
-def test_torch_port_matches_reference_golden_whole_model(golden_dir):
-    """oracle/torch_port.py is the denominator of every cpu_baseline / --impl reference number bench.py prints: its whole-model
+@pytest.mark.parametrize("embed_dim,name", [(32, "uformer32_b2"), (64, "uformer64_b1")])
+def test_torch_port_matches_reference_golden_whole_model(golden_dir, embed_dim, name):
+    """(embed_dim 64 = the reference's head_dim 64 variant, My_model_1.py:962: C = 64 ... 1024, one recorded tile.)
+    oracle/torch_port.py is the denominator of every cpu_baseline / --impl reference number bench.py prints: its whole-model
     forward must reproduce the UNMODIFIED reference's recorded output (tests/golden/uformer32_b2.npz, written by
     oracle/make_golden.py from /root/reference) on the same weights and the same 18 key-sample draws.  The port runs the
     reference's own ATen op sequence, so the only slack is near-tie top-u rows (none at fp32 accuracy on this fixture)."""
@@ -166,13 +168,14 @@ def test_torch_port_matches_reference_golden_whole_model(golden_dir):
     import torch
     import lewin_b200 as L
     from oracle import param_fill, torch_port
-    z = np.load(os.path.join(golden_dir, "uformer32_b2.npz"))
-    model = L.Uformer(img_size=128, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff")
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = L.Uformer(img_size=128, embed_dim=embed_dim, win_size=8, token_projection="linear", token_mlp="leff")
     param_fill.fill_module(model, int(z["seed"]))
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     with torch.no_grad():
         out = torch_port.uformer_forward(torch.from_numpy(z["x"]), sd, torch.from_numpy(z["idx"].astype(np.int64)))
     e = (out - torch.from_numpy(z["y"])).abs()
-    print(f"torch_port vs reference: max {float(e.max()):.3e} median {float(e.median()):.3e}")
-    assert float(e.median()) < 1e-5
-    assert float((e > 1e-3).float().mean()) < 1e-3
+    scale = max(1.0, float(np.abs(z["y"]).max()))
+    print(f"torch_port vs reference ({name}): max {float(e.max()):.3e} median {float(e.median()):.3e} (output scale {scale:.2f})")
+    assert float(e.median()) < 1e-5 * scale
+    assert float((e > 1e-3 * scale).float().mean()) < 1e-3

@@ -246,12 +246,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_fused_kernel(const GemmArgs
 // (nn.LayerNorm, My_model_1.py:769/776).  G lanes per row (G = min(32, row bytes / 16)), 16-byte loads, so a warp
 // streams 512 contiguous bytes per load whatever C is; two-pass statistics from registers.  HBM-bound: C*sizeof(T)
 // bytes per token.
-template <typename T, int G>
+template <typename T, int G, int MAXV = 4>          // MAXV loads per lane: C <= G * EPL * MAXV
 __global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, long long rows, int C,
                                                        float* __restrict__ mean, float* __restrict__ rstd) {
     constexpr int EPL = 16 / sizeof(T);            // elements per 16-byte load
     constexpr int RPW = 32 / G;                    // rows per warp
-    constexpr int MAXV = 4;                        // loads per lane: C <= G * EPL * MAXV
     const int lane = threadIdx.x & 31;
     const int sub = lane / G, gl = lane % G;
     const long long warp_global = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -326,7 +325,12 @@ cudaError_t launch_ln_stats(const T* x, long long rows, int C, float* mean, floa
         ln_stats_kernel<T, G><<<grid, wpb * 32, 0, stream>>>(x, rows, C, mean, rstd);
         return cudaGetLastError();
     };
-    if (chunks > 128) return cudaErrorInvalidValue;      // C <= 32 lanes * 4 loads * EPL
+    if (chunks > 256) return cudaErrorInvalidValue;      // C <= 32 lanes * 8 loads * EPL
+    if (chunks > 128) {                                   // fp32 rows of 516 ... 1024 channels (embed_dim 64: C = 1024 at the bottleneck)
+        const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+        ln_stats_kernel<T, 32, 8><<<grid, wpb * 32, 0, stream>>>(x, rows, C, mean, rstd);
+        return cudaGetLastError();
+    }
     if (chunks <= 4) return go(std::integral_constant<int, 4>{});
     if (chunks <= 8) return go(std::integral_constant<int, 8>{});
     if (chunks <= 16) return go(std::integral_constant<int, 16>{});

@@ -43,7 +43,7 @@ typedef struct CUevent_st*  lewin_event_t;  /* == cudaEvent_t  */
 
 /* error codes (negative) */
 #define LEWIN_E_NULL      (-1)  /* a required pointer is NULL */
-#define LEWIN_E_SHAPE     (-2)  /* unsupported dims (C % 32, head_dim = C / nH not in {32, 64, 128}, H/W % 8, ...) */
+#define LEWIN_E_SHAPE     (-2)  /* unsupported dims (C % 32, C > 1024, head_dim = C / nH not in {32, 64, 128}, H/W % 8, ...) */
 #define LEWIN_E_ALIGN     (-3)  /* a pointer is not 16-byte aligned */
 #define LEWIN_E_WORKSPACE (-4)  /* workspace too small */
 #define LEWIN_E_DTYPE     (-5)  /* unknown dtype tag */

@@ -85,6 +85,7 @@ int check_attn(const LewinAttnFwdArgs* a) {
     if (a->use_rpb && !a->rpb_table && !a->rpb_dense) return LEWIN_E_NULL;
     if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->nH <= 0) return LEWIN_E_SHAPE;
     if (a->H % 8 || a->W % 8 || a->C % 32 || !head_dim_ok(a->C, a->nH)) return LEWIN_E_SHAPE;
+    if (a->C > 1024) return LEWIN_E_SHAPE;        // the LayerNorm pre-passes handle rows of up to 1024 channels (embed_dim 64's bottleneck)
     if (a->shift < 0 || a->shift >= 8) return LEWIN_E_SHAPE;
     if (a->shift > 0 && ((a->H <= 8 && !a->band_mode) || a->W <= 8)) return LEWIN_E_SHAPE;   // My_model_1.py:764-766 forces shift 0
     if (a->band_mode && (a->windowed || a->save_for_backward || a->band_y0 < 0 || a->band_Hg < a->H || a->band_y0 % 8 || a->band_Hg % 8))
@@ -332,6 +333,7 @@ int check_leff(const LewinLeffFwdArgs* a) {
     if (a->save_for_backward && (!a->a1 || !a->a2)) return LEWIN_E_NULL;
     if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->hidden <= 0) return LEWIN_E_SHAPE;
     if (a->C % 32 || a->hidden % 32) return LEWIN_E_SHAPE;
+    if (a->C > 1024) return LEWIN_E_SHAPE;        // as in check_attn
     if (a->ld_out != 0 && (a->ld_out < a->C || a->ld_out % 8)) return LEWIN_E_SHAPE;
     const void* ps[] = {a->y, a->out, a->ln_w, a->ln_b, a->w1, a->b1, a->w_dw, a->b_dw, a->w2, a->b2, a->h1, a->h2, a->a1, a->a2,
                         a->w1_bf16, a->w2_bf16};
@@ -707,7 +709,7 @@ const char* lewin_error_string(int code) {
     switch (code) {
         case 0: return "ok";
         case LEWIN_E_NULL: return "required pointer is NULL";
-        case LEWIN_E_SHAPE: return "unsupported shape (need H,W % 8 == 0, C % 32 == 0, head_dim = C / nH in {32, 64, 128}, shift in {0..7})";
+        case LEWIN_E_SHAPE: return "unsupported shape (need H,W % 8 == 0, C % 32 == 0, C <= 1024, head_dim = C / nH in {32, 64, 128}, shift in {0..7})";
         case LEWIN_E_ALIGN: return "pointer not 16-byte aligned";
         case LEWIN_E_WORKSPACE: return "workspace missing or too small";
         case LEWIN_E_DTYPE: return "unknown dtype";

@@ -213,9 +213,11 @@ class Uformer(nn.Module):
                 "lewin_b200.Uformer implements the configuration the reference instantiates (utils/model_utils.py:94: "
                 f"token_projection='linear', token_mlp='leff'); got token_projection={token_projection!r}, token_mlp={token_mlp!r} "
                 "(the constructor keeps the reference's default token_mlp='ffn' in its signature, so pass token_mlp='leff')")
-        if embed_dim not in (32, 64, 128):
-            raise NotImplementedError(f"lewin_b200.Uformer: embed_dim {embed_dim} gives head_dim {embed_dim} (My_model_1.py:962); "
-                                      "32, 64 and 128 are built")
+        if embed_dim not in (32, 64):
+            raise NotImplementedError(
+                f"lewin_b200.Uformer: embed_dim {embed_dim} is not built.  head_dim = embed_dim (My_model_1.py:962) must be 32, 64 or "
+                "128 and the widest level (16 x embed_dim channels at the bottleneck) at most 1024 channels, so whole models exist "
+                "for embed_dim 32 and 64; head_dim 128 is available at block level (LeWinTransformerBlock with dim <= 1024)")
         self.num_enc_layers = len(depths) // 2
         self.num_dec_layers = len(depths) // 2
         self.embed_dim, self.patch_norm, self.mlp_ratio = embed_dim, patch_norm, mlp_ratio

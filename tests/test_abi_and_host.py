@@ -269,3 +269,18 @@ def test_tile_glue_indices_equal_the_slicing_functions(H, W, world):
         _, out_idx, _, _, _ = fullres.tile_glue_indices(H, W, C, ps, r, world, img.device)
         got = gathered.reshape(-1).index_select(0, out_idx).view(1, C, H, W)
         assert torch.equal(got, fullres.from_tiles(fake_out, L, ps)[:, :, :H, :W])
+
+
+def test_uformer_constructor_states_what_is_built():
+    """Whole models exist for embed_dim 32 and 64 (head_dim = embed_dim, My_model_1.py:962; the widest level has 16 x embed_dim
+    channels and the kernels take rows of up to 1024); anything else is refused at construction with the reason, instead of
+    failing inside a forward (embed_dim 16 used to fail at the first launch with LEWIN_E_SHAPE)."""
+    import lewin_b200 as L
+    for ed in (32, 64):
+        m = L.Uformer(img_size=128, embed_dim=ed, win_size=8, token_projection="linear", token_mlp="leff")
+        assert m.embed_dim == ed
+    for ed in (16, 128):
+        with pytest.raises(NotImplementedError, match="embed_dim"):
+            L.Uformer(img_size=128, embed_dim=ed, win_size=8, token_projection="linear", token_mlp="leff")
+    with pytest.raises(NotImplementedError, match="token_mlp"):
+        L.Uformer(img_size=128, embed_dim=32)                      # the reference signature's default token_mlp='ffn'

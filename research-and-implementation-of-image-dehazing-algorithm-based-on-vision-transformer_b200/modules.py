@@ -209,7 +209,7 @@ class WindowAttention(nn.Module):
         head_dim = dim // num_heads
         if dim % num_heads or head_dim not in (32, 64, 128):
             raise NotImplementedError(f"lewin_b200: head_dim = dim // num_heads = {dim}/{num_heads} is not built; 32, 64 and "
-                                      "128 are (embed_dim 32 / 64 / 128 of My_model_1.py:962; the reference's embed_dim=16 "
+                                      "128 are (head_dim = embed_dim, My_model_1.py:962; the reference's embed_dim=16 "
                                       "variant, utils/model_utils.py:97, is not)")
         self.scale = qk_scale or head_dim ** -0.5
         self.ProbSpare = AttentionLayer(self.dim, self.num_heads)
